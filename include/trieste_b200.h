@@ -1,0 +1,138 @@
+/*
+ * trieste_b200 — C-ABI of the B200-native GP-posterior + acquisition engine.
+ *
+ * This is the drop-in boundary for the hot path named by BASELINE.json `north_star`
+ * (SURVEY.md §8b).  The reference has no FFI: its boundary is a set of Python structural
+ * protocols.  Each entry point below cites the reference interface it stands behind
+ * (paths relative to /root/reference/).  The Python host layer (`trieste_b200/`) binds these
+ * with ctypes and mirrors the reference's class/method names on top; INTEGRATION.md shows the
+ * binding a trieste maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; tb_last_error() returns the
+ *     thread-local message (the Python layer raises ValueError / RuntimeError from it);
+ *     nothing aborts the process (the BO loop records exceptions, bayesian_optimizer.py:855-875).
+ *   - plain pointers + sizes only.  Every array pointer may be a HOST pointer or a DEVICE pointer
+ *     on the handle's GPU (detected with cudaPointerGetAttributes); host buffers are staged
+ *     through the handle's stream inside the call.
+ *   - row-major, dense; fp64 unless the handle was created with TB_F32.
+ *   - one caller per handle, one CUDA stream per handle, synchronous return
+ *     (results are immediately `.numpy()`-ed by the reference, optimizer.py:665-666).
+ */
+#ifndef TRIESTE_B200_H
+#define TRIESTE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tb_gp tb_gp;   /* exact-GPR posterior: owns device copies of X, Linv, alpha, hyper-params */
+typedef struct tb_rff tb_rff; /* random-Fourier-feature trajectory: owns W, b, theta */
+
+enum tb_dtype { TB_F64 = 0, TB_F32 = 1 };
+/* gpflow.kernels.{SquaredExponential,Matern12,Matern32,Matern52}; trieste default Matern52
+ * (models/gpflow/builders.py:399) */
+enum tb_kernel { TB_RBF = 0, TB_MATERN12 = 1, TB_MATERN32 = 2, TB_MATERN52 = 3 };
+enum tb_acq {
+  TB_ACQ_EI = 0,      /* expected_improvement.__call__, acquisition/function/function.py:215-223 */
+  TB_ACQ_LOG_EI = 1,  /* log of the above; ABSENT in the reference */
+  TB_ACQ_NEG_LCB = 2, /* NegativeLowerConfidenceBound, function.py:358-359 (−lower_confidence_bound :415-416) */
+  TB_ACQ_LCB = 3      /* lower_confidence_bound, function.py:389-418 */
+};
+
+/* ---- errors / build info ------------------------------------------------------------------ */
+const char* tb_last_error(void);
+const char* tb_version(void);
+int tb_device_count(int* count);
+
+/* ---- model handle ----------------------------------------------------------------------------
+ * mirrors GaussianProcessRegression (models/gpflow/models.py:69-186) + GPflowPredictor's posterior
+ * cache (models/gpflow/interface.py:89-112). */
+int tb_gp_create(tb_gp** out, int device, int dtype);
+int tb_gp_destroy(tb_gp* gp);
+
+/* GPR data Variables assign, models.py:171-186 (update_encoded).  X [N,D], y [N] (E = 1). */
+int tb_gp_set_data(tb_gp* gp, const void* X, const void* y, int64_t N, int D);
+
+/* kernel / likelihood / mean-function hyper-parameters (gpflow Parameters read through
+ * get_kernel / get_observation_noise / get_mean_function, models/interfaces.py:166-225).
+ * lengthscales: n_ls = 1 (isotropic) or D (ARD), always double. */
+int tb_gp_set_hyper(tb_gp* gp, int kernel, double variance, const double* lengthscales, int n_ls,
+                    double noise_variance, double mean_const);
+
+/* update_posterior_cache (interface.py:108-112): err = y − m(X), L = chol(K(X,X) + σ²I) (cuSOLVER,
+ * once per BO step, off the per-candidate path), then Linv and alpha = K⁻¹err packed for the kernels. */
+int tb_gp_update_posterior_cache(tb_gp* gp);
+
+/* copy out the cached Cholesky factor L [N,N] row-major lower (tests / diagnostics). */
+int tb_gp_get_cholesky(tb_gp* gp, void* L_out);
+
+/* predict_encoded (interface.py:119-124): Xc [M,D] → mean [M], var [M] (clipped to ≥ 1e-12). */
+int tb_gp_predict(tb_gp* gp, const void* Xc, int64_t M, void* mean, void* var);
+
+/* predict_joint_encoded (interface.py:126-133): Xc [B,q,D] → mean [B,q], cov [B,q,q]
+ * (diagonal clipped to ≥ 1e-12). */
+int tb_gp_predict_joint(tb_gp* gp, const void* Xc, int64_t B, int q, void* mean, void* cov);
+
+/* ---- fused predict + acquisition tail --------------------------------------------------------
+ * acq: tb_acq; param = eta (EI / log-EI) or beta (LCB).  Xc [M,D] → out [M].
+ * grad (nullable): [M,D] = d out / d Xc (what tfp.math.value_and_gradient returns at
+ * acquisition/optimizer.py:621-629). */
+int tb_acq_eval(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* grad);
+
+/* generate_random_search_optimizer / _get_max_discrete_points (optimizer.py:124-150, 973-1011):
+ * fused evaluation + first-max argmax.  best_value (1 scalar of the handle dtype, host),
+ * best_index (host).  out may be NULL (values are then never written to HBM). */
+int tb_acq_argmax(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out,
+                  void* best_value, int64_t* best_index);
+
+/* batch_monte_carlo_expected_improvement.__call__ (function.py:1181-1186) on top of
+ * BatchReparametrizationSampler.sample (models/gpflow/sampler.py:208-287):
+ * Xc [B,q,D], eps [q,S] (the sampler's fixed base samples, injected) → out [B]. */
+int tb_acq_batch_mc_ei(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S,
+                       double eta, double jitter, void* out);
+
+/* BatchReparametrizationSampler.sample (sampler.py:208-287): → samples [B,S,q]. */
+int tb_gp_reparam_sample(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S,
+                         double jitter, void* samples);
+
+/* ---- streaming reductions over candidate scores ----------------------------------------------
+ * tf.math.top_k as used by generate_initial_points (optimizer.py:321-335): values [M] →
+ * top values [k] (descending, ties → lower index), indices [k].  Host or device pointers. */
+int tb_topk(int device, int dtype, const void* values, int64_t M, int k, void* top_values,
+            int64_t* top_indices);
+
+/* ---- random-Fourier-feature trajectories -----------------------------------------------------
+ * feature_decomposition_trajectory.__call__ (models/gpflow/sampler.py:901-936) with
+ * ResampleableRandomFourierFeatureFunctions (:741-806): always fp64 (sampler.py:782). */
+int tb_rff_create(tb_rff** out, int device);
+int tb_rff_destroy(tb_rff* r);
+/* W [F,D], b [F], lengthscales [D], theta [nb,F] (nb trajectories = batch size B). */
+int tb_rff_set(tb_rff* r, const double* W, const double* b, int F, int D, const double* lengthscales,
+               double variance, double mean_const);
+int tb_rff_set_theta(tb_rff* r, const double* theta, int nb);
+/* Xc [M,D] evaluated under all nb trajectories → out [M,nb]; ThompsonSamplerFromTrajectory
+ * (acquisition/sampler.py:262-271): argmin per trajectory → min_value [nb], min_index [nb]
+ * (either may be NULL). */
+int tb_rff_eval(tb_rff* r, const void* Xc, int64_t M, void* out, double* min_value,
+                int64_t* min_index);
+
+/* ---- instrumentation (bench / tests) ---------------------------------------------------------
+ * kernels launched by this library in this process since the last reset; device time (ms) of the
+ * dominant kernel (triangular DMMA GEMM) accumulated with CUDA events on the handle's stream when
+ * profiling is enabled. */
+int64_t tb_launch_count(void);
+void tb_launch_count_reset(void);
+int tb_gp_profile(tb_gp* gp, int enable);
+/* the handle's CUDA stream (cudaStream_t as void*), so callers can record CUDA events on the stream the
+ * kernels are launched on (torch.cuda.ExternalStream in bench.py). */
+int tb_gp_stream(tb_gp* gp, void** stream);
+int tb_gp_profile_read(tb_gp* gp, double* trigemm_ms, int64_t* trigemm_launches, double* flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIESTE_B200_H */

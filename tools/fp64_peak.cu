@@ -1,0 +1,58 @@
+// Micro-benchmark: peak fp64 rate of DMMA (mma.m8n8k4.f64) vs DFMA on this GPU.  Denominator sanity
+// for the roofline of the triangular GEMM (bench.py uses a cuBLAS DGEMM probe as the official peak).
+#include <cstdio>
+#include <cuda_runtime.h>
+__global__ void dmma_loop(double* out, int iters, int nacc_dummy) {
+  double c[16][2];
+  for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+  double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-4;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0; for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void dfma_loop(double* out, int iters) {
+  double c[16];
+  for (int i = 0; i < 16; ++i) c[i] = i;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+  }
+  double s = 0; for (int i = 0; i < 16; ++i) s += c[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  int sms = p.multiProcessorCount;
+  double* out; cudaMalloc(&out, sizeof(double) * sms * 8 * 1024);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int warps : {4, 8, 16, 32}) {
+    int iters = 20000;
+    for (int rep = 0; rep < 2; ++rep) {
+      cudaEventRecord(e0);
+      dmma_loop<<<sms, warps * 32>>>(out, iters, 0);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+    }
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double flops = 2.0 * 256 * 16 * (double)iters * warps * sms;
+    printf("DMMA warps/SM=%2d  %.2f TFLOP/s  (%.3f ms)\n", warps, flops / ms * 1e-9, ms);
+  }
+  for (int warps : {8, 16, 32}) {
+    int iters = 20000;
+    for (int rep = 0; rep < 2; ++rep) {
+      cudaEventRecord(e0);
+      dfma_loop<<<sms, warps * 32>>>(out, iters);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+    }
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double flops = 2.0 * 32 * 16 * (double)iters * warps * sms;
+    printf("DFMA warps/SM=%2d  %.2f TFLOP/s  (%.3f ms)\n", warps, flops / ms * 1e-9, ms);
+  }
+  printf("SMs=%d clock=%d kHz\n", sms, p.clockRate);
+  return 0;
+}

@@ -1,0 +1,243 @@
+"""Analytic and Monte-Carlo single-objective acquisition functions of the hot path — mirrors
+trieste/acquisition/function/function.py (EI :96-223, LCB :328-418, batch MC-EI :1074-1186).
+
+Each callable keeps the reference's shape contract (``x: [..., 1, D] -> [..., 1]``; batch
+functions ``[..., B, D] -> [..., 1]``) but evaluates predict + tail in ONE pass of fused GPU
+kernels behind the C-ABI instead of ``model.predict`` followed by separate elementwise ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from .. import _lib
+from ..data import Dataset
+from ..models import GaussianProcessRegression, _flatten_leading, _ptr
+from .interface import AcquisitionFunctionClass, SingleModelAcquisitionBuilder
+
+JITTER = 1e-6  # trieste/utils/misc.py:183
+
+
+def _check_populated(dataset: Optional[Dataset]) -> Dataset:
+    if dataset is None:
+        raise ValueError("Dataset must be populated.")
+    if len(dataset) == 0:
+        raise ValueError("Dataset must be populated.")
+    return dataset
+
+
+def _require_native(model) -> GaussianProcessRegression:
+    if not isinstance(model, GaussianProcessRegression):
+        raise ValueError(
+            f"trieste_b200 acquisition functions need a trieste_b200.GaussianProcessRegression model; received {model!r}"
+        )
+    return model
+
+
+class _FusedSingleQuery(AcquisitionFunctionClass):
+    """Common machinery: squeeze the B=1 axis, run the fused kernel chain, restore shapes."""
+
+    _acq: int = -1
+
+    def __init__(self, model: GaussianProcessRegression, param: float):
+        self._model = _require_native(model)
+        self._param = float(param)
+
+    def _squeeze(self, x):
+        x, _ = _lib.as_f64_contiguous(x)
+        if x.ndim < 2 or x.shape[-2] != 1:
+            raise ValueError(
+                f"This acquisition function only supports batch sizes of one; got input of shape {tuple(x.shape)}"
+            )
+        self._model._check_dim(x)
+        return _flatten_leading(x.reshape(tuple(x.shape[:-2]) + (x.shape[-1],)), 1)
+
+    def __call__(self, x):
+        flat, lead = self._squeeze(x)
+        M = flat.shape[0]
+        out, po = _lib.empty_like_kind(flat, (M, 1))
+        _lib.check(_lib.lib().tb_acq_eval(self._model.handle, self._acq, self._param, _ptr(flat), M, po, None))
+        return out.reshape(lead + (1,))
+
+    def value_and_gradient(self, x):
+        """``tfp.math.value_and_gradient(fn, x)`` as used at acquisition/optimizer.py:621-629:
+        returns (values [..., 1], d values / d x [..., 1, D])."""
+        flat, lead = self._squeeze(x)
+        M, D = flat.shape
+        out, po = _lib.empty_like_kind(flat, (M, 1))
+        grad, pg = _lib.empty_like_kind(flat, (M, D))
+        _lib.check(_lib.lib().tb_acq_eval(self._model.handle, self._acq, self._param, _ptr(flat), M, po, pg))
+        return out.reshape(lead + (1,)), grad.reshape(lead + (1, D))
+
+    def fused_argmax(self, points):
+        """points [M, D] -> (first-max index, value) without writing the M values to HBM
+        (generate_random_search_optimizer / _get_max_discrete_points, optimizer.py:124-150)."""
+        pts, _ = _lib.as_f64_contiguous(points)
+        if pts.ndim != 2:
+            raise ValueError(f"points must be [M, D], got {tuple(pts.shape)}")
+        self._model._check_dim(pts)
+        best = C.c_double()
+        idx = C.c_int64()
+        _lib.check(
+            _lib.lib().tb_acq_argmax(
+                self._model.handle, self._acq, self._param, _ptr(pts), pts.shape[0], None, C.byref(best), C.byref(idx)
+            )
+        )
+        return int(idx.value), float(best.value)
+
+
+class expected_improvement(_FusedSingleQuery):
+    """function.py:190-223: ``(eta - mean) * cdf(eta) + variance * pdf(eta)``."""
+
+    _acq = _lib.ACQ_EI
+
+    def __init__(self, model, eta):
+        super().__init__(model, float(np.asarray(eta).reshape(-1)[0]))
+
+    def update(self, eta) -> None:
+        self._param = float(np.asarray(eta).reshape(-1)[0])
+
+    @property
+    def eta(self) -> float:
+        return self._param
+
+
+class log_expected_improvement(expected_improvement):
+    """log of :class:`expected_improvement`.  ABSENT in the reference at this commit;
+    defined here (numerically stable for z << 0); parity unpinned."""
+
+    _acq = _lib.ACQ_LOG_EI
+
+
+class _lcb(_FusedSingleQuery):
+    def __init__(self, model, beta: float, negate: bool):
+        if beta < 0:
+            raise ValueError("Standard deviation scaling parameter beta must not be negative")
+        super().__init__(model, beta)
+        self._acq = _lib.ACQ_NEG_LCB if negate else _lib.ACQ_LCB
+
+
+def lower_confidence_bound(model, beta: float):
+    """function.py:389-418: ``mean - beta * sqrt(variance)``."""
+    return _lcb(model, beta, negate=False)
+
+
+def _eta_from_model(model, dataset: Dataset, search_space=None) -> float:
+    """function.py:133-149: eta = min over the (feasible) training inputs of the posterior mean."""
+    mean, _ = model.predict(np.asarray(dataset.query_points, dtype=np.float64))
+    return float(np.min(mean, axis=0)[0])
+
+
+class ExpectedImprovement(SingleModelAcquisitionBuilder):
+    """function.py:96-187."""
+
+    _fn_class = expected_improvement
+
+    def __init__(self, search_space=None):
+        self._search_space = search_space
+
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}({self._search_space!r})"
+
+    def prepare_acquisition_function(self, model, dataset: Optional[Dataset] = None):
+        dataset = _check_populated(dataset)
+        return self._fn_class(model, _eta_from_model(model, dataset, self._search_space))
+
+    def update_acquisition_function(self, function, model, dataset: Optional[Dataset] = None):
+        dataset = _check_populated(dataset)
+        if not isinstance(function, self._fn_class):
+            raise ValueError(f"expected a {self._fn_class.__name__} function, got {function!r}")
+        function.update(_eta_from_model(model, dataset, self._search_space))  # same object: no re-build
+        return function
+
+
+class LogExpectedImprovement(ExpectedImprovement):
+    _fn_class = log_expected_improvement
+
+
+class NegativeLowerConfidenceBound(SingleModelAcquisitionBuilder):
+    """function.py:328-372: negated LCB so that maximisation minimises the bound."""
+
+    def __init__(self, beta: float = 1.96):
+        if beta < 0:
+            raise ValueError(f"Confidence parameter's standard deviation scaling must not be negative, got {beta}")
+        self._beta = beta
+
+    def __repr__(self) -> str:
+        return f"NegativeLowerConfidenceBound({self._beta!r})"
+
+    def prepare_acquisition_function(self, model, dataset: Optional[Dataset] = None):
+        return _lcb(model, self._beta, negate=True)
+
+    def update_acquisition_function(self, function, model, dataset: Optional[Dataset] = None):
+        return function  # no dependence on data (function.py:361-372)
+
+
+class batch_monte_carlo_expected_improvement(AcquisitionFunctionClass):
+    """function.py:1150-1186: mean over S reparametrised joint samples of
+    ``max(eta - min_q sample, 0)``."""
+
+    def __init__(self, sample_size: int, model, eta, jitter: float):
+        if not hasattr(model, "reparam_sampler"):
+            raise ValueError(
+                "The batch Monte-Carlo expected improvement acquisition function only supports models that "
+                f"implement a reparam_sampler method; received {model!r}"
+            )
+        self._sample_size = sample_size
+        self._model = _require_native(model)
+        self._sampler = model.reparam_sampler(sample_size)
+        self._eta = float(np.asarray(eta).reshape(-1)[0])
+        self._jitter = jitter
+
+    def update(self, eta) -> None:
+        self._eta = float(np.asarray(eta).reshape(-1)[0])
+        self._sampler.reset_sampler()
+
+    def __call__(self, x):
+        x, _ = _lib.as_f64_contiguous(x)
+        if x.ndim < 2:
+            raise ValueError(f"expected [..., B, D] query batches, got shape {tuple(x.shape)}")
+        self._model._check_dim(x)
+        flat, lead = _flatten_leading(x, 2)
+        nb, q = flat.shape[0], flat.shape[1]
+        eps = self._sampler._get_eps(q)  # [q, S] float64 host, fixed until reset
+        out, po = _lib.empty_like_kind(flat, (nb, 1))
+        _lib.check(
+            _lib.lib().tb_acq_batch_mc_ei(
+                self._model.handle, _ptr(flat), nb, q, eps.ctypes.data, eps.shape[1], self._eta, self._jitter, po
+            )
+        )
+        return out.reshape(lead + (1,))
+
+
+class BatchMonteCarloExpectedImprovement(SingleModelAcquisitionBuilder):
+    """function.py:1074-1147."""
+
+    def __init__(self, sample_size: int, *, jitter: float = JITTER):
+        if sample_size <= 0:
+            raise ValueError(f"sample_size must be positive, got {sample_size}")
+        if jitter < 0:
+            raise ValueError(f"jitter must be non-negative, got {jitter}")
+        self._sample_size = sample_size
+        self._jitter = jitter
+
+    def __repr__(self) -> str:
+        return f"BatchMonteCarloExpectedImprovement({self._sample_size!r}, jitter={self._jitter!r})"
+
+    def prepare_acquisition_function(self, model, dataset: Optional[Dataset] = None):
+        dataset = _check_populated(dataset)
+        mean, _ = model.predict(np.asarray(dataset.query_points, dtype=np.float64))
+        if mean.shape[-1] != 1:
+            raise ValueError("Expected model with event shape [1].")
+        eta = np.min(mean, axis=0)
+        return batch_monte_carlo_expected_improvement(self._sample_size, model, eta, self._jitter)
+
+    def update_acquisition_function(self, function, model, dataset: Optional[Dataset] = None):
+        dataset = _check_populated(dataset)
+        if not isinstance(function, batch_monte_carlo_expected_improvement):
+            raise ValueError(f"expected a batch_monte_carlo_expected_improvement, got {function!r}")
+        mean, _ = model.predict(np.asarray(dataset.query_points, dtype=np.float64))
+        function.update(np.min(mean, axis=0))
+        return function

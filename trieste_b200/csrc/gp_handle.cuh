@@ -1,0 +1,91 @@
+// The model handle: device-resident posterior cache + scratch, and its once-per-step precompute.
+#pragma once
+#include "kernels_f64.cuh"
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+
+namespace tb {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    TB_CUDA(cudaMalloc(&p, bytes));
+    cap = bytes;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+inline bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// supported padded input dimensions of the distance loop (even, so rows load as double2)
+inline int pick_dp(int D) {
+  static const int opts[] = {2, 4, 6, 8, 10, 12, 16, 20, 24, 32};
+  for (int o : opts)
+    if (D <= o) return o;
+  return -1;
+}
+
+}  // namespace tb
+
+struct tb_gp {
+  int device = 0;
+  int dtype = TB_F64;
+  cudaStream_t stream = nullptr;
+  cublasHandle_t cublas = nullptr;
+  cusolverDnHandle_t cusolver = nullptr;
+
+  // model (host copies of the small things)
+  int64_t N = 0;
+  int D = 0, DP = 0;
+  int kernel = TB_MATERN52;
+  double variance = 1.0, noise = 1.0, mean_const = 0.0;
+  std::vector<double> ls;  // [D]
+  bool have_data = false, have_hyper = false, cache_valid = false;
+
+  // geometry of the packed cache
+  int nkc = 0;  // k panels = ceil(N/16)
+  int NB = 0;   // row-blocks = ceil(N/128)
+
+  tb::DevBuf dX, dy;            // raw data [N,D], [N]
+  tb::DevBuf dXs;               // [nkc*16][DP] scaled, zero padded
+  tb::DevBuf dInvLs;            // [DP]
+  tb::DevBuf dAlpha;            // [nkc*16]
+  tb::DevBuf dL;                // [N,N] column-major lower Cholesky factor
+  tb::DevBuf dLinv;             // [N,N] column-major Linv (kept: predict_joint / gradients reuse it)
+  tb::DevBuf dLinvP;            // packed lower panels
+  tb::DevBuf dWork, dInfo;      // cusolver workspace
+
+  // per-call scratch
+  tb::DevBuf sKs, sPartial, sMean, sVals, sVar, sXc, sBlkBest, sBlkIdx, sRun;
+  tb::DevBuf sA, sV, sGrad, sMisc;  // A / V panels (joint + gradient paths), misc staging
+
+  // profiling of the dominant kernel
+  bool profile = false;
+  double prof_ms = 0.0, prof_flops = 0.0;
+  int64_t prof_launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  std::vector<double> prof_event_flops;
+};

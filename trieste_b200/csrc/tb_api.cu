@@ -1,0 +1,562 @@
+// C-ABI entry points (include/trieste_b200.h).  Host orchestration only: every per-candidate flop
+// runs in the kernels of kernels_f64.cuh / kernels_extra.cuh.
+#include "gp_handle.cuh"
+#include "kernels_extra.cuh"
+
+using namespace tb;
+
+// =================================================================================================
+// once-per-step precompute kernels (posterior cache)
+// =================================================================================================
+namespace tb {
+
+// Xs[k][d] = X[k][d] / l_d, zero padded to [nkc*16][DP]
+__global__ void scale_inputs_kernel(const double* __restrict__ X, const double* __restrict__ inv_ls,
+                                    int64_t N, int D, int DP, int64_t rows, double* __restrict__ Xs) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * DP) return;
+  int64_t k = i / DP;
+  int d = (int)(i % DP);
+  Xs[i] = (k < N && d < D) ? X[k * D + d] * inv_ls[d] : 0.0;
+}
+
+// K(X,X) + noise I, full symmetric, column-major [N,N]
+template <int KIND>
+__global__ void gram_kernel(const double* __restrict__ Xs, int64_t N, int DP, double variance,
+                            double noise, double* __restrict__ K) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t j = blockIdx.y;
+  if (i >= N) return;
+  double r2 = 0.0;
+  for (int d = 0; d < DP; ++d) {
+    double df = Xs[i * DP + d] - Xs[j * DP + d];
+    r2 = fma(df, df, r2);
+  }
+  double v = kernel_from_r2<KIND>(r2, variance);
+  if (i == j) v = variance + noise;
+  K[i + j * N] = v;
+}
+
+__global__ void identity_kernel(int64_t N, double* __restrict__ A) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * N) return;
+  A[i] = (i % N == i / N) ? 1.0 : 0.0;
+}
+
+__global__ void zero_upper_kernel(int64_t N, double* __restrict__ A) {  // column-major: zero i < j
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t j = blockIdx.y;
+  if (i < N && i < j) A[i + j * N] = 0.0;
+}
+
+__global__ void residual_kernel(const double* __restrict__ y, int64_t N, int64_t rows, double mean_const,
+                                double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) out[i] = (i < N) ? y[i] - mean_const : 0.0;
+}
+
+// one CTA per (row-block I, k-panel kc) of the lower triangle: Linv (column-major) -> packed panel
+__global__ void pack_lower_panels_kernel(const double* __restrict__ Linv, int64_t N, int nkc,
+                                         double* __restrict__ P) {
+  const int I = blockIdx.y, kc = blockIdx.x;
+  const int nk = min((I + 1) * (BM / BK), nkc);
+  if (kc >= nk) return;
+  double* dst = P + (rowblock_panel_offset(I) + kc) * PANEL;
+  for (int e = threadIdx.x; e < PANEL; e += blockDim.x) {
+    // iterate in source-friendly order: r fastest (column-major source), scatter into the panel
+    int r = e % BM, k = e / BM;
+    int64_t n = (int64_t)I * BM + r, kk = (int64_t)kc * BK + k;
+    double v = (n < N && kk <= n) ? Linv[n + kk * N] : 0.0;
+    dst[panel_elem_index(r, k)] = v;
+  }
+}
+
+// column-major lower factor -> row-major dense (upper zeroed), for tb_gp_get_cholesky
+__global__ void colmajor_lower_to_rowmajor_kernel(const double* __restrict__ A, int64_t N,
+                                                  double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t j = blockIdx.y;
+  if (i < N) out[i * N + j] = (j <= i) ? A[i + j * N] : 0.0;
+}
+
+}  // namespace tb
+
+#define TB_CUSOLVER(expr)                                                                          \
+  do {                                                                                             \
+    cusolverStatus_t _s = (expr);                                                                  \
+    if (_s != CUSOLVER_STATUS_SUCCESS) return tb::fail(std::string(#expr) + ": cusolver status " + \
+                                                       std::to_string((int)_s));                   \
+  } while (0)
+#define TB_CUBLAS(expr)                                                                        \
+  do {                                                                                         \
+    cublasStatus_t _s = (expr);                                                                \
+    if (_s != CUBLAS_STATUS_SUCCESS) return tb::fail(std::string(#expr) + ": cublas status " + \
+                                                     std::to_string((int)_s));                 \
+  } while (0)
+
+static const char* kVersion = "trieste_b200 0.1 (sm_100a; fp64 DMMA triangular GEMM)";
+
+extern "C" {
+
+const char* tb_last_error(void) { return tb::last_error().c_str(); }
+const char* tb_version(void) { return kVersion; }
+int tb_device_count(int* count) {
+  TB_CHECK(count != nullptr, "tb_device_count: null output");
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    cudaGetLastError();
+    return tb::fail(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+int64_t tb_launch_count(void) { return tb::launch_counter().load(); }
+void tb_launch_count_reset(void) { tb::launch_counter().store(0); }
+
+int tb_gp_create(tb_gp** out, int device, int dtype) {
+  TB_CHECK(out != nullptr, "tb_gp_create: null output");
+  TB_CHECK(dtype == TB_F64, "tb_gp_create: only TB_F64 is implemented in this build");
+  int n = 0;
+  TB_TRY(tb_device_count(&n));
+  TB_CHECK(n > 0, "tb_gp_create: no CUDA device visible (this library has no CPU fallback)");
+  TB_CHECK(device >= 0 && device < n, "tb_gp_create: device index out of range");
+  TB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TB_CUDA(cudaGetDeviceProperties(&prop, device));
+  TB_CHECK(prop.major == 10, "tb_gp_create: this library is built for sm_100a (B200) only; found sm_" +
+                                 std::to_string(prop.major) + std::to_string(prop.minor));
+  tb_gp* gp = new tb_gp();
+  gp->device = device;
+  gp->dtype = dtype;
+  TB_CUDA(cudaStreamCreateWithFlags(&gp->stream, cudaStreamNonBlocking));
+  TB_CUBLAS(cublasCreate(&gp->cublas));
+  TB_CUBLAS(cublasSetStream(gp->cublas, gp->stream));
+  TB_CUSOLVER(cusolverDnCreate(&gp->cusolver));
+  TB_CUSOLVER(cusolverDnSetStream(gp->cusolver, gp->stream));
+  TB_CUDA(cudaFuncSetAttribute(trigemm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)TG_SMEM));
+  TB_TRY(tb::extra_kernels_init());
+  *out = gp;
+  return 0;
+}
+
+int tb_gp_destroy(tb_gp* gp) {
+  if (!gp) return 0;
+  cudaSetDevice(gp->device);
+  cudaStreamSynchronize(gp->stream);
+  for (tb::DevBuf* b : {&gp->dX, &gp->dy, &gp->dXs, &gp->dInvLs, &gp->dAlpha, &gp->dL, &gp->dLinv,
+                        &gp->dLinvP, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
+                        &gp->sVals, &gp->sVar, &gp->sXc, &gp->sBlkBest, &gp->sBlkIdx, &gp->sRun,
+                        &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc})
+    b->release();
+  for (auto& ev : gp->prof_events) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  if (gp->cusolver) cusolverDnDestroy(gp->cusolver);
+  if (gp->cublas) cublasDestroy(gp->cublas);
+  if (gp->stream) cudaStreamDestroy(gp->stream);
+  delete gp;
+  return 0;
+}
+
+int tb_gp_set_data(tb_gp* gp, const void* X, const void* y, int64_t N, int D) {
+  TB_CHECK(gp && X && y, "tb_gp_set_data: null argument");
+  TB_CHECK(N > 0, "tb_gp_set_data: dataset must be populated (N > 0)");
+  TB_CHECK(D > 0 && tb::pick_dp(D) > 0, "tb_gp_set_data: input dimension must be in [1, 32]");
+  TB_CHECK(N <= 65536, "tb_gp_set_data: N > 65536 is not supported");
+  TB_CUDA(cudaSetDevice(gp->device));
+  gp->N = N;
+  gp->D = D;
+  gp->DP = tb::pick_dp(D);
+  gp->nkc = (int)((N + BK - 1) / BK);
+  gp->NB = (int)((N + BM - 1) / BM);
+  TB_TRY(gp->dX.reserve(sizeof(double) * N * D));
+  TB_TRY(gp->dy.reserve(sizeof(double) * N));
+  TB_CUDA(cudaMemcpyAsync(gp->dX.p, X, sizeof(double) * N * D, cudaMemcpyDefault, gp->stream));
+  TB_CUDA(cudaMemcpyAsync(gp->dy.p, y, sizeof(double) * N, cudaMemcpyDefault, gp->stream));
+  TB_CUDA(cudaStreamSynchronize(gp->stream));
+  gp->have_data = true;
+  gp->cache_valid = false;
+  if ((int)gp->ls.size() != D && gp->ls.size() == 1) gp->ls.assign(D, gp->ls[0]);
+  return 0;
+}
+
+int tb_gp_set_hyper(tb_gp* gp, int kernel, double variance, const double* lengthscales, int n_ls,
+                    double noise_variance, double mean_const) {
+  TB_CHECK(gp && lengthscales, "tb_gp_set_hyper: null argument");
+  TB_CHECK(kernel >= TB_RBF && kernel <= TB_MATERN52, "tb_gp_set_hyper: unknown kernel kind");
+  TB_CHECK(variance > 0.0, "tb_gp_set_hyper: kernel variance must be positive");
+  TB_CHECK(noise_variance > 0.0, "tb_gp_set_hyper: likelihood variance must be positive");
+  TB_CHECK(n_ls >= 1, "tb_gp_set_hyper: need at least one lengthscale");
+  for (int i = 0; i < n_ls; ++i)
+    TB_CHECK(lengthscales[i] > 0.0, "tb_gp_set_hyper: lengthscales must be positive");
+  TB_CHECK(!gp->have_data || n_ls == 1 || n_ls == gp->D,
+           "tb_gp_set_hyper: lengthscales must have 1 or D entries");
+  gp->kernel = kernel;
+  gp->variance = variance;
+  gp->noise = noise_variance;
+  gp->mean_const = mean_const;
+  gp->ls.assign(lengthscales, lengthscales + n_ls);
+  if (gp->have_data && n_ls == 1) gp->ls.assign(gp->D, lengthscales[0]);
+  gp->have_hyper = true;
+  gp->cache_valid = false;
+  return 0;
+}
+
+int tb_gp_update_posterior_cache(tb_gp* gp) {
+  TB_CHECK(gp, "tb_gp_update_posterior_cache: null handle");
+  TB_CHECK(gp->have_data && gp->have_hyper, "tb_gp_update_posterior_cache: set data and hyper-parameters first");
+  TB_CHECK((int)gp->ls.size() == gp->D, "tb_gp_update_posterior_cache: lengthscales must have 1 or D entries");
+  TB_CUDA(cudaSetDevice(gp->device));
+  const int64_t N = gp->N;
+  const int D = gp->D, DP = gp->DP;
+  const int64_t rows = (int64_t)gp->nkc * BK;
+  cudaStream_t st = gp->stream;
+
+  std::vector<double> inv_ls(DP, 0.0);
+  for (int d = 0; d < D; ++d) inv_ls[d] = 1.0 / gp->ls[d];
+  TB_TRY(gp->dInvLs.reserve(sizeof(double) * DP));
+  TB_CUDA(cudaMemcpyAsync(gp->dInvLs.p, inv_ls.data(), sizeof(double) * DP, cudaMemcpyHostToDevice, st));
+  TB_TRY(gp->dXs.reserve(sizeof(double) * rows * DP));
+  {
+    int64_t tot = rows * DP;
+    scale_inputs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+        gp->dX.as<double>(), gp->dInvLs.as<double>(), N, D, DP, rows, gp->dXs.as<double>());
+    TB_LAUNCHED();
+  }
+  TB_TRY(gp->dL.reserve(sizeof(double) * N * N));
+  TB_TRY(gp->dLinv.reserve(sizeof(double) * N * N));
+  {
+    dim3 grid((unsigned)((N + 127) / 128), (unsigned)N);
+    double* K = gp->dL.as<double>();
+    const double* Xs = gp->dXs.as<double>();
+    switch (gp->kernel) {
+      case TB_RBF: gram_kernel<TB_RBF><<<grid, 128, 0, st>>>(Xs, N, DP, gp->variance, gp->noise, K); break;
+      case TB_MATERN12: gram_kernel<TB_MATERN12><<<grid, 128, 0, st>>>(Xs, N, DP, gp->variance, gp->noise, K); break;
+      case TB_MATERN32: gram_kernel<TB_MATERN32><<<grid, 128, 0, st>>>(Xs, N, DP, gp->variance, gp->noise, K); break;
+      default: gram_kernel<TB_MATERN52><<<grid, 128, 0, st>>>(Xs, N, DP, gp->variance, gp->noise, K); break;
+    }
+    TB_LAUNCHED();
+  }
+  // L = chol(K + noise I): library call on the once-per-step path (cuSOLVER), SURVEY.md §8 a3 / §8f-1
+  int lwork = 0;
+  TB_CUSOLVER(cusolverDnDpotrf_bufferSize(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dL.as<double>(),
+                                          (int)N, &lwork));
+  TB_TRY(gp->dWork.reserve(sizeof(double) * (size_t)std::max(lwork, 1)));
+  TB_TRY(gp->dInfo.reserve(sizeof(int)));
+  TB_CUSOLVER(cusolverDnDpotrf(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dL.as<double>(), (int)N,
+                               gp->dWork.as<double>(), lwork, gp->dInfo.as<int>()));
+  int info = 0;
+  TB_CUDA(cudaMemcpyAsync(&info, gp->dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CHECK(info == 0, "tb_gp_update_posterior_cache: Cholesky decomposition was not successful "
+                      "(K + noise*I not positive definite at leading minor " + std::to_string(info) + ")");
+  {
+    dim3 grid((unsigned)((N + 127) / 128), (unsigned)N);
+    zero_upper_kernel<<<grid, 128, 0, st>>>(N, gp->dL.as<double>());
+    TB_LAUNCHED();
+  }
+  // alpha = K^-1 err
+  TB_TRY(gp->dAlpha.reserve(sizeof(double) * rows));
+  residual_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(gp->dy.as<double>(), N, rows, gp->mean_const,
+                                                                  gp->dAlpha.as<double>());
+  TB_LAUNCHED();
+  TB_CUSOLVER(cusolverDnDpotrs(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, 1, gp->dL.as<double>(), (int)N,
+                               gp->dAlpha.as<double>(), (int)N, gp->dInfo.as<int>()));
+  // Linv = L^-1 (triangular solve against the identity)
+  {
+    int64_t tot = N * N;
+    identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(N, gp->dLinv.as<double>());
+    TB_LAUNCHED();
+    const double one = 1.0;
+    TB_CUBLAS(cublasDtrsm(gp->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
+                          (int)N, (int)N, &one, gp->dL.as<double>(), (int)N, gp->dLinv.as<double>(), (int)N));
+  }
+  // pack the lower triangle of Linv into DMMA-fragment-ordered panels
+  {
+    int64_t npanels = rowblock_panel_offset(gp->NB);
+    TB_TRY(gp->dLinvP.reserve(sizeof(double) * npanels * PANEL));
+    TB_CUDA(cudaMemsetAsync(gp->dLinvP.p, 0, sizeof(double) * npanels * PANEL, st));
+    dim3 grid((unsigned)std::min<int64_t>(gp->nkc, (int64_t)gp->NB * (BM / BK)), (unsigned)gp->NB);
+    pack_lower_panels_kernel<<<grid, 256, 0, st>>>(gp->dLinv.as<double>(), N, gp->nkc, gp->dLinvP.as<double>());
+    TB_LAUNCHED();
+  }
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
+  gp->cache_valid = true;
+  return 0;
+}
+
+int tb_gp_get_cholesky(tb_gp* gp, void* L_out) {
+  TB_CHECK(gp && L_out, "tb_gp_get_cholesky: null argument");
+  TB_CHECK(gp->cache_valid, "tb_gp_get_cholesky: posterior cache is not built");
+  TB_CUDA(cudaSetDevice(gp->device));
+  const int64_t N = gp->N;
+  TB_TRY(gp->sMisc.reserve(sizeof(double) * N * N));
+  dim3 grid((unsigned)((N + 127) / 128), (unsigned)N);
+  colmajor_lower_to_rowmajor_kernel<<<grid, 128, 0, gp->stream>>>(gp->dL.as<double>(), N, gp->sMisc.as<double>());
+  TB_LAUNCHED();
+  TB_CUDA(cudaMemcpyAsync(L_out, gp->sMisc.p, sizeof(double) * N * N, cudaMemcpyDefault, gp->stream));
+  TB_CUDA(cudaStreamSynchronize(gp->stream));
+  return 0;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// per-candidate path: chunked driver for predict / acquisition / argmax
+// =================================================================================================
+namespace tb {
+
+struct EvalRequest {
+  int acq = -1;  // -1: predict only
+  double param = 0.0;
+  const double* Xc = nullptr;  // host or device, [M, D]
+  int64_t M = 0;
+  double* out_vals = nullptr;  // host or device (nullable)
+  double* out_mean = nullptr;
+  double* out_var = nullptr;
+  double* out_grad = nullptr;  // [M, D] (nullable)
+  bool want_argmax = false;
+  double best_value = 0.0;
+  int64_t best_index = -1;
+};
+
+static int launch_kstar(tb_gp* gp, const double* Xc_dev, int64_t mc, int tiles, double* KsP, double* mean) {
+  const double* Xs = gp->dXs.as<double>();
+  const double* al = gp->dAlpha.as<double>();
+  const double* il = gp->dInvLs.as<double>();
+  const int N = (int)gp->N, nkc = gp->nkc, D = gp->D;
+  const double var = gp->variance, mc0 = gp->mean_const;
+  cudaStream_t st = gp->stream;
+#define TB_KSTAR(KIND, DPV)                                                                               \
+  kstar_panels_kernel<KIND, DPV><<<tiles, 512, 0, st>>>(Xs, al, Xc_dev, il, N, nkc, D, mc, 0, var, mc0, KsP, mean)
+#define TB_KSTAR_DP(KIND)                                   \
+  switch (gp->DP) {                                         \
+    case 2: TB_KSTAR(KIND, 2); break;                       \
+    case 4: TB_KSTAR(KIND, 4); break;                       \
+    case 6: TB_KSTAR(KIND, 6); break;                       \
+    case 8: TB_KSTAR(KIND, 8); break;                       \
+    case 10: TB_KSTAR(KIND, 10); break;                     \
+    case 12: TB_KSTAR(KIND, 12); break;                     \
+    case 16: TB_KSTAR(KIND, 16); break;                     \
+    case 20: TB_KSTAR(KIND, 20); break;                     \
+    case 24: TB_KSTAR(KIND, 24); break;                     \
+    default: TB_KSTAR(KIND, 32); break;                     \
+  }
+  switch (gp->kernel) {
+    case TB_RBF: TB_KSTAR_DP(TB_RBF); break;
+    case TB_MATERN12: TB_KSTAR_DP(TB_MATERN12); break;
+    case TB_MATERN32: TB_KSTAR_DP(TB_MATERN32); break;
+    default: TB_KSTAR_DP(TB_MATERN52); break;
+  }
+#undef TB_KSTAR_DP
+#undef TB_KSTAR
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// candidates per chunk: bounded by the Ks scratch budget, a whole number of 148-CTA waves when possible
+static int64_t chunk_tiles(const tb_gp* gp) {
+  const size_t per_tile = (size_t)gp->nkc * PANEL * sizeof(double);
+  const size_t budget = (size_t)1536 << 20;
+  int64_t t = (int64_t)(budget / per_tile);
+  t = std::max<int64_t>(t, 1);
+  if (t >= 148) t = (t / 148) * 148;
+  return std::min<int64_t>(t, 148 * 16);
+}
+
+static int pick_groups(const tb_gp* gp, int tiles) {
+  if (tiles >= 148) return 1;
+  int G = (2 * 148 + tiles - 1) / tiles;
+  return std::max(1, std::min(G, gp->NB));
+}
+
+static int run_eval(tb_gp* gp, EvalRequest& rq) {
+  TB_CHECK(gp->cache_valid, "posterior cache is not built: call tb_gp_update_posterior_cache first");
+  TB_CHECK(rq.M >= 0, "negative candidate count");
+  TB_CUDA(cudaSetDevice(gp->device));
+  cudaStream_t st = gp->stream;
+  const int D = gp->D;
+  if (rq.want_argmax) {
+    TB_CHECK(rq.M > 0, "argmax over an empty candidate set");
+    TB_TRY(gp->sRun.reserve(16));
+    double init_v = -DBL_MAX;
+    int64_t init_i = INT64_MAX;
+    TB_CUDA(cudaMemcpyAsync(gp->sRun.p, &init_v, 8, cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaMemcpyAsync((char*)gp->sRun.p + 8, &init_i, 8, cudaMemcpyHostToDevice, st));
+  }
+  if (rq.M == 0) return 0;
+
+  const bool xc_dev = is_device_ptr(rq.Xc);
+  const bool vals_dev = is_device_ptr(rq.out_vals), mean_dev = is_device_ptr(rq.out_mean),
+             var_dev = is_device_ptr(rq.out_var);
+  const int64_t max_tiles = chunk_tiles(gp);
+  const int64_t Mc_max = max_tiles * BT;
+  const int64_t chunk_cap = std::min<int64_t>(Mc_max, ((rq.M + BT - 1) / BT) * BT);
+  const int64_t tiles_cap = chunk_cap / BT;
+  const int Gmax = pick_groups(gp, (int)std::min<int64_t>(tiles_cap, 1 << 30));
+
+  TB_TRY(gp->sKs.reserve((size_t)tiles_cap * gp->nkc * PANEL * sizeof(double)));
+  TB_TRY(gp->sPartial.reserve(sizeof(double) * (size_t)Gmax * chunk_cap));
+  TB_TRY(gp->sMean.reserve(sizeof(double) * chunk_cap));
+  if (!xc_dev) TB_TRY(gp->sXc.reserve(sizeof(double) * chunk_cap * D));
+  if (rq.out_vals && !vals_dev) TB_TRY(gp->sVals.reserve(sizeof(double) * chunk_cap));
+  if (rq.out_var && !var_dev) TB_TRY(gp->sVar.reserve(sizeof(double) * chunk_cap));
+  const int tail_blocks_cap = (int)((chunk_cap + 255) / 256);
+  if (rq.want_argmax) {
+    TB_TRY(gp->sBlkBest.reserve(sizeof(double) * tail_blocks_cap));
+    TB_TRY(gp->sBlkIdx.reserve(sizeof(int64_t) * tail_blocks_cap));
+  }
+
+  for (int64_t c0 = 0; c0 < rq.M; c0 += chunk_cap) {
+    const int64_t mc = std::min<int64_t>(chunk_cap, rq.M - c0);
+    const int tiles = (int)((mc + BT - 1) / BT);
+    const int64_t McPad = (int64_t)tiles * BT;
+    const int G = pick_groups(gp, tiles);
+
+    const double* xc_chunk;
+    if (xc_dev) {
+      xc_chunk = rq.Xc + c0 * D;
+    } else {
+      TB_CUDA(cudaMemcpyAsync(gp->sXc.p, rq.Xc + c0 * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, st));
+      xc_chunk = gp->sXc.as<double>();
+    }
+    TB_TRY(launch_kstar(gp, xc_chunk, mc, tiles, gp->sKs.as<double>(), gp->sMean.as<double>()));
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (gp->profile) {
+      TB_CUDA(cudaEventCreate(&e0));
+      TB_CUDA(cudaEventCreate(&e1));
+      TB_CUDA(cudaEventRecord(e0, st));
+    }
+    trigemm_sumsq_kernel<<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
+        gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, gp->sPartial.as<double>());
+    TB_LAUNCHED();
+    if (gp->profile) {
+      TB_CUDA(cudaEventRecord(e1, st));
+      gp->prof_events.emplace_back(e0, e1);
+      gp->prof_event_flops.push_back((double)McPad * (double)gp->N * (double)gp->N);
+    }
+    TB_CUDA(cudaGetLastError());
+
+    if (rq.out_grad) TB_TRY(tb::gradient_chunk(gp, rq.acq, rq.param, xc_chunk, mc, tiles, G, McPad, rq.out_grad + c0 * D));
+
+    double* d_vals = rq.out_vals ? (vals_dev ? rq.out_vals + c0 : gp->sVals.as<double>()) : nullptr;
+    double* d_mean = rq.out_mean ? (mean_dev ? rq.out_mean + c0 : nullptr) : nullptr;  // sMean already holds it
+    double* d_var = rq.out_var ? (var_dev ? rq.out_var + c0 : gp->sVar.as<double>()) : nullptr;
+    const int tb_blocks = (int)((mc + 255) / 256);
+    tail_kernel<<<tb_blocks, 256, 0, st>>>(gp->sPartial.as<double>(), G, McPad, gp->sMean.as<double>(), mc, c0,
+                                           gp->variance, rq.acq, rq.param, d_vals, d_mean, d_var,
+                                           rq.want_argmax ? gp->sBlkBest.as<double>() : nullptr,
+                                           rq.want_argmax ? gp->sBlkIdx.as<int64_t>() : nullptr);
+    TB_LAUNCHED();
+    if (rq.want_argmax) {
+      argmax_fold_kernel<<<1, 256, 0, st>>>(gp->sBlkBest.as<double>(), gp->sBlkIdx.as<int64_t>(), tb_blocks,
+                                            gp->sRun.as<double>(), reinterpret_cast<int64_t*>((char*)gp->sRun.p + 8));
+      TB_LAUNCHED();
+    }
+    if (rq.out_vals && !vals_dev)
+      TB_CUDA(cudaMemcpyAsync(rq.out_vals + c0, gp->sVals.p, sizeof(double) * mc, cudaMemcpyDeviceToHost, st));
+    if (rq.out_mean && !mean_dev)
+      TB_CUDA(cudaMemcpyAsync(rq.out_mean + c0, gp->sMean.p, sizeof(double) * mc, cudaMemcpyDeviceToHost, st));
+    if (rq.out_var && !var_dev)
+      TB_CUDA(cudaMemcpyAsync(rq.out_var + c0, gp->sVar.p, sizeof(double) * mc, cudaMemcpyDeviceToHost, st));
+    // scratch is reused by the next chunk: host-staged copies must drain first
+    if (!xc_dev || (rq.out_vals && !vals_dev) || (rq.out_mean && !mean_dev) || (rq.out_var && !var_dev))
+      TB_CUDA(cudaStreamSynchronize(st));
+  }
+  if (rq.want_argmax) {
+    TB_CUDA(cudaMemcpyAsync(&rq.best_value, gp->sRun.p, 8, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaMemcpyAsync(&rq.best_index, (char*)gp->sRun.p + 8, 8, cudaMemcpyDeviceToHost, st));
+  }
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
+  if (gp->profile) {
+    for (size_t i = 0; i < gp->prof_events.size(); ++i) {
+      float ms = 0.f;
+      TB_CUDA(cudaEventElapsedTime(&ms, gp->prof_events[i].first, gp->prof_events[i].second));
+      gp->prof_ms += ms;
+      gp->prof_flops += gp->prof_event_flops[i];
+      gp->prof_launches += 1;
+      cudaEventDestroy(gp->prof_events[i].first);
+      cudaEventDestroy(gp->prof_events[i].second);
+    }
+    gp->prof_events.clear();
+    gp->prof_event_flops.clear();
+  }
+  return 0;
+}
+
+}  // namespace tb
+
+extern "C" {
+
+int tb_gp_predict(tb_gp* gp, const void* Xc, int64_t M, void* mean, void* var) {
+  TB_CHECK(gp && (M == 0 || (Xc && mean && var)), "tb_gp_predict: null argument");
+  tb::EvalRequest rq;
+  rq.Xc = (const double*)Xc;
+  rq.M = M;
+  rq.out_mean = (double*)mean;
+  rq.out_var = (double*)var;
+  return tb::run_eval(gp, rq);
+}
+
+int tb_acq_eval(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* grad) {
+  TB_CHECK(gp && (M == 0 || (Xc && out)), "tb_acq_eval: null argument");
+  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_LCB, "tb_acq_eval: unknown acquisition kind");
+  if (acq == TB_ACQ_LCB || acq == TB_ACQ_NEG_LCB)
+    TB_CHECK(param >= 0.0, "Standard deviation scaling parameter beta must not be negative");
+  tb::EvalRequest rq;
+  rq.acq = acq;
+  rq.param = param;
+  rq.Xc = (const double*)Xc;
+  rq.M = M;
+  rq.out_vals = (double*)out;
+  rq.out_grad = (double*)grad;
+  return tb::run_eval(gp, rq);
+}
+
+int tb_acq_argmax(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* best_value,
+                  int64_t* best_index) {
+  TB_CHECK(gp && Xc && best_value && best_index, "tb_acq_argmax: null argument");
+  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_LCB, "tb_acq_argmax: unknown acquisition kind");
+  if (acq == TB_ACQ_LCB || acq == TB_ACQ_NEG_LCB)
+    TB_CHECK(param >= 0.0, "Standard deviation scaling parameter beta must not be negative");
+  tb::EvalRequest rq;
+  rq.acq = acq;
+  rq.param = param;
+  rq.Xc = (const double*)Xc;
+  rq.M = M;
+  rq.out_vals = (double*)out;
+  rq.want_argmax = true;
+  TB_TRY(tb::run_eval(gp, rq));
+  *(double*)best_value = rq.best_value;
+  *best_index = rq.best_index;
+  return 0;
+}
+
+int tb_gp_profile(tb_gp* gp, int enable) {
+  TB_CHECK(gp, "tb_gp_profile: null handle");
+  gp->profile = enable != 0;
+  gp->prof_ms = 0.0;
+  gp->prof_flops = 0.0;
+  gp->prof_launches = 0;
+  return 0;
+}
+int tb_gp_stream(tb_gp* gp, void** stream) {
+  TB_CHECK(gp && stream, "tb_gp_stream: null argument");
+  *stream = (void*)gp->stream;
+  return 0;
+}
+int tb_gp_profile_read(tb_gp* gp, double* trigemm_ms, int64_t* trigemm_launches, double* flops) {
+  TB_CHECK(gp, "tb_gp_profile_read: null handle");
+  if (trigemm_ms) *trigemm_ms = gp->prof_ms;
+  if (trigemm_launches) *trigemm_launches = gp->prof_launches;
+  if (flops) *flops = gp->prof_flops;
+  return 0;
+}
+
+}  // extern "C"

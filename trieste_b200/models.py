@@ -1,0 +1,267 @@
+"""Model side of the drop-in boundary.
+
+``GaussianProcessRegression`` mirrors trieste's wrapper of the same name
+(trieste/models/gpflow/models.py:69-526) together with the ``GPflowPredictor`` posterior cache
+(trieste/models/gpflow/interface.py:89-133).  It satisfies the structural protocols
+``ProbabilisticModel`` / ``SupportsPredictJoint`` / ``HasReparamSampler`` / ``HasTrajectorySampler``
+/ ``TrainableProbabilisticModel`` (trieste/models/interfaces.py:38-327) by method name, argument
+meaning and output shape.  All arithmetic runs on the GPU behind the C-ABI; arrays may be NumPy
+(host, staged per call) or ``torch.cuda`` tensors (device-resident, zero-copy).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .data import Dataset
+from .kernels import Constant, Matern52, Stationary
+from .space import SearchSpace
+
+# builders.py:41-82
+KERNEL_LENGTHSCALE = 0.2
+SIGNAL_NOISE_RATIO_LIKELIHOOD = 10.0
+
+
+class GPRSpec:
+    """What ``gpflow.models.GPR(data, kernel, mean_function, noise_variance)`` carries."""
+
+    def __init__(self, data, kernel: Stationary, mean_function: Optional[Constant] = None, noise_variance: float = 1.0):
+        if isinstance(data, Dataset):
+            data = data.astuple()
+        self.X = np.ascontiguousarray(np.asarray(data[0], dtype=np.float64))
+        self.Y = np.ascontiguousarray(np.asarray(data[1], dtype=np.float64))
+        self.kernel = kernel
+        self.mean_function = mean_function if mean_function is not None else Constant(0.0)
+        self.noise_variance = float(noise_variance)
+
+
+def build_gpr(
+    data: Dataset,
+    search_space: Optional[SearchSpace] = None,
+    kernel_priors: bool = True,
+    likelihood_variance: Optional[float] = None,
+    trainable_likelihood: bool = False,
+    kernel: Optional[Stationary] = None,
+) -> GPRSpec:
+    """``build_gpr`` defaults (trieste/models/gpflow/builders.py:85-155): Matern52, constant mean
+    = mean(y), kernel variance = Var(y), lengthscales 0.2 * (upper - lower) * sqrt(D) (:413-423),
+    noise = Var(y) / 10^2 unless given (:432-443).  Priors only matter for hyper-parameter
+    training, which is out of scope here."""
+    X, Y = np.asarray(data.query_points, dtype=np.float64), np.asarray(data.observations, dtype=np.float64)
+    if X.shape[0] == 0:
+        raise ValueError("Dataset must be populated.")
+    variance = float(np.var(Y))
+    if variance <= 0:
+        variance = 1.0
+    mean = float(np.mean(Y))
+    D = X.shape[-1]
+    if kernel is None:
+        if search_space is not None:
+            rng_ = np.asarray(search_space.upper) - np.asarray(search_space.lower)
+            ls = KERNEL_LENGTHSCALE * rng_ * math.sqrt(D)
+            ls = np.where(rng_ == 0, 1.0, ls)
+        else:
+            ls = np.full(D, KERNEL_LENGTHSCALE * math.sqrt(D))
+        kernel = Matern52(variance=variance, lengthscales=ls)
+    if likelihood_variance is None:
+        noise = variance / SIGNAL_NOISE_RATIO_LIKELIHOOD**2
+    else:
+        if likelihood_variance <= 0:
+            raise ValueError("likelihood_variance must be positive")
+        noise = float(likelihood_variance)
+    return GPRSpec((X, Y), kernel, Constant(mean), noise)
+
+
+def _flatten_leading(x, keep: int):
+    """[..., k1..k_keep] -> ([prod, k...], leading_shape)."""
+    lead = tuple(x.shape[: x.ndim - keep])
+    return x.reshape((-1,) + tuple(x.shape[x.ndim - keep :])), lead
+
+
+class GaussianProcessRegression:
+    """B200-native exact GPR posterior.  Construct from a :class:`GPRSpec` (or ``build_gpr(...)``)."""
+
+    def __init__(self, model: GPRSpec, device: int = 0, num_rff_features: int = 1000, use_decoupled_sampler: bool = False):
+        _lib.require_gpu()
+        if num_rff_features <= 0:
+            raise ValueError(f"num_rff_features must be greater or equal to zero, got {num_rff_features}.")
+        self._spec = model
+        self._device = device
+        self._num_rff_features = num_rff_features
+        self._use_decoupled_sampler = use_decoupled_sampler
+        if use_decoupled_sampler:
+            raise NotImplementedError("DecoupledTrajectorySampler is listed as 'next' (SURVEY.md §8f-2)")
+        h = C.c_void_p()
+        _lib.check(_lib.lib().tb_gp_create(C.byref(h), device, _lib.TB_F64))
+        self._h = h
+        self._push_data()
+        self._push_hyper()
+        self.update_posterior_cache()
+
+    # ---- handle plumbing ---------------------------------------------------------------------
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().tb_gp_destroy(h)
+            except Exception:  # pragma: no cover
+                pass
+            self._h = None
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    @property
+    def device(self) -> int:
+        return self._device
+
+    def _push_data(self) -> None:
+        X, Y = self._spec.X, self._spec.Y
+        if X.ndim != 2 or Y.ndim != 2 or Y.shape[1] != 1 or X.shape[0] != Y.shape[0]:
+            raise ValueError(f"expected query_points [N, D] and observations [N, 1], got {X.shape} and {Y.shape}")
+        if X.shape[0] == 0:
+            raise ValueError("Dataset must be populated.")
+        y = np.ascontiguousarray(Y[:, 0])
+        _lib.check(_lib.lib().tb_gp_set_data(self._h, X.ctypes.data, y.ctypes.data, X.shape[0], X.shape[1]))
+
+    def _push_hyper(self) -> None:
+        k = self._spec.kernel
+        ls = np.ascontiguousarray(k.lengthscales, dtype=np.float64)
+        _lib.check(
+            _lib.lib().tb_gp_set_hyper(
+                self._h,
+                _lib.KERNEL_IDS[k.kind],
+                k.variance,
+                ls.ctypes.data_as(C.POINTER(C.c_double)),
+                int(ls.size),
+                self._spec.noise_variance,
+                self._spec.mean_function.c,
+            )
+        )
+
+    def update_posterior_cache(self) -> None:
+        """interface.py:108-112 — must follow any change of data or hyper-parameters."""
+        _lib.check(_lib.lib().tb_gp_update_posterior_cache(self._h))
+
+    # ---- ProbabilisticModel ------------------------------------------------------------------
+    def predict(self, query_points) -> Tuple[np.ndarray, np.ndarray]:
+        """[..., D] -> (mean [..., 1], var [..., 1]), variance clipped to >= 1e-12
+        (interfaces.py:55-64; interface.py:119-124)."""
+        x, _ = _lib.as_f64_contiguous(query_points)
+        self._check_dim(x)
+        flat, lead = _flatten_leading(x, 1)
+        M = flat.shape[0]
+        mean, pm = _lib.empty_like_kind(flat, (M, 1))
+        var, pv = _lib.empty_like_kind(flat, (M, 1))
+        _lib.check(_lib.lib().tb_gp_predict(self._h, _ptr(flat), M, pm, pv))
+        return mean.reshape(lead + (1,)), var.reshape(lead + (1,))
+
+    def predict_joint(self, query_points) -> Tuple[np.ndarray, np.ndarray]:
+        """[..., B, D] -> (mean [..., B, 1], cov [..., 1, B, B]) (interfaces.py:133-140;
+        interface.py:126-133)."""
+        x, _ = _lib.as_f64_contiguous(query_points)
+        if x.ndim < 2:
+            raise ValueError(f"predict_joint needs query points of rank >= 2, got shape {tuple(x.shape)}")
+        self._check_dim(x)
+        flat, lead = _flatten_leading(x, 2)
+        nb, q = flat.shape[0], flat.shape[1]
+        mean, pm = _lib.empty_like_kind(flat, (nb, q, 1))
+        cov, pc = _lib.empty_like_kind(flat, (nb, 1, q, q))
+        _lib.check(_lib.lib().tb_gp_predict_joint(self._h, _ptr(flat), nb, q, pm, pc))
+        return mean.reshape(lead + (q, 1)), cov.reshape(lead + (1, q, q))
+
+    def predict_y(self, query_points):
+        """Gaussian likelihood: adds the observation noise to the variance (models.py:126-131)."""
+        mean, var = self.predict(query_points)
+        return mean, var + self._spec.noise_variance
+
+    def sample(self, query_points, num_samples: int, seed: Optional[int] = None):
+        """[..., N, D] -> [..., S, N, 1]: joint samples through ``predict_joint`` + Cholesky
+        (interface.py:135-138 -> gpflow predict_f_samples)."""
+        if num_samples <= 0:
+            raise ValueError(f"num_samples must be positive, got {num_samples}")
+        x = np.asarray(query_points, dtype=np.float64)
+        q = x.shape[-2]
+        eps = np.random.default_rng(seed).standard_normal((q, num_samples))
+        from .sampler import _reparam_sample
+
+        return _reparam_sample(self, x, eps, 1e-6)
+
+    def log(self, dataset: Optional[Dataset] = None) -> None:
+        """TensorBoard summaries in the reference (models/utils.py:33-107): observability only."""
+
+    # ---- TrainableProbabilisticModel -----------------------------------------------------------
+    def update(self, dataset: Dataset) -> None:
+        """models.py:171-186: swap the data, refresh the posterior cache."""
+        X = np.ascontiguousarray(np.asarray(dataset.query_points, dtype=np.float64))
+        Y = np.ascontiguousarray(np.asarray(dataset.observations, dtype=np.float64))
+        if X.ndim != 2 or X.shape[-1] != self._spec.X.shape[-1]:
+            raise ValueError(f"new query points must be [N, {self._spec.X.shape[-1]}], got {X.shape}")
+        self._spec.X, self._spec.Y = X, Y
+        self._push_data()
+        self.update_posterior_cache()
+
+    def optimize(self, dataset: Dataset) -> None:
+        """Hyper-parameter training (models.py:256-292) is the once-per-step model fit and is OUT OF
+        SCOPE of this engine: hyper-parameters are set through
+        :meth:`set_hyperparameters`; the cache refresh that follows training in the reference
+        (models.py:290-291) is kept."""
+        self.update_posterior_cache()
+
+    def set_hyperparameters(self, kernel: Optional[Stationary] = None, noise_variance: Optional[float] = None,
+                            mean_constant: Optional[float] = None) -> None:
+        if kernel is not None:
+            self._spec.kernel = kernel
+        if noise_variance is not None:
+            self._spec.noise_variance = float(noise_variance)
+        if mean_constant is not None:
+            self._spec.mean_function = Constant(mean_constant)
+        self._push_hyper()
+        self.update_posterior_cache()
+
+    # ---- getters used by samplers (interfaces.py:166-225) -------------------------------------------
+    def get_kernel(self) -> Stationary:
+        return self._spec.kernel
+
+    def get_mean_function(self) -> Constant:
+        return self._spec.mean_function
+
+    def get_observation_noise(self) -> float:
+        return self._spec.noise_variance
+
+    def get_internal_data(self) -> Dataset:
+        return Dataset(self._spec.X, self._spec.Y)
+
+    def get_cholesky(self) -> np.ndarray:
+        N = self._spec.X.shape[0]
+        out = np.empty((N, N))
+        _lib.check(_lib.lib().tb_gp_get_cholesky(self._h, out.ctypes.data))
+        return out
+
+    # ---- samplers --------------------------------------------------------------------------------
+    def reparam_sampler(self, num_samples: int):
+        """interface.py:189-195 -> BatchReparametrizationSampler."""
+        from .sampler import BatchReparametrizationSampler
+
+        return BatchReparametrizationSampler(num_samples, self)
+
+    def trajectory_sampler(self):
+        """models.py:323-345 (RFF branch, ``use_decoupled_sampler=False``)."""
+        from .sampler import RandomFourierFeatureTrajectorySampler
+
+        return RandomFourierFeatureTrajectorySampler(self, self._num_rff_features)
+
+    # ---- helpers -----------------------------------------------------------------------------------
+    def _check_dim(self, x) -> None:
+        D = self._spec.X.shape[-1]
+        if x.ndim < 1 or x.shape[-1] != D:
+            raise ValueError(f"query points must have trailing dimension {D}, got shape {tuple(x.shape)}")
+
+
+def _ptr(a) -> int:
+    return a.data_ptr() if _lib.is_torch(a) else a.ctypes.data
