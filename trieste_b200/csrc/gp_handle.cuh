@@ -76,6 +76,8 @@ struct tb_gp {
   tb::DevBuf dL;                // [N,N] column-major lower Cholesky factor
   tb::DevBuf dLinv;             // [N,N] column-major Linv (kept: predict_joint / gradients reuse it)
   tb::DevBuf dLinvP;            // packed lower panels
+  tb::DevBuf dLinvTP;           // packed upper panels of Linv^T (lazy; gradient path)
+  bool upper_valid = false;
   tb::DevBuf dWork, dInfo;      // cusolver workspace
 
   // per-call scratch

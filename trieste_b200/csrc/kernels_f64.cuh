@@ -95,28 +95,54 @@ kstar_panels_kernel(const double* __restrict__ Xs,      // [nkc*16][DP] training
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1b: triangular DMMA GEMM with sum-of-squares epilogue.
+// K1b: triangular DMMA GEMM  C = T · B  with T a packed triangular factor (Linv lower, or Linv^T upper)
 //   grid = (candidate tiles, G row-block groups); 8 consumer warps (2 x 4, warp tile 64 rows x 32
 //   candidates, 64 fp64 accumulators / thread) + 1 producer warp that streams packed 16 KB panels of
-//   Linv and Ks with 1-D bulk TMA copies through a 4-stage mbarrier ring.
-//   partial[g][t] = sum over the group's rows n of (sum_k Linv[n,k] Ks[k,t])^2
+//   T and B with 1-D bulk TMA copies through a 4-stage mbarrier ring.
+//   Epilogues (compile-time):
+//     EPI_SUMSQ         partial[g][t] = sum over the group's rows n of C[n,t]^2            (variance)
+//     EPI_SUMSQ_PACKED  + C stored as B-operand panels [tile][row/16][PANEL]   (feeds the Linv^T GEMM)
+//     EPI_PLAIN         C stored plain, candidate-major: Cplain[t][ldc] (n contiguous)    (joint / V)
+//     EPI_SUMSQ_PLAIN   both
 // ------------------------------------------------------------------------------------------------
 constexpr int TG_STAGES = 4;
 constexpr int TG_CONSUMER_WARPS = 8;
 constexpr int TG_THREADS = (TG_CONSUMER_WARPS + 1) * 32;
 constexpr size_t TG_SMEM = (size_t)TG_STAGES * 2 * PANEL * sizeof(double) + 2 * TG_STAGES * 8 + 2 * BT * 8 + 64;
 
+enum { EPI_SUMSQ = 0, EPI_SUMSQ_PACKED = 1, EPI_PLAIN = 2, EPI_SUMSQ_PLAIN = 3 };
+
 __device__ __forceinline__ int serpentine_rowblock(int i, int g, int G) {
-  // i-th row-block of group g: ..., balances the triangular cost across groups
+  // i-th row-block of group g (increasing in i); balances the triangular cost across groups
   int base = (i >> 1) * 2 * G;
   return (i & 1) ? base + 2 * G - 1 - g : base + g;
 }
 
+// panel range [k0, k1) and storage offset of row-block I
+template <bool UPPER>
+__device__ __forceinline__ void rowblock_range(int I, int nkB, int& k0, int& k1, int64_t& off) {
+  if (!UPPER) {
+    k0 = 0;
+    k1 = min((I + 1) * (BM / BK), nkB);
+    off = rowblock_panel_offset(I);
+  } else {
+    k0 = I * (BM / BK);
+    k1 = nkB;
+    off = (int64_t)I * nkB - rowblock_panel_offset(I - 1) - (int64_t)k0;  // so that panel kc sits at off + kc
+  }
+}
+__host__ __device__ inline int64_t upper_panel_count(int NB, int nkB) {
+  return (int64_t)NB * nkB - rowblock_panel_offset(NB - 1);
+}
+
+template <bool UPPER, int EPI>
 __global__ void __launch_bounds__(TG_THREADS, 1)
-trigemm_sumsq_kernel(const double* __restrict__ LinvP,  // packed lower-triangular panels
-                     const double* __restrict__ KsP,    // [tiles][nkc][PANEL]
-                     int NB, int nkc, int G, int64_t McPad,
-                     double* __restrict__ partial) {    // [G][McPad]
+trigemm_kernel(const double* __restrict__ TP,   // packed triangular panels
+               const double* __restrict__ BP,   // [tiles][nkB][PANEL]
+               int NB, int nkB, int G, int64_t McPad,
+               double* __restrict__ partial,    // [G][McPad]                (SUMSQ variants)
+               double* __restrict__ Cpacked,    // [tiles][NB*8][PANEL]      (EPI_SUMSQ_PACKED)
+               double* __restrict__ Cplain, int64_t ldc) {  // [McPad][ldc] (PLAIN variants)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sA = reinterpret_cast<double*>(smem_raw);
   double* sB = sA + TG_STAGES * PANEL;
@@ -136,7 +162,7 @@ trigemm_sumsq_kernel(const double* __restrict__ LinvP,  // packed lower-triangul
   }
   __syncthreads();
 
-  const double* ksTile = KsP + (int64_t)tile * nkc * PANEL;
+  const double* bTile = BP + (int64_t)tile * nkB * PANEL;
 
   if (warp == TG_CONSUMER_WARPS) {
     // ===== producer warp: one elected lane issues the bulk copies =====
@@ -144,15 +170,17 @@ trigemm_sumsq_kernel(const double* __restrict__ LinvP,  // packed lower-triangul
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0;; ++i) {
-        const int I = serpentine_rowblock(i, g, G);  // increasing in i
+        const int I = serpentine_rowblock(i, g, G);
         if (I >= NB) break;
-        const int nk = min((I + 1) * (BM / BK), nkc);
-        const double* aRow = LinvP + rowblock_panel_offset(I) * PANEL;
-        for (int kc = 0; kc < nk; ++kc) {
+        int k0, k1;
+        int64_t off;
+        rowblock_range<UPPER>(I, nkB, k0, k1, off);
+        const double* aRow = TP + off * PANEL;
+        for (int kc = k0; kc < k1; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], 2 * PANEL * sizeof(double));
           bulk_g2s(sA + stage * PANEL, aRow + (int64_t)kc * PANEL, PANEL * sizeof(double), &full[stage]);
-          bulk_g2s(sB + stage * PANEL, ksTile + (int64_t)kc * PANEL, PANEL * sizeof(double), &full[stage]);
+          bulk_g2s(sB + stage * PANEL, bTile + (int64_t)kc * PANEL, PANEL * sizeof(double), &full[stage]);
           if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -176,8 +204,10 @@ trigemm_sumsq_kernel(const double* __restrict__ LinvP,  // packed lower-triangul
   for (int i = 0;; ++i) {
     const int I = serpentine_rowblock(i, g, G);
     if (I >= NB) break;
-    const int nk = min((I + 1) * (BM / BK), nkc);
-    for (int kc = 0; kc < nk; ++kc) {
+    int k0, k1;
+    int64_t off;
+    rowblock_range<UPPER>(I, nkB, k0, k1, off);
+    for (int kc = k0; kc < k1; ++kc) {
       mbar_wait(&full[stage], phase);
       const double2* a2 = reinterpret_cast<const double2*>(sA + stage * PANEL);
       const double2* b2 = reinterpret_cast<const double2*>(sB + stage * PANEL);
@@ -201,7 +231,35 @@ trigemm_sumsq_kernel(const double* __restrict__ LinvP,  // packed lower-triangul
       if (lane == 0) mbar_arrive(&empty[stage]);
       if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
     }
-    // row-block epilogue: fold the squared A entries into the running column sums
+    // ---- row-block epilogue ----
+    if (EPI == EPI_SUMSQ_PACKED) {
+      // C[n,t] -> B-operand panel of the next GEMM: "k" = n % 16, "row" = t within the tile
+      double* cTile = Cpacked + ((int64_t)tile * NB * (BM / BK) + (int64_t)I * (BM / BK)) * PANEL;
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const int np = wm * 4 + (ii >> 1);  // 16-row panel within the row-block
+        double* pn = cTile + (int64_t)np * PANEL;
+        const int p = ii & 1, s = lane >> 4, kq = (lane >> 2) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int g8 = wt * 4 + j, rr = (lane & 3) * 2 + c;
+            pn[(((g8 * 2 + p) * 32 + rr * 4 + kq) << 1) + s] = acc[ii][j][c];
+          }
+      }
+    }
+    if (EPI == EPI_PLAIN || EPI == EPI_SUMSQ_PLAIN) {
+      const int64_t tbase = (int64_t)tile * BT + wt * 32 + (lane & 3) * 2;
+      const int64_t nbase = (int64_t)I * BM + wm * 64 + (lane >> 2);
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            Cplain[(tbase + j * 8 + c) * ldc + nbase + ii * 8] = acc[ii][j][c];
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       double s0 = 0.0, s1 = 0.0;
@@ -217,6 +275,7 @@ trigemm_sumsq_kernel(const double* __restrict__ LinvP,  // packed lower-triangul
     }
   }
 
+  if (EPI == EPI_PLAIN) return;
   // reduce over the 8 row-lanes (lane / 4) of the warp, then over the two row-warps
 #pragma unroll
   for (int j = 0; j < 4; ++j)

@@ -4,6 +4,9 @@
 #include "kernels_extra.cuh"
 
 using namespace tb;
+namespace tb {
+int kernels_init();
+}
 
 // =================================================================================================
 // once-per-step precompute kernels (posterior cache)
@@ -133,9 +136,7 @@ int tb_gp_create(tb_gp** out, int device, int dtype) {
   TB_CUBLAS(cublasSetStream(gp->cublas, gp->stream));
   TB_CUSOLVER(cusolverDnCreate(&gp->cusolver));
   TB_CUSOLVER(cusolverDnSetStream(gp->cusolver, gp->stream));
-  TB_CUDA(cudaFuncSetAttribute(trigemm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)TG_SMEM));
-  TB_TRY(tb::extra_kernels_init());
+  TB_TRY(tb::kernels_init());
   *out = gp;
   return 0;
 }
@@ -145,7 +146,7 @@ int tb_gp_destroy(tb_gp* gp) {
   cudaSetDevice(gp->device);
   cudaStreamSynchronize(gp->stream);
   for (tb::DevBuf* b : {&gp->dX, &gp->dy, &gp->dXs, &gp->dInvLs, &gp->dAlpha, &gp->dL, &gp->dLinv,
-                        &gp->dLinvP, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
+                        &gp->dLinvP, &gp->dLinvTP, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
                         &gp->sVals, &gp->sVar, &gp->sXc, &gp->sBlkBest, &gp->sBlkIdx, &gp->sRun,
                         &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc})
     b->release();
@@ -285,6 +286,7 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
   TB_CUDA(cudaStreamSynchronize(st));
   TB_CUDA(cudaGetLastError());
   gp->cache_valid = true;
+  gp->upper_valid = false;
   return 0;
 }
 
@@ -374,6 +376,85 @@ static int pick_groups(const tb_gp* gp, int tiles) {
   return std::max(1, std::min(G, gp->NB));
 }
 
+int kernels_init() {
+  TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
+  TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
+  TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
+  TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<true, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
+  return 0;
+}
+
+// Linv^T packed upper panels: built lazily, only the gradient path needs them
+static int ensure_upper_panels(tb_gp* gp) {
+  if (gp->upper_valid) return 0;
+  const int nkB = gp->NB * (BM / BK);
+  const int64_t np = upper_panel_count(gp->NB, nkB);
+  TB_TRY(gp->dLinvTP.reserve(sizeof(double) * np * PANEL));
+  dim3 grid((unsigned)nkB, (unsigned)gp->NB);
+  pack_upper_panels_kernel<<<grid, 256, 0, gp->stream>>>(gp->dLinv.as<double>(), gp->N, gp->NB, nkB,
+                                                         gp->dLinvTP.as<double>());
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  gp->upper_valid = true;
+  return 0;
+}
+
+template <int KIND>
+static void launch_grad_dp(tb_gp* gp, const double* xc, int64_t mc, double* grad_dev) {
+  const int blocks = (int)((mc + 7) / 8);
+  const double* Xs = gp->dXs.as<double>();
+  const double* al = gp->dAlpha.as<double>();
+  const double* il = gp->dInvLs.as<double>();
+  const double* V = gp->sV.as<double>();
+  const int64_t ldv = (int64_t)gp->NB * BM;
+  const double* cmu = gp->sMisc.as<double>();
+  const double* cvar = cmu + mc;
+#define TB_GRAD(DPV) \
+  grad_kernel<KIND, DPV><<<blocks, 256, 0, gp->stream>>>(Xs, al, xc, il, (int)gp->N, gp->D, mc, V, ldv, cmu, cvar, gp->variance, grad_dev)
+  switch (gp->DP) {
+    case 2: TB_GRAD(2); break;
+    case 4: TB_GRAD(4); break;
+    case 6: TB_GRAD(6); break;
+    case 8: TB_GRAD(8); break;
+    case 10: TB_GRAD(10); break;
+    case 12: TB_GRAD(12); break;
+    case 16: TB_GRAD(16); break;
+    case 20: TB_GRAD(20); break;
+    case 24: TB_GRAD(24); break;
+    default: TB_GRAD(32); break;
+  }
+#undef TB_GRAD
+}
+
+// after the lower GEMM (A stored as packed panels in sA, sum-of-squares in sPartial):
+// V = Linv^T A, then the gradient assembly
+static int gradient_chunk(tb_gp* gp, int acq, double param, const double* xc, int64_t mc, int tiles, int G,
+                          int64_t McPad, double* out_grad) {
+  cudaStream_t st = gp->stream;
+  double* cmu = gp->sMisc.as<double>();
+  acq_partials_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, st>>>(gp->sPartial.as<double>(), G, McPad,
+                                                                    gp->sMean.as<double>(), mc, gp->variance, acq,
+                                                                    param, cmu, cmu + mc);
+  TB_LAUNCHED();
+  const int nkB = gp->NB * (BM / BK);
+  trigemm_kernel<true, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
+      gp->dLinvTP.as<double>(), gp->sA.as<double>(), gp->NB, nkB, G, McPad, nullptr, nullptr, gp->sV.as<double>(),
+      (int64_t)gp->NB * BM);
+  TB_LAUNCHED();
+  const bool gdev = is_device_ptr(out_grad);
+  double* gd = gdev ? out_grad : gp->sGrad.as<double>();
+  switch (gp->kernel) {
+    case TB_RBF: launch_grad_dp<TB_RBF>(gp, xc, mc, gd); break;
+    case TB_MATERN12: launch_grad_dp<TB_MATERN12>(gp, xc, mc, gd); break;
+    case TB_MATERN32: launch_grad_dp<TB_MATERN32>(gp, xc, mc, gd); break;
+    default: launch_grad_dp<TB_MATERN52>(gp, xc, mc, gd); break;
+  }
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  if (!gdev) TB_CUDA(cudaMemcpyAsync(out_grad, gd, sizeof(double) * mc * gp->D, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
 static int run_eval(tb_gp* gp, EvalRequest& rq) {
   TB_CHECK(gp->cache_valid, "posterior cache is not built: call tb_gp_update_posterior_cache first");
   TB_CHECK(rq.M >= 0, "negative candidate count");
@@ -405,6 +486,14 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
   if (!xc_dev) TB_TRY(gp->sXc.reserve(sizeof(double) * chunk_cap * D));
   if (rq.out_vals && !vals_dev) TB_TRY(gp->sVals.reserve(sizeof(double) * chunk_cap));
   if (rq.out_var && !var_dev) TB_TRY(gp->sVar.reserve(sizeof(double) * chunk_cap));
+  if (rq.out_grad) {
+    TB_CHECK(rq.acq >= 0, "gradients need an acquisition kind");
+    TB_TRY(ensure_upper_panels(gp));
+    TB_TRY(gp->sA.reserve((size_t)tiles_cap * gp->NB * (BM / BK) * PANEL * sizeof(double)));
+    TB_TRY(gp->sV.reserve((size_t)chunk_cap * gp->NB * BM * sizeof(double)));
+    TB_TRY(gp->sMisc.reserve(sizeof(double) * 2 * chunk_cap));
+    if (!is_device_ptr(rq.out_grad)) TB_TRY(gp->sGrad.reserve(sizeof(double) * chunk_cap * D));
+  }
   const int tail_blocks_cap = (int)((chunk_cap + 255) / 256);
   if (rq.want_argmax) {
     TB_TRY(gp->sBlkBest.reserve(sizeof(double) * tail_blocks_cap));
@@ -432,8 +521,14 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
       TB_CUDA(cudaEventCreate(&e1));
       TB_CUDA(cudaEventRecord(e0, st));
     }
-    trigemm_sumsq_kernel<<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
-        gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, gp->sPartial.as<double>());
+    if (rq.out_grad)
+      trigemm_kernel<false, EPI_SUMSQ_PACKED><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
+          gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, gp->sPartial.as<double>(),
+          gp->sA.as<double>(), nullptr, 0);
+    else
+      trigemm_kernel<false, EPI_SUMSQ><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
+          gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, gp->sPartial.as<double>(),
+          nullptr, nullptr, 0);
     TB_LAUNCHED();
     if (gp->profile) {
       TB_CUDA(cudaEventRecord(e1, st));
@@ -442,7 +537,7 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
     }
     TB_CUDA(cudaGetLastError());
 
-    if (rq.out_grad) TB_TRY(tb::gradient_chunk(gp, rq.acq, rq.param, xc_chunk, mc, tiles, G, McPad, rq.out_grad + c0 * D));
+    if (rq.out_grad) TB_TRY(gradient_chunk(gp, rq.acq, rq.param, xc_chunk, mc, tiles, G, McPad, rq.out_grad + c0 * D));
 
     double* d_vals = rq.out_vals ? (vals_dev ? rq.out_vals + c0 : gp->sVals.as<double>()) : nullptr;
     double* d_mean = rq.out_mean ? (mean_dev ? rq.out_mean + c0 : nullptr) : nullptr;  // sMean already holds it
@@ -465,7 +560,8 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
     if (rq.out_var && !var_dev)
       TB_CUDA(cudaMemcpyAsync(rq.out_var + c0, gp->sVar.p, sizeof(double) * mc, cudaMemcpyDeviceToHost, st));
     // scratch is reused by the next chunk: host-staged copies must drain first
-    if (!xc_dev || (rq.out_vals && !vals_dev) || (rq.out_mean && !mean_dev) || (rq.out_var && !var_dev))
+    if (!xc_dev || (rq.out_vals && !vals_dev) || (rq.out_mean && !mean_dev) || (rq.out_var && !var_dev) ||
+        (rq.out_grad && !is_device_ptr(rq.out_grad)))
       TB_CUDA(cudaStreamSynchronize(st));
   }
   if (rq.want_argmax) {
@@ -556,6 +652,431 @@ int tb_gp_profile_read(tb_gp* gp, double* trigemm_ms, int64_t* trigemm_launches,
   if (trigemm_ms) *trigemm_ms = gp->prof_ms;
   if (trigemm_launches) *trigemm_launches = gp->prof_launches;
   if (flops) *flops = gp->prof_flops;
+  return 0;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// joint posterior of q-batches: predict_joint / reparam samples / MC-qEI
+// =================================================================================================
+namespace tb {
+
+struct JointRequest {
+  int mode = JOINT_PREDICT;
+  const double* Xc = nullptr;  // [B, q, D]
+  int64_t B = 0;
+  int q = 0;
+  const double* eps = nullptr;  // [q, S] host or device
+  int S = 0;
+  double eta = 0.0, jitter = 0.0;
+  double* out_mean = nullptr;     // [B, q]
+  double* out_cov = nullptr;      // [B, q, q]
+  double* out_samples = nullptr;  // [B, S, q]
+  double* out_qei = nullptr;      // [B]
+};
+
+template <int KIND>
+static int launch_joint(tb_gp* gp, int QT, int blocks, size_t smem, const double* A, int64_t lda, int Nrows,
+                        const double* mean, const double* xc, int64_t nb, const JointRequest& rq, const double* eps_dev,
+                        double* om, double* oc, double* os, double* oq, int* err) {
+  const double* il = gp->dInvLs.as<double>();
+#define TB_JOINT(QTV)                                                                                              \
+  {                                                                                                                \
+    TB_CUDA(cudaFuncSetAttribute(joint_kernel<KIND, QTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    joint_kernel<KIND, QTV><<<blocks, JOINT_WARPS * 32, smem, gp->stream>>>(A, lda, Nrows, mean, xc, il, gp->D, nb, rq.q, \
+        gp->variance, rq.mode, eps_dev, rq.S, rq.eta, rq.jitter, om, oc, os, oq, err);                               \
+  }
+  switch (QT) {
+    case 1: TB_JOINT(1); break;
+    case 2: TB_JOINT(2); break;
+    case 3: TB_JOINT(3); break;
+    default: TB_JOINT(4); break;
+  }
+#undef TB_JOINT
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int run_joint(tb_gp* gp, JointRequest& rq) {
+  TB_CHECK(gp->cache_valid, "posterior cache is not built: call tb_gp_update_posterior_cache first");
+  TB_CHECK(rq.q >= 1 && rq.q <= 32, "batch size q must be in [1, 32]");
+  TB_CHECK(rq.B >= 0, "negative batch count");
+  if (rq.mode != JOINT_PREDICT) {
+    TB_CHECK(rq.S >= 1 && rq.eps, "need S >= 1 base samples");
+    TB_CHECK(rq.jitter >= 0.0, "jitter must be non-negative");
+  }
+  if (rq.B == 0) return 0;
+  TB_CUDA(cudaSetDevice(gp->device));
+  cudaStream_t st = gp->stream;
+  const int D = gp->D, q = rq.q;
+  const int QT = (q + 7) / 8, QP = QT * 8;
+  const int64_t lda = (int64_t)gp->NB * BM;
+
+  const int64_t max_tiles = chunk_tiles(gp);
+  int64_t nbc_cap = std::max<int64_t>(1, (max_tiles * BT) / q);  // whole batches per chunk
+  nbc_cap = std::min<int64_t>(nbc_cap, rq.B);
+  const int64_t cand_cap = nbc_cap * q;
+  const int64_t tiles_cap = (cand_cap + BT - 1) / BT;
+  TB_TRY(gp->sKs.reserve((size_t)tiles_cap * gp->nkc * PANEL * sizeof(double)));
+  TB_TRY(gp->sV.reserve((size_t)tiles_cap * BT * lda * sizeof(double)));  // A plain
+  TB_TRY(gp->sMean.reserve(sizeof(double) * tiles_cap * BT));
+  const bool xc_dev = is_device_ptr(rq.Xc);
+  if (!xc_dev) TB_TRY(gp->sXc.reserve(sizeof(double) * cand_cap * D));
+  const double* eps_dev = nullptr;
+  if (rq.mode != JOINT_PREDICT) {
+    if (is_device_ptr(rq.eps)) {
+      eps_dev = rq.eps;
+    } else {
+      TB_TRY(gp->sMisc.reserve(sizeof(double) * (size_t)q * rq.S + 64));
+      TB_CUDA(cudaMemcpyAsync(gp->sMisc.p, rq.eps, sizeof(double) * (size_t)q * rq.S, cudaMemcpyHostToDevice, st));
+      eps_dev = gp->sMisc.as<double>();
+    }
+  }
+  TB_TRY(gp->sRun.reserve(16));
+  int* err = reinterpret_cast<int*>(gp->sRun.p);
+  TB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+  // host-staged outputs
+  struct Out { double* user; size_t per_batch; tb::DevBuf* buf; };
+  Out outs[4] = {{rq.out_mean, (size_t)q, &gp->sVals}, {rq.out_cov, (size_t)q * q, &gp->sVar},
+                 {rq.out_samples, (size_t)rq.S * q, &gp->sGrad}, {rq.out_qei, 1, &gp->sBlkBest}};
+  bool any_host_out = false;
+  for (auto& o : outs)
+    if (o.user && !is_device_ptr(o.user)) {
+      TB_TRY(o.buf->reserve(sizeof(double) * o.per_batch * nbc_cap));
+      any_host_out = true;
+    }
+  const size_t smem = (size_t)JOINT_WARPS * (QP * QP + QP * D + QP) * sizeof(double);
+
+  for (int64_t b0 = 0; b0 < rq.B; b0 += nbc_cap) {
+    const int64_t nbc = std::min<int64_t>(nbc_cap, rq.B - b0);
+    const int64_t mc = nbc * q;
+    const int tiles = (int)((mc + BT - 1) / BT);
+    const int64_t McPad = (int64_t)tiles * BT;
+    const int G = pick_groups(gp, tiles);
+    const double* xc_chunk;
+    if (xc_dev) {
+      xc_chunk = rq.Xc + b0 * q * D;
+    } else {
+      TB_CUDA(cudaMemcpyAsync(gp->sXc.p, rq.Xc + b0 * q * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, st));
+      xc_chunk = gp->sXc.as<double>();
+    }
+    TB_TRY(launch_kstar(gp, xc_chunk, mc, tiles, gp->sKs.as<double>(), gp->sMean.as<double>()));
+    trigemm_kernel<false, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
+        gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, nullptr, nullptr,
+        gp->sV.as<double>(), lda);
+    TB_LAUNCHED();
+    TB_CUDA(cudaGetLastError());
+    double* dptr[4];
+    for (int i = 0; i < 4; ++i) {
+      Out& o = outs[i];
+      dptr[i] = !o.user ? nullptr : (is_device_ptr(o.user) ? o.user + b0 * o.per_batch : o.buf->as<double>());
+    }
+    const int blocks = (int)((nbc + JOINT_WARPS - 1) / JOINT_WARPS);
+    const int Nrows = (int)lda;
+    switch (gp->kernel) {
+      case TB_RBF: TB_TRY(launch_joint<TB_RBF>(gp, QT, blocks, smem, gp->sV.as<double>(), lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, rq, eps_dev, dptr[0], dptr[1], dptr[2], dptr[3], err)); break;
+      case TB_MATERN12: TB_TRY(launch_joint<TB_MATERN12>(gp, QT, blocks, smem, gp->sV.as<double>(), lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, rq, eps_dev, dptr[0], dptr[1], dptr[2], dptr[3], err)); break;
+      case TB_MATERN32: TB_TRY(launch_joint<TB_MATERN32>(gp, QT, blocks, smem, gp->sV.as<double>(), lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, rq, eps_dev, dptr[0], dptr[1], dptr[2], dptr[3], err)); break;
+      default: TB_TRY(launch_joint<TB_MATERN52>(gp, QT, blocks, smem, gp->sV.as<double>(), lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, rq, eps_dev, dptr[0], dptr[1], dptr[2], dptr[3], err)); break;
+    }
+    for (auto& o : outs)
+      if (o.user && !is_device_ptr(o.user))
+        TB_CUDA(cudaMemcpyAsync(o.user + b0 * o.per_batch, o.buf->p, sizeof(double) * o.per_batch * nbc,
+                                cudaMemcpyDeviceToHost, st));
+    if (!xc_dev || any_host_out) TB_CUDA(cudaStreamSynchronize(st));
+  }
+  int herr = 0;
+  TB_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
+  TB_CHECK(herr == 0, "Cholesky decomposition was not successful. The input might not be valid "
+                      "(covariance + jitter*I of a query batch is not positive definite)");
+  return 0;
+}
+
+}  // namespace tb
+
+extern "C" {
+
+int tb_gp_predict_joint(tb_gp* gp, const void* Xc, int64_t B, int q, void* mean, void* cov) {
+  TB_CHECK(gp && (B == 0 || (Xc && mean && cov)), "tb_gp_predict_joint: null argument");
+  tb::JointRequest rq;
+  rq.mode = JOINT_PREDICT;
+  rq.Xc = (const double*)Xc;
+  rq.B = B;
+  rq.q = q;
+  rq.out_mean = (double*)mean;
+  rq.out_cov = (double*)cov;
+  return tb::run_joint(gp, rq);
+}
+
+int tb_acq_batch_mc_ei(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S, double eta,
+                       double jitter, void* out) {
+  TB_CHECK(gp && (B == 0 || (Xc && eps && out)), "tb_acq_batch_mc_ei: null argument");
+  tb::JointRequest rq;
+  rq.mode = JOINT_QEI;
+  rq.Xc = (const double*)Xc;
+  rq.B = B;
+  rq.q = q;
+  rq.eps = (const double*)eps;
+  rq.S = S;
+  rq.eta = eta;
+  rq.jitter = jitter;
+  rq.out_qei = (double*)out;
+  return tb::run_joint(gp, rq);
+}
+
+int tb_gp_reparam_sample(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S, double jitter,
+                         void* samples) {
+  TB_CHECK(gp && (B == 0 || (Xc && eps && samples)), "tb_gp_reparam_sample: null argument");
+  tb::JointRequest rq;
+  rq.mode = JOINT_SAMPLE;
+  rq.Xc = (const double*)Xc;
+  rq.B = B;
+  rq.q = q;
+  rq.eps = (const double*)eps;
+  rq.S = S;
+  rq.jitter = jitter;
+  rq.out_samples = (double*)samples;
+  return tb::run_joint(gp, rq);
+}
+
+// ---- top-k ---------------------------------------------------------------------------------------
+int tb_topk(int device, int dtype, const void* values, int64_t M, int k, void* top_values, int64_t* top_indices) {
+  TB_CHECK(dtype == TB_F64, "tb_topk: only TB_F64 is implemented in this build");
+  TB_CHECK(values && top_values && top_indices, "tb_topk: null argument");
+  TB_CHECK(M >= 1 && k >= 1 && k <= M, "tb_topk: need 1 <= k <= M");
+  TB_CUDA(cudaSetDevice(device));
+  int64_t P = BIT_TILE;
+  while (P < M) P <<= 1;
+  const bool vdev = is_device_ptr(values), tvdev = is_device_ptr(top_values), tidev = is_device_ptr(top_indices);
+  tb::DevBuf a, vin, tv, ti;
+  int rc = 0;
+  auto body = [&]() -> int {
+    TB_TRY(a.reserve(sizeof(VI) * P));
+    const double* vd = (const double*)values;
+    if (!vdev) {
+      TB_TRY(vin.reserve(sizeof(double) * M));
+      TB_CUDA(cudaMemcpy(vin.p, values, sizeof(double) * M, cudaMemcpyHostToDevice));
+      vd = vin.as<double>();
+    }
+    topk_init_kernel<<<(unsigned)((P + 255) / 256), 256>>>(vd, M, P, a.as<VI>());
+    TB_LAUNCHED();
+    const unsigned nblk = (unsigned)(P / BIT_TILE);
+    bitonic_local_kernel<<<nblk, 1024>>>(a.as<VI>(), 2, BIT_TILE);
+    TB_LAUNCHED();
+    for (int64_t kk = (int64_t)BIT_TILE * 2; kk <= P; kk <<= 1) {
+      for (int64_t j = kk >> 1; j >= BIT_TILE; j >>= 1) {
+        bitonic_global_kernel<<<(unsigned)((P / 2 + 255) / 256), 256>>>(a.as<VI>(), P, kk, j);
+        TB_LAUNCHED();
+      }
+      bitonic_local_kernel<<<nblk, 1024>>>(a.as<VI>(), kk, kk);
+      TB_LAUNCHED();
+    }
+    double* tvd = (double*)top_values;
+    int64_t* tid = top_indices;
+    if (!tvdev) { TB_TRY(tv.reserve(sizeof(double) * k)); tvd = tv.as<double>(); }
+    if (!tidev) { TB_TRY(ti.reserve(sizeof(int64_t) * k)); tid = ti.as<int64_t>(); }
+    topk_emit_kernel<<<(k + 255) / 256, 256>>>(a.as<VI>(), k, tvd, tid);
+    TB_LAUNCHED();
+    TB_CUDA(cudaGetLastError());
+    if (!tvdev) TB_CUDA(cudaMemcpy(top_values, tvd, sizeof(double) * k, cudaMemcpyDeviceToHost));
+    if (!tidev) TB_CUDA(cudaMemcpy(top_indices, tid, sizeof(int64_t) * k, cudaMemcpyDeviceToHost));
+    TB_CUDA(cudaDeviceSynchronize());
+    return 0;
+  };
+  rc = body();
+  a.release(); vin.release(); tv.release(); ti.release();
+  return rc;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// random-Fourier-feature trajectories
+// =================================================================================================
+struct tb_rff {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int F = 0, D = 0, DP = 0, nb = 0;
+  double variance = 1.0, mean_const = 0.0;
+  tb::DevBuf dW, dB, dTheta, dInvLs, sXc, sOut, sBlkBest, sBlkIdx, sRunV, sRunI;
+};
+
+extern "C" {
+
+int tb_rff_create(tb_rff** out, int device) {
+  TB_CHECK(out, "tb_rff_create: null output");
+  int n = 0;
+  TB_TRY(tb_device_count(&n));
+  TB_CHECK(n > 0, "tb_rff_create: no CUDA device visible (this library has no CPU fallback)");
+  TB_CHECK(device >= 0 && device < n, "tb_rff_create: device index out of range");
+  TB_CUDA(cudaSetDevice(device));
+  tb_rff* r = new tb_rff();
+  r->device = device;
+  TB_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+  *out = r;
+  return 0;
+}
+
+int tb_rff_destroy(tb_rff* r) {
+  if (!r) return 0;
+  cudaSetDevice(r->device);
+  cudaStreamSynchronize(r->stream);
+  for (tb::DevBuf* b : {&r->dW, &r->dB, &r->dTheta, &r->dInvLs, &r->sXc, &r->sOut, &r->sBlkBest, &r->sBlkIdx,
+                        &r->sRunV, &r->sRunI})
+    b->release();
+  cudaStreamDestroy(r->stream);
+  delete r;
+  return 0;
+}
+
+int tb_rff_set(tb_rff* r, const double* W, const double* b, int F, int D, const double* lengthscales,
+               double variance, double mean_const) {
+  TB_CHECK(r && W && b && lengthscales, "tb_rff_set: null argument");
+  TB_CHECK(F >= 1, "tb_rff_set: need at least one feature");
+  TB_CHECK(D >= 1 && tb::pick_dp(D) > 0, "tb_rff_set: input dimension must be in [1, 32]");
+  TB_CHECK(variance > 0.0, "tb_rff_set: kernel variance must be positive");
+  TB_CUDA(cudaSetDevice(r->device));
+  const int DP = tb::pick_dp(D);
+  std::vector<double> Wp((size_t)F * DP, 0.0), il(DP, 0.0);
+  for (int f = 0; f < F; ++f)
+    for (int d = 0; d < D; ++d) Wp[(size_t)f * DP + d] = W[(size_t)f * D + d];
+  for (int d = 0; d < D; ++d) {
+    TB_CHECK(lengthscales[d] > 0.0, "tb_rff_set: lengthscales must be positive");
+    il[d] = 1.0 / lengthscales[d];
+  }
+  TB_TRY(r->dW.reserve(sizeof(double) * Wp.size()));
+  TB_TRY(r->dB.reserve(sizeof(double) * F));
+  TB_TRY(r->dInvLs.reserve(sizeof(double) * DP));
+  TB_CUDA(cudaMemcpy(r->dW.p, Wp.data(), sizeof(double) * Wp.size(), cudaMemcpyHostToDevice));
+  TB_CUDA(cudaMemcpy(r->dB.p, b, sizeof(double) * F, cudaMemcpyHostToDevice));
+  TB_CUDA(cudaMemcpy(r->dInvLs.p, il.data(), sizeof(double) * DP, cudaMemcpyHostToDevice));
+  r->F = F;
+  r->D = D;
+  r->DP = DP;
+  r->variance = variance;
+  r->mean_const = mean_const;
+  r->nb = 0;
+  return 0;
+}
+
+int tb_rff_set_theta(tb_rff* r, const double* theta, int nb) {
+  TB_CHECK(r && theta, "tb_rff_set_theta: null argument");
+  TB_CHECK(r->F > 0, "tb_rff_set_theta: call tb_rff_set first");
+  TB_CHECK(nb >= 1, "tb_rff_set_theta: need at least one trajectory");
+  TB_CUDA(cudaSetDevice(r->device));
+  TB_TRY(r->dTheta.reserve(sizeof(double) * (size_t)nb * r->F));
+  TB_CUDA(cudaMemcpy(r->dTheta.p, theta, sizeof(double) * (size_t)nb * r->F, cudaMemcpyDefault));
+  r->nb = nb;
+  return 0;
+}
+
+}  // extern "C"
+
+namespace tb {
+template <int DP>
+static int launch_rff(tb_rff* r, int nbt, int blocks, const double* xc, int b0, int64_t mc, int64_t idx0, double scale,
+                      double* out, double* bb, int64_t* bi) {
+  const size_t smem = sizeof(double) * ((size_t)RFF_FCHUNK * DP + RFF_FCHUNK + (size_t)nbt * RFF_FCHUNK);
+#define TB_RFF(NBT)                                                                                              \
+  {                                                                                                              \
+    TB_CUDA(cudaFuncSetAttribute(rff_eval_kernel<DP, NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    rff_eval_kernel<DP, NBT><<<blocks, RFF_THREADS, smem, r->stream>>>(r->dW.as<double>(), r->dB.as<double>(),      \
+        r->dTheta.as<double>(), xc, r->dInvLs.as<double>(), r->D, r->F, r->nb, b0, mc, idx0, scale, r->mean_const,  \
+        out, bb, bi);                                                                                             \
+  }
+  switch (nbt) {
+    case 1: TB_RFF(1); break;
+    case 2: TB_RFF(2); break;
+    default: TB_RFF(4); break;
+  }
+#undef TB_RFF
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace tb
+
+extern "C" {
+
+int tb_rff_eval(tb_rff* r, const void* Xc, int64_t M, void* out, double* min_value, int64_t* min_index) {
+  TB_CHECK(r && (M == 0 || Xc), "tb_rff_eval: null argument");
+  TB_CHECK(r->F > 0 && r->nb > 0, "tb_rff_eval: features and theta must be set first");
+  TB_CHECK((min_value == nullptr) == (min_index == nullptr), "tb_rff_eval: min_value and min_index go together");
+  TB_CHECK(M > 0 || !min_value, "tb_rff_eval: argmin over an empty candidate set");
+  if (M == 0) return 0;
+  TB_CUDA(cudaSetDevice(r->device));
+  cudaStream_t st = r->stream;
+  const int D = r->D, nb = r->nb;
+  const double scale = std::sqrt(2.0 * r->variance / (double)r->F);
+  const bool xdev = is_device_ptr(Xc), odev = is_device_ptr(out);
+  const int64_t chunk = std::min<int64_t>(M, (int64_t)1 << 22);
+  const int blocks_cap = (int)((chunk + RFF_THREADS - 1) / RFF_THREADS);
+  if (!xdev) TB_TRY(r->sXc.reserve(sizeof(double) * chunk * D));
+  if (out && !odev) TB_TRY(r->sOut.reserve(sizeof(double) * chunk * nb));
+  const bool want_min = min_value != nullptr;
+  if (want_min) {
+    TB_TRY(r->sBlkBest.reserve(sizeof(double) * (size_t)nb * blocks_cap));
+    TB_TRY(r->sBlkIdx.reserve(sizeof(int64_t) * (size_t)nb * blocks_cap));
+    TB_TRY(r->sRunV.reserve(sizeof(double) * nb));
+    TB_TRY(r->sRunI.reserve(sizeof(int64_t) * nb));
+    std::vector<double> iv(nb, -DBL_MAX);
+    std::vector<int64_t> ii(nb, INT64_MAX);
+    TB_CUDA(cudaMemcpyAsync(r->sRunV.p, iv.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaMemcpyAsync(r->sRunI.p, ii.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+  }
+  for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+    const int64_t mc = std::min<int64_t>(chunk, M - c0);
+    const int blocks = (int)((mc + RFF_THREADS - 1) / RFF_THREADS);
+    const double* xc = (const double*)Xc + c0 * D;
+    if (!xdev) {
+      TB_CUDA(cudaMemcpyAsync(r->sXc.p, xc, sizeof(double) * mc * D, cudaMemcpyHostToDevice, st));
+      xc = r->sXc.as<double>();
+    }
+    double* od = out ? (odev ? (double*)out + c0 * nb : r->sOut.as<double>()) : nullptr;
+    for (int b0 = 0; b0 < nb; b0 += 4) {
+      const int rem = nb - b0;
+      const int nbt = rem >= 3 ? 4 : rem;  // kernel handles up to nbt trajectories per pass
+      double* bb = want_min ? r->sBlkBest.as<double>() : nullptr;
+      int64_t* bi = want_min ? r->sBlkIdx.as<int64_t>() : nullptr;
+#define TB_RFF_DP(DPV) TB_TRY((tb::launch_rff<DPV>(r, nbt, blocks, xc, b0, mc, c0, scale, od, bb, bi)))
+      switch (r->DP) {
+        case 2: TB_RFF_DP(2); break;
+        case 4: TB_RFF_DP(4); break;
+        case 6: TB_RFF_DP(6); break;
+        case 8: TB_RFF_DP(8); break;
+        case 10: TB_RFF_DP(10); break;
+        case 12: TB_RFF_DP(12); break;
+        case 16: TB_RFF_DP(16); break;
+        case 20: TB_RFF_DP(20); break;
+        case 24: TB_RFF_DP(24); break;
+        default: TB_RFF_DP(32); break;
+      }
+#undef TB_RFF_DP
+    }
+    if (want_min) {
+      // blk arrays are laid out [nb][blocks of this launch]
+      rff_fold_kernel<<<nb, 256, 0, st>>>(r->sBlkBest.as<double>(), r->sBlkIdx.as<int64_t>(), blocks,
+                                          r->sRunV.as<double>(), r->sRunI.as<int64_t>());
+      TB_LAUNCHED();
+    }
+    if (out && !odev)
+      TB_CUDA(cudaMemcpyAsync((double*)out + c0 * nb, r->sOut.p, sizeof(double) * mc * nb, cudaMemcpyDeviceToHost, st));
+    if (!xdev || (out && !odev)) TB_CUDA(cudaStreamSynchronize(st));
+  }
+  if (want_min) {
+    std::vector<double> hv(nb);
+    TB_CUDA(cudaMemcpyAsync(hv.data(), r->sRunV.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaMemcpyAsync(min_index, r->sRunI.p, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < nb; ++b) min_value[b] = -hv[b];
+  }
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
   return 0;
 }
 
