@@ -1,0 +1,105 @@
+"""GPU parity: predict_joint, BatchReparametrizationSampler, BatchMonteCarloExpectedImprovement (C3)."""
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as o
+from tests.util import candidates, model_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,D,q", [(20, 2, 1), (20, 2, 3), (300, 6, 8), (300, 6, 5), (128, 6, 16), (300, 10, 11)])
+def test_predict_joint_matches_oracle(N, D, q):
+    obj = o.branin if D == 2 else (o.hartmann_6 if D == 6 else o.ackley)
+    om, nm = model_pair(obj, N, D)
+    X = candidates(37 * q, D).reshape(37, q, D)
+    mean, cov = nm.predict_joint(X)
+    omean, ocov = o.predict_joint(om, X)
+    assert mean.shape == (37, q, 1) and cov.shape == (37, 1, q, q)
+    np.testing.assert_allclose(mean, omean, rtol=1e-9, atol=1e-9 * np.sqrt(om.variance))
+    np.testing.assert_allclose(cov, ocov, rtol=0, atol=1e-9 * om.variance)
+    # diagonal agrees with the marginal predict (clip included)
+    _, var = nm.predict(X.reshape(-1, D))
+    np.testing.assert_allclose(np.diagonal(cov[:, 0], axis1=-2, axis2=-1).reshape(-1, 1), var, rtol=0, atol=1e-10 * om.variance)
+
+
+def test_predict_joint_leading_dims():
+    om, nm = model_pair(o.hartmann_6, 64, 6)
+    X = candidates(2 * 3 * 4, 6).reshape(2, 3, 4, 6)
+    mean, cov = nm.predict_joint(X)
+    assert mean.shape == (2, 3, 4, 1) and cov.shape == (2, 3, 1, 4, 4)
+    omean, ocov = o.predict_joint(om, X)
+    np.testing.assert_allclose(cov, ocov, rtol=0, atol=1e-9 * om.variance)
+
+
+@pytest.mark.parametrize("q,S", [(1, 64), (4, 100), (8, 512)])
+def test_reparam_sampler_matches_oracle(q, S):
+    om, nm = model_pair(o.hartmann_6, 200, 6)
+    X = candidates(21 * q, 6).reshape(21, q, 6)
+    sampler = nm.reparam_sampler(S)
+    eps = np.random.default_rng(3).standard_normal((q, S))
+    sampler.set_eps(eps)
+    samples = sampler.sample(X, jitter=1e-6)
+    assert samples.shape == (21, S, q, 1)
+    omean, ocov = o.predict_joint(om, X)
+    osamples = o.batch_reparam_sample(omean, ocov, eps[None], 1e-6)
+    np.testing.assert_allclose(samples, osamples, rtol=1e-7, atol=1e-7 * np.sqrt(om.variance))
+    # repeatability + fixed batch size (sampler.py:329-352)
+    np.testing.assert_array_equal(sampler.sample(X), samples)
+    with pytest.raises(ValueError):
+        sampler.sample(candidates(3 * (q + 1), 6).reshape(3, q + 1, 6))
+
+
+def test_reparam_sampler_moments():
+    # reference test restated (tests/unit/models/gpflow/test_sampler.py:297-326): sample mean / cov
+    # match predict_joint within rtol 0.02 / 0.04 (here: absolute tolerances scaled by the prior variance)
+    om, nm = model_pair(o.hartmann_6, 100, 6)
+    X = candidates(3, 6).reshape(1, 3, 6)
+    sampler = nm.reparam_sampler(20000)
+    s = sampler.sample(X)[0, :, :, 0]
+    mean, cov = nm.predict_joint(X)
+    np.testing.assert_allclose(s.mean(0), mean[0, :, 0], atol=0.02 * np.sqrt(om.variance))
+    np.testing.assert_allclose(np.cov(s.T), cov[0, 0] + 1e-6 * np.eye(3), atol=0.04 * om.variance)
+
+
+@pytest.mark.parametrize("N,D,q,S", [(300, 6, 8, 512), (300, 6, 3, 100), (1024, 10, 8, 512)])
+def test_batch_monte_carlo_expected_improvement(N, D, q, S):
+    from trieste_b200 import Dataset
+    from trieste_b200.acquisition import BatchMonteCarloExpectedImprovement
+
+    obj = o.hartmann_6 if D == 6 else o.ackley
+    om, nm = model_pair(obj, N, D)
+    builder = BatchMonteCarloExpectedImprovement(S, jitter=1e-6)
+    fn = builder.prepare_acquisition_function(nm, Dataset(om.X, om.y))
+    eps = np.random.default_rng(3).standard_normal((q, S))
+    fn._sampler.set_eps(eps)
+    X = candidates(257 * q, D).reshape(257, q, D)
+    out = fn(X)
+    ref = o.batch_monte_carlo_expected_improvement(om, X, eps[None], o.ei_eta(om), 1e-6)
+    assert out.shape == (257, 1)
+    np.testing.assert_allclose(out, ref, rtol=1e-6, atol=1e-12)
+    fn2 = builder.update_acquisition_function(fn, nm, Dataset(om.X, om.y))
+    assert fn2 is fn
+
+
+def test_qei_q1_reproduces_ei():
+    # reference known answer (test_function.py:1359-1371): qEI at q=1 ~ EI within rtol 0.06
+    from trieste_b200 import Dataset
+    from trieste_b200.acquisition import BatchMonteCarloExpectedImprovement, ExpectedImprovement
+
+    om, nm = model_pair(o.branin, 20, 2)
+    ds = Dataset(om.X, om.y)
+    X = candidates(200, 2)
+    ei = ExpectedImprovement().prepare_acquisition_function(nm, ds)(X[:, None, :])
+    qei = BatchMonteCarloExpectedImprovement(40000).prepare_acquisition_function(nm, ds)(X[:, None, :])
+    big = ei[:, 0] > 0.05 * ei.max()  # MC noise dominates where improvement events are rare
+    np.testing.assert_allclose(qei[big], ei[big], rtol=0.06)
+
+
+def test_builder_argument_checks():
+    from trieste_b200.acquisition import BatchMonteCarloExpectedImprovement
+
+    with pytest.raises(ValueError):
+        BatchMonteCarloExpectedImprovement(0)
+    with pytest.raises(ValueError):
+        BatchMonteCarloExpectedImprovement(10, jitter=-1.0)

@@ -1,0 +1,221 @@
+"""CPU: host-side logic that needs no GPU — containers, search spaces, the vectorised L-BFGS, the
+multi-rank argmax exchange (gloo, world_size 2)."""
+import os
+
+import numpy as np
+import pytest
+
+from trieste_b200.acquisition.optimizer import (
+    FailedOptimizationError,
+    _get_max_discrete_points,
+    _perform_parallel_continuous_optimization,
+    batchify_joint,
+    generate_random_search_optimizer,
+    sample_from_space,
+)
+from trieste_b200.data import Dataset
+from trieste_b200.parallel import merge_best, shard_bounds
+from trieste_b200.space import Box, DiscreteSearchSpace
+
+
+class Quadratic:
+    """f(x) = -sum a (x - c)^2 with analytic gradient: stands in for an acquisition function."""
+
+    def __init__(self, c, a=None):
+        self.c = np.asarray(c, dtype=float)
+        self.a = np.ones_like(self.c) if a is None else np.asarray(a, dtype=float)
+        self.calls = 0
+
+    def __call__(self, x):
+        x = np.asarray(x)
+        return -(self.a * (x[..., 0, :] - self.c) ** 2).sum(-1, keepdims=True)
+
+    def value_and_gradient(self, x):
+        self.calls += 1
+        d = x[:, 0, :] - self.c
+        return -(self.a * d * d).sum(-1, keepdims=True), (-2 * self.a * d)[:, None, :]
+
+
+def test_dataset_shapes_and_concat():
+    d = Dataset(np.zeros((3, 2)), np.ones((3, 1)))
+    assert len(d + d) == 6
+    with pytest.raises(ValueError):
+        Dataset(np.zeros((3, 2)), np.ones((4, 1)))
+    with pytest.raises(ValueError):
+        Dataset(np.zeros(3), np.ones(3))
+
+
+def test_box_sampling_and_power():
+    b = Box([0.0, -1.0], [1.0, 3.0])
+    s = b.sample(1000, seed=0)
+    assert s.shape == (1000, 2) and b.contains(s).all()
+    assert (b**3).dimension == 6
+    with pytest.raises(ValueError):
+        Box([1.0], [0.0])
+    with pytest.raises(ValueError):
+        b.sample(-1)
+    np.testing.assert_array_equal(b.sample(5, seed=3), b.sample(5, seed=3))
+
+
+def test_random_search_generic_path_and_vectorised():
+    space = Box([0.0, 0.0], [1.0, 1.0])
+    f = Quadratic([0.25, 0.75])
+    pt = generate_random_search_optimizer(4000)(space, f)
+    assert pt.shape == (1, 2) and np.abs(pt[0] - [0.25, 0.75]).max() < 0.05
+
+    def vec(x):  # [N, 2, D] -> [N, 2]
+        return np.stack([-((x[:, 0] - 0.2) ** 2).sum(-1), -((x[:, 1] - 0.8) ** 2).sum(-1)], axis=1)
+
+    pts = _get_max_discrete_points(space.sample(4000, seed=1)[:, None, :], (vec, 2))
+    assert pts.shape == (2, 2) and np.abs(pts[0] - 0.2).max() < 0.05 and np.abs(pts[1] - 0.8).max() < 0.05
+    with pytest.raises(ValueError):
+        _get_max_discrete_points(space.sample(10)[:, None, :], (lambda x: np.zeros((10, 3)), 2))
+    d = DiscreteSearchSpace(np.array([[0.0, 0.0], [0.3, 0.7], [1.0, 1.0]]))
+    from trieste_b200.acquisition.optimizer import optimize_discrete
+
+    np.testing.assert_array_equal(optimize_discrete(d, f), [[0.3, 0.7]])
+
+
+def test_first_max_tie_rule():
+    pts = np.array([[0.0], [1.0], [2.0], [3.0]])[:, None, :]
+    best = _get_max_discrete_points(pts, lambda x: np.array([[1.0], [5.0], [5.0], [0.0]]))
+    np.testing.assert_array_equal(best, [[1.0]])
+
+
+def test_sample_from_space_chunks():
+    space = Box([0.0], [1.0])
+    chunks = list(sample_from_space(10, batch_size=4)(space))
+    assert [c.shape[0] for c in chunks] == [4, 4, 2]
+    with pytest.raises(ValueError):
+        sample_from_space(0)
+
+
+@pytest.mark.parametrize("D", [2, 6, 20])
+def test_vectorised_lbfgs_interior_and_bound_optima(D):
+    rng = np.random.default_rng(D)
+    c = rng.uniform(-0.3, 1.3, size=D)  # some optima outside the unit box -> active bounds
+    a = rng.uniform(0.5, 50.0, size=D)
+    f = Quadratic(c, a)
+    x0 = rng.uniform(size=(64, 1, D))
+    success, fun, xs, nfev = _perform_parallel_continuous_optimization(f, np.zeros(D), np.ones(D), x0, {})
+    assert success.all()
+    np.testing.assert_allclose(xs[:, 0, :], np.broadcast_to(np.clip(c, 0, 1), (64, D)), atol=1e-4)
+    assert nfev.max() < 60
+    # every iteration is ONE batched evaluation for all active starts, not one per start
+    assert f.calls < 80
+
+
+def test_lbfgs_rosenbrock_from_many_starts():
+    class Rosen:
+        def __call__(self, x):
+            return self.value_and_gradient(np.asarray(x))[0]
+
+        def value_and_gradient(self, x):
+            u, v = x[:, 0, 0], x[:, 0, 1]
+            val = -((1 - u) ** 2 + 100 * (v - u * u) ** 2)
+            g = -np.stack([-2 * (1 - u) - 400 * u * (v - u * u), 200 * (v - u * u)], axis=1)
+            return val[:, None], g[:, None, :]
+
+    x0 = np.random.default_rng(0).uniform(-1.5, 1.5, size=(32, 1, 2))
+    success, fun, xs, _ = _perform_parallel_continuous_optimization(Rosen(), np.full(2, -2.0), np.full(2, 2.0), x0, {})
+    assert success.mean() > 0.9
+    np.testing.assert_allclose(xs[success[:, 0], 0, :], 1.0, atol=1e-3)
+
+
+def test_failed_optimisation_raises():
+    from trieste_b200.acquisition.optimizer import generate_continuous_optimizer
+
+    class Bad:
+        def __call__(self, x):
+            return np.full(np.shape(x)[:-2] + (1,), np.nan)
+
+        def value_and_gradient(self, x):
+            return np.full((x.shape[0], 1), np.nan), np.full(x.shape, np.nan)
+
+    import trieste_b200.acquisition.optimizer as opt
+
+    orig = opt.generate_initial_points
+    opt.generate_initial_points = lambda k, s, space, fn, vectorization=1: space.sample(k)[:, None, :]
+    try:
+        with pytest.raises(FailedOptimizationError):
+            generate_continuous_optimizer(10, 2, num_recovery_runs=1)(Box([0.0], [1.0]), Bad())
+    finally:
+        opt.generate_initial_points = orig
+    with pytest.raises(ValueError):
+        generate_continuous_optimizer(5, 10)
+
+
+def test_batchify_joint_reshapes():
+    space = Box([0.0, 0.0], [1.0, 1.0])
+
+    def joint(x):  # [..., q=3, D=2] -> [..., 1]: wants the 3 points at 0.1, 0.5, 0.9
+        t = np.array([0.1, 0.5, 0.9])[:, None]
+        return -((x - t) ** 2).sum((-1, -2))[..., None]
+
+    opt = batchify_joint(generate_random_search_optimizer(20000), 3)
+    pts = opt(space, joint)
+    assert pts.shape == (3, 2)
+    assert np.abs(pts - np.array([0.1, 0.5, 0.9])[:, None]).max() < 0.2
+
+
+def test_shard_bounds_partition():
+    for total in [0, 1, 7, 8, 1000003]:
+        for world in [1, 2, 3, 8]:
+            cuts = [shard_bounds(total, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == total
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+def test_merge_best_tie_and_nan_rules():
+    assert merge_best([(1.0, 5), (3.0, 9), (3.0, 2), (float("nan"), 0)]) == (3.0, 2)
+    assert merge_best([(-np.inf, -1), (0.5, 7)]) == (0.5, 7)
+    assert merge_best([]) == (-np.inf, -1)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from trieste_b200.parallel import sharded_argmax
+
+        pts = np.random.default_rng(0).uniform(size=(1001, 3))
+        vals = -((pts - 0.5) ** 2).sum(-1)
+        vals[[10, 900]] = 1.0  # a tie straddling the two shards: global index 10 must win everywhere
+
+        class Fn:  # stands in for the fused GPU argmax of one rank's shard
+            def fused_argmax(self, p):
+                lo = int(np.where((pts == p[0]).all(1))[0][0])
+                v = vals[lo : lo + len(p)]
+                i = int(np.argmax(v))
+                return i, float(v[i])
+
+        pt, bv, bi = sharded_argmax(Fn(), pts)
+        q.put((rank, bi, bv, pt.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_argmax_gloo_world2():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pts = np.random.default_rng(0).uniform(size=(1001, 3))
+    for rank, bi, bv, pt in res:
+        assert bi == 10 and bv == 1.0
+        np.testing.assert_allclose(pt[0], pts[10])

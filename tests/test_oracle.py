@@ -1,0 +1,151 @@
+"""CPU: pins the oracle (oracle/gp_oracle.py) against (i) the committed scikit-learn fixtures and
+(ii) restatements of the reference's own model-independent known-answer tests."""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as o
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "gpr_sklearn_*.npz")))
+
+
+def _load(path):
+    z = np.load(path)
+    om = o.build_model(str(z["kind"]), z["X"], z["y"], float(z["variance"]), z["lengthscales"], float(z["noise"]), float(z["mean_const"]))
+    return z, om
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[12:-4] for p in GOLDEN])
+def test_oracle_matches_sklearn_fixture(path):
+    z, om = _load(path)
+    mean, var = o.predict_f(om, z["Xq"])
+    np.testing.assert_allclose(mean[:, 0], z["mean"], rtol=1e-9, atol=1e-9 * math.sqrt(om.variance))
+    np.testing.assert_allclose(var[:, 0], z["var"], rtol=0, atol=1e-9 * om.variance)
+    _, cov = o.predict_f(om, z["Xq"][:8], full_cov=True)
+    np.testing.assert_allclose(cov, z["cov"][:8, :8], rtol=0, atol=1e-9 * om.variance)
+
+
+def test_golden_fixtures_present():
+    assert len(GOLDEN) >= 4
+
+
+def test_predict_clips_variance_and_joint_matches_marginal():
+    om = o.synthetic_model(o.branin, 20, 2, noise=1e-7)
+    mean, var = o.predict(om, om.X)
+    assert var.min() >= 1e-12
+    X = np.random.default_rng(1).uniform(size=(5, 3, 2))
+    jm, jc = o.predict_joint(om, X)
+    mm, mv = o.predict(om, X.reshape(-1, 2))
+    assert jm.shape == (5, 3, 1) and jc.shape == (5, 1, 3, 3)
+    np.testing.assert_allclose(jm.reshape(-1, 1), mm, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(np.diagonal(jc[:, 0], axis1=-2, axis2=-1).reshape(-1, 1), mv, rtol=0, atol=1e-10 * om.variance)
+
+
+def test_lcb_closed_form():
+    # tests/unit/acquisition/function/test_function.py:786-790: with mean = sum x^2 and var = 1, LCB = x^2 - beta
+    x = np.linspace(-3, 3, 13)[:, None]
+    mean, var = (x**2).sum(-1, keepdims=True), np.ones((13, 1))
+    np.testing.assert_allclose(o.lower_confidence_bound(mean, var, 1.96), x**2 - 1.96, rtol=1e-12)
+    with pytest.raises(ValueError):
+        o.lower_confidence_bound(mean, var, -1.0)
+
+
+@pytest.mark.parametrize("variance_scale", [0.1, 1.0, 10.0, 100.0])
+@pytest.mark.parametrize("best", [0.0, 1.0, -2.0])
+def test_expected_improvement_vs_monte_carlo(variance_scale, best):
+    # test_function.py:290-332 restated: analytic EI vs a Monte-Carlo estimate, rtol 0.01
+    rng = np.random.default_rng(0)
+    mean = np.linspace(-1.5, 1.5, 7)[:, None]
+    var = np.full_like(mean, variance_scale)
+    ei = o.expected_improvement(mean, var, best)
+    samples = mean + np.sqrt(var) * rng.standard_normal((7, 400_000))
+    mc = np.maximum(best - samples, 0.0).mean(-1, keepdims=True)
+    np.testing.assert_allclose(ei, mc, rtol=0.02, atol=2e-3 * math.sqrt(variance_scale))
+
+
+def test_log_ei_matches_log_of_ei_and_stays_finite():
+    mean = np.linspace(-3, 40, 200)[:, None]
+    var = np.full_like(mean, 0.5)
+    ei = o.expected_improvement(mean, var, 0.0)
+    lei = o.log_expected_improvement(mean, var, 0.0)
+    ok = ei[:, 0] > 1e-300
+    np.testing.assert_allclose(lei[ok], np.log(ei[ok]), rtol=1e-7, atol=1e-7)
+    assert np.all(np.isfinite(lei)) and np.all(np.diff(lei[:, 0]) < 0)
+
+
+def test_ei_eta_is_min_posterior_mean_and_gradient_fd():
+    om = o.synthetic_model(o.hartmann_6, 60, 6)
+    eta = o.ei_eta(om)
+    assert eta == o.predict(om, om.X)[0].min()
+    Xq = np.random.default_rng(2).uniform(size=(4, 6))
+    _, g = o.ei_gradient(om, Xq, eta)
+    h = 1e-6
+    for d in range(6):
+        e = np.zeros(6)
+        e[d] = h
+        fd = (o.expected_improvement(*o.predict(om, Xq + e), eta) - o.expected_improvement(*o.predict(om, Xq - e), eta)) / (2 * h)
+        np.testing.assert_allclose(g[:, d], fd[:, 0], rtol=1e-4, atol=1e-9 * np.abs(g).max())
+
+
+def test_qei_q1_matches_ei_and_mvn_samples():
+    # test_function.py:1359-1394 restated
+    om = o.synthetic_model(o.branin, 20, 2)
+    eta = o.ei_eta(om)
+    X = np.random.default_rng(1).uniform(size=(30, 1, 2))
+    eps = np.random.default_rng(3).standard_normal((1, 1, 50_000))
+    qei = o.batch_monte_carlo_expected_improvement(om, X, eps, eta)
+    ei = o.expected_improvement(*o.predict(om, X[:, 0]), eta)
+    big = ei[:, 0] > 0.05 * ei.max()  # MC noise dominates where improvement events are rare
+    np.testing.assert_allclose(qei[big], ei[big], rtol=0.06)
+    # q = 3 against direct multivariate-normal sampling
+    Xb = np.random.default_rng(4).uniform(size=(1, 3, 2))
+    mean, cov = o.predict_joint(om, Xb)
+    mvn = np.random.default_rng(5).multivariate_normal(mean[0, :, 0], cov[0, 0], size=200_000)
+    direct = np.maximum(eta - mvn.min(-1), 0).mean()
+    eps3 = np.random.default_rng(6).standard_normal((1, 3, 200_000))
+    np.testing.assert_allclose(o.batch_monte_carlo_expected_improvement(om, Xb, eps3, eta)[0, 0], direct, rtol=0.05, atol=1e-4)
+
+
+def test_rff_design_equals_gram_and_moments():
+    # tests/unit/models/gpflow/test_sampler.py:530-542 (design == gram, rtol 0.02) and
+    # test_models.py:638-681 (trajectory moments vs predict)
+    om = o.synthetic_model(o.hartmann_6, 100, 6, kind="rbf")
+    rng = np.random.default_rng(0)
+    W, b = o.rff_draw("rbf", 100, 6, rng)
+    # force both routes on the same features: n = 100, F = 100 -> gram; drop one data point -> design
+    mg, cg = o.rff_theta_posterior(om, W, b)
+    om2 = o.build_model(om.kind, np.concatenate([om.X, om.X[:1] + 1e-3]), np.concatenate([om.y, om.y[:1]]), om.variance,
+                        om.lengthscales, om.noise, om.mean_const)
+    md, cd = o.rff_theta_posterior(om2, W, b)  # F < n: design space
+    assert np.abs(mg - md).max() < 0.05 * np.abs(mg).max() + 0.05
+    # moments, in the reference test's own setting: 1-D, x = 0..4, y = 3x + noise, Matern32(1, 1), 1000 features
+    x = np.arange(5.0).reshape(-1, 1)
+    y = 3.0 * x + 0.1 * rng.standard_normal((5, 1))
+    for noise_var in [1e-5, 1e-1]:
+        m1 = o.build_model("matern32", x, y, 1.0, np.ones(1), noise_var, 0.0)
+        W2, b2 = o.rff_draw("matern32", 1000, 1, rng)
+        tm, tc = o.rff_theta_posterior(m1, W2, b2)
+        thetas = tm + rng.standard_normal((400, 1000)) @ tc.T
+        xp = np.array([[1.0], [2.0], [3.0], [1.5], [2.5], [3.5]])
+        f = o.rff_trajectory(np.repeat(xp[:, None, :], 400, 1), W2, b2, thetas, 1.0, np.ones(1), 0.0)[:, :, 0]
+        mean, var = o.predict(m1, xp)
+        np.testing.assert_allclose(f.mean(1) + 1.0, mean[:, 0] + 1.0, rtol=0.1)
+        np.testing.assert_allclose(f.var(1)[3:], var[3:, 0], rtol=0.5, atol=1e-3)
+
+
+def test_topk_and_argmax_semantics():
+    v = np.array([1.0, 3.0, 3.0, -1.0, 3.0, 2.0])
+    assert o.argmax_first(v) == 1
+    tv, ti = o.top_k(v, 4)
+    np.testing.assert_array_equal(ti, [1, 2, 4, 5])
+    np.testing.assert_array_equal(tv, [3.0, 3.0, 3.0, 2.0])
+
+
+def test_objectives_known_minima():
+    # trieste/objectives/single_objectives.py minimiser tables
+    np.testing.assert_allclose(o.hartmann_6(np.array([[0.20169, 0.150011, 0.476874, 0.275332, 0.311652, 0.6573]])), [[-3.32237]], atol=1e-5)
+    np.testing.assert_allclose(o.ackley(np.full((1, 5), 0.5)), [[0.0]], atol=1e-12)
+    np.testing.assert_allclose(o.branin(np.array([[0.5427728, 0.1516667]])), [[0.397887]], atol=1e-5)
