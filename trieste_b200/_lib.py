@@ -110,18 +110,24 @@ def is_torch(x) -> bool:
     return type(x).__module__.split(".")[0] == "torch"
 
 
-def as_f64_contiguous(x):
-    """Return (array_like, pointer).  numpy in -> numpy float64 C-contiguous; torch.cuda in -> same."""
+def as_contiguous(x, dtype=np.float64):
+    """Return (array_like, pointer) in ``dtype`` (np.float64 / np.float32).  numpy in -> numpy
+    C-contiguous; torch.cuda in -> contiguous device tensor (zero-copy when already conforming)."""
     if is_torch(x):
         import torch
 
+        tdt = torch.float64 if dtype == np.float64 else torch.float32
         t = x.detach()
-        if t.dtype != torch.float64:
-            t = t.to(torch.float64)
+        if t.dtype != tdt:
+            t = t.to(tdt)
         t = t.contiguous()
         return t, t.data_ptr()
-    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    a = np.ascontiguousarray(np.asarray(x, dtype=dtype))
     return a, a.ctypes.data
+
+
+def as_f64_contiguous(x):
+    return as_contiguous(x, np.float64)
 
 
 def empty_like_kind(ref, shape, dtype=np.float64):
@@ -129,7 +135,7 @@ def empty_like_kind(ref, shape, dtype=np.float64):
     if is_torch(ref):
         import torch
 
-        tdt = {np.float64: torch.float64, np.int64: torch.int64}[dtype]
+        tdt = {np.float64: torch.float64, np.float32: torch.float32, np.int64: torch.int64}[dtype]
         t = torch.empty(shape, dtype=tdt, device=ref.device)
         return t, t.data_ptr()
     a = np.empty(shape, dtype=dtype)

@@ -46,7 +46,7 @@ class _FusedSingleQuery(AcquisitionFunctionClass):
         self._param = float(param)
 
     def _squeeze(self, x):
-        x, _ = _lib.as_f64_contiguous(x)
+        x, _ = _lib.as_contiguous(x, self._model.dtype)
         if x.ndim < 2 or x.shape[-2] != 1:
             raise ValueError(
                 f"This acquisition function only supports batch sizes of one; got input of shape {tuple(x.shape)}"
@@ -57,7 +57,7 @@ class _FusedSingleQuery(AcquisitionFunctionClass):
     def __call__(self, x):
         flat, lead = self._squeeze(x)
         M = flat.shape[0]
-        out, po = _lib.empty_like_kind(flat, (M, 1))
+        out, po = _lib.empty_like_kind(flat, (M, 1), self._model.dtype)
         _lib.check(_lib.lib().tb_acq_eval(self._model.handle, self._acq, self._param, _ptr(flat), M, po, None))
         return out.reshape(lead + (1,))
 
@@ -66,19 +66,19 @@ class _FusedSingleQuery(AcquisitionFunctionClass):
         returns (values [..., 1], d values / d x [..., 1, D])."""
         flat, lead = self._squeeze(x)
         M, D = flat.shape
-        out, po = _lib.empty_like_kind(flat, (M, 1))
-        grad, pg = _lib.empty_like_kind(flat, (M, D))
+        out, po = _lib.empty_like_kind(flat, (M, 1), self._model.dtype)
+        grad, pg = _lib.empty_like_kind(flat, (M, D), self._model.dtype)
         _lib.check(_lib.lib().tb_acq_eval(self._model.handle, self._acq, self._param, _ptr(flat), M, po, pg))
         return out.reshape(lead + (1,)), grad.reshape(lead + (1, D))
 
     def fused_argmax(self, points):
         """points [M, D] -> (first-max index, value) without writing the M values to HBM
         (generate_random_search_optimizer / _get_max_discrete_points, optimizer.py:124-150)."""
-        pts, _ = _lib.as_f64_contiguous(points)
+        pts, _ = _lib.as_contiguous(points, self._model.dtype)
         if pts.ndim != 2:
             raise ValueError(f"points must be [M, D], got {tuple(pts.shape)}")
         self._model._check_dim(pts)
-        best = C.c_double()
+        best = C.c_double() if self._model.dtype == np.float64 else C.c_float()
         idx = C.c_int64()
         _lib.check(
             _lib.lib().tb_acq_argmax(
@@ -126,7 +126,7 @@ def lower_confidence_bound(model, beta: float):
 
 def _eta_from_model(model, dataset: Dataset, search_space=None) -> float:
     """function.py:133-149: eta = min over the (feasible) training inputs of the posterior mean."""
-    mean, _ = model.predict(np.asarray(dataset.query_points, dtype=np.float64))
+    mean, _ = model.predict(np.asarray(dataset.query_points))
     return float(np.min(mean, axis=0)[0])
 
 
@@ -196,14 +196,14 @@ class batch_monte_carlo_expected_improvement(AcquisitionFunctionClass):
         self._sampler.reset_sampler()
 
     def __call__(self, x):
-        x, _ = _lib.as_f64_contiguous(x)
+        x, _ = _lib.as_contiguous(x, self._model.dtype)
         if x.ndim < 2:
             raise ValueError(f"expected [..., B, D] query batches, got shape {tuple(x.shape)}")
         self._model._check_dim(x)
         flat, lead = _flatten_leading(x, 2)
         nb, q = flat.shape[0], flat.shape[1]
-        eps = self._sampler._get_eps(q)  # [q, S] float64 host, fixed until reset
-        out, po = _lib.empty_like_kind(flat, (nb, 1))
+        eps = np.ascontiguousarray(self._sampler._get_eps(q), dtype=self._model.dtype)  # [q, S] host, fixed until reset
+        out, po = _lib.empty_like_kind(flat, (nb, 1), self._model.dtype)
         _lib.check(
             _lib.lib().tb_acq_batch_mc_ei(
                 self._model.handle, _ptr(flat), nb, q, eps.ctypes.data, eps.shape[1], self._eta, self._jitter, po
@@ -228,7 +228,7 @@ class BatchMonteCarloExpectedImprovement(SingleModelAcquisitionBuilder):
 
     def prepare_acquisition_function(self, model, dataset: Optional[Dataset] = None):
         dataset = _check_populated(dataset)
-        mean, _ = model.predict(np.asarray(dataset.query_points, dtype=np.float64))
+        mean, _ = model.predict(np.asarray(dataset.query_points))
         if mean.shape[-1] != 1:
             raise ValueError("Expected model with event shape [1].")
         eta = np.min(mean, axis=0)
@@ -238,6 +238,6 @@ class BatchMonteCarloExpectedImprovement(SingleModelAcquisitionBuilder):
         dataset = _check_populated(dataset)
         if not isinstance(function, batch_monte_carlo_expected_improvement):
             raise ValueError(f"expected a batch_monte_carlo_expected_improvement, got {function!r}")
-        mean, _ = model.predict(np.asarray(dataset.query_points, dtype=np.float64))
+        mean, _ = model.predict(np.asarray(dataset.query_points))
         function.update(np.min(mean, axis=0))
         return function

@@ -118,7 +118,7 @@ void tb_launch_count_reset(void) { tb::launch_counter().store(0); }
 
 int tb_gp_create(tb_gp** out, int device, int dtype) {
   TB_CHECK(out != nullptr, "tb_gp_create: null output");
-  TB_CHECK(dtype == TB_F64, "tb_gp_create: only TB_F64 is implemented in this build");
+  TB_CHECK(dtype == TB_F64 || dtype == TB_F32, "tb_gp_create: dtype must be TB_F64 or TB_F32");
   int n = 0;
   TB_TRY(tb_device_count(&n));
   TB_CHECK(n > 0, "tb_gp_create: no CUDA device visible (this library has no CPU fallback)");
@@ -161,7 +161,7 @@ int tb_gp_destroy(tb_gp* gp) {
   return 0;
 }
 
-int tb_gp_set_data(tb_gp* gp, const void* X, const void* y, int64_t N, int D) {
+static int tb_gp_set_data_f64(tb_gp* gp, const void* X, const void* y, int64_t N, int D) {
   TB_CHECK(gp && X && y, "tb_gp_set_data: null argument");
   TB_CHECK(N > 0, "tb_gp_set_data: dataset must be populated (N > 0)");
   TB_CHECK(D > 0 && tb::pick_dp(D) > 0, "tb_gp_set_data: input dimension must be in [1, 32]");
@@ -290,7 +290,7 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
   return 0;
 }
 
-int tb_gp_get_cholesky(tb_gp* gp, void* L_out) {
+static int tb_gp_get_cholesky_f64(tb_gp* gp, void* L_out) {
   TB_CHECK(gp && L_out, "tb_gp_get_cholesky: null argument");
   TB_CHECK(gp->cache_valid, "tb_gp_get_cholesky: posterior cache is not built");
   TB_CUDA(cudaSetDevice(gp->device));
@@ -590,7 +590,7 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
 
 extern "C" {
 
-int tb_gp_predict(tb_gp* gp, const void* Xc, int64_t M, void* mean, void* var) {
+static int tb_gp_predict_f64(tb_gp* gp, const void* Xc, int64_t M, void* mean, void* var) {
   TB_CHECK(gp && (M == 0 || (Xc && mean && var)), "tb_gp_predict: null argument");
   tb::EvalRequest rq;
   rq.Xc = (const double*)Xc;
@@ -600,7 +600,7 @@ int tb_gp_predict(tb_gp* gp, const void* Xc, int64_t M, void* mean, void* var) {
   return tb::run_eval(gp, rq);
 }
 
-int tb_acq_eval(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* grad) {
+static int tb_acq_eval_f64(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* grad) {
   TB_CHECK(gp && (M == 0 || (Xc && out)), "tb_acq_eval: null argument");
   TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_LCB, "tb_acq_eval: unknown acquisition kind");
   if (acq == TB_ACQ_LCB || acq == TB_ACQ_NEG_LCB)
@@ -615,7 +615,7 @@ int tb_acq_eval(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, voi
   return tb::run_eval(gp, rq);
 }
 
-int tb_acq_argmax(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* best_value,
+static int tb_acq_argmax_f64(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* best_value,
                   int64_t* best_index) {
   TB_CHECK(gp && Xc && best_value && best_index, "tb_acq_argmax: null argument");
   TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_LCB, "tb_acq_argmax: unknown acquisition kind");
@@ -800,7 +800,7 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
 
 extern "C" {
 
-int tb_gp_predict_joint(tb_gp* gp, const void* Xc, int64_t B, int q, void* mean, void* cov) {
+static int tb_gp_predict_joint_f64(tb_gp* gp, const void* Xc, int64_t B, int q, void* mean, void* cov) {
   TB_CHECK(gp && (B == 0 || (Xc && mean && cov)), "tb_gp_predict_joint: null argument");
   tb::JointRequest rq;
   rq.mode = JOINT_PREDICT;
@@ -812,7 +812,7 @@ int tb_gp_predict_joint(tb_gp* gp, const void* Xc, int64_t B, int q, void* mean,
   return tb::run_joint(gp, rq);
 }
 
-int tb_acq_batch_mc_ei(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S, double eta,
+static int tb_acq_batch_mc_ei_f64(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S, double eta,
                        double jitter, void* out) {
   TB_CHECK(gp && (B == 0 || (Xc && eps && out)), "tb_acq_batch_mc_ei: null argument");
   tb::JointRequest rq;
@@ -828,7 +828,7 @@ int tb_acq_batch_mc_ei(tb_gp* gp, const void* Xc, int64_t B, int q, const void* 
   return tb::run_joint(gp, rq);
 }
 
-int tb_gp_reparam_sample(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S, double jitter,
+static int tb_gp_reparam_sample_f64(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S, double jitter,
                          void* samples) {
   TB_CHECK(gp && (B == 0 || (Xc && eps && samples)), "tb_gp_reparam_sample: null argument");
   tb::JointRequest rq;
@@ -1078,6 +1078,206 @@ int tb_rff_eval(tb_rff* r, const void* Xc, int64_t M, void* out, double* min_val
   TB_CUDA(cudaStreamSynchronize(st));
   TB_CUDA(cudaGetLastError());
   return 0;
+}
+
+}  // extern "C"
+
+
+// =================================================================================================
+// dtype dispatch.  TB_F32 handles (fp32 models, e.g. BASELINE config 5) take and return float arrays;
+// in this build the arithmetic still runs on the fp64 DMMA path (inputs widened on the device, outputs
+// narrowed), which exceeds the fp32 tolerance; an fp32-native tensor path is listed as next in DESIGN.md.
+// =================================================================================================
+namespace tb {
+
+__global__ void widen_kernel(const float* __restrict__ in, int64_t n, double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)in[i];
+}
+__global__ void narrow_kernel(const double* __restrict__ in, int64_t n, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+// per-call staging of float arrays as device doubles
+struct F32Bridge {
+  tb_gp* gp;
+  std::vector<void*> allocs;
+  struct Pending { double* dev; void* user; int64_t n; };
+  std::vector<Pending> outs;
+  explicit F32Bridge(tb_gp* g) : gp(g) {}
+  ~F32Bridge() { for (void* p : allocs) cudaFree(p); }
+  int alloc(void** p, size_t bytes) {
+    TB_CUDA(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+    allocs.push_back(*p);
+    return 0;
+  }
+  int in(const void* user, int64_t n, const double** out) {  // float (host or device) -> device double
+    *out = nullptr;
+    if (!user || n == 0) return 0;
+    const float* src = (const float*)user;
+    if (!is_device_ptr(user)) {
+      void* tmp;
+      TB_TRY(alloc(&tmp, sizeof(float) * n));
+      TB_CUDA(cudaMemcpyAsync(tmp, user, sizeof(float) * n, cudaMemcpyHostToDevice, gp->stream));
+      src = (const float*)tmp;
+    }
+    void* d;
+    TB_TRY(alloc(&d, sizeof(double) * n));
+    widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, gp->stream>>>(src, n, (double*)d);
+    TB_LAUNCHED();
+    *out = (const double*)d;
+    return 0;
+  }
+  int out(void* user, int64_t n, double** dev) {  // device double scratch, narrowed into `user` by finish()
+    *dev = nullptr;
+    if (!user || n == 0) return 0;
+    void* d;
+    TB_TRY(alloc(&d, sizeof(double) * n));
+    *dev = (double*)d;
+    outs.push_back({(double*)d, user, n});
+    return 0;
+  }
+  int finish() {
+    for (auto& o : outs) {
+      float* dst = (float*)o.user;
+      void* tmp = nullptr;
+      const bool dev = is_device_ptr(o.user);
+      if (!dev) {
+        TB_TRY(alloc(&tmp, sizeof(float) * o.n));
+        dst = (float*)tmp;
+      }
+      narrow_kernel<<<(unsigned)((o.n + 255) / 256), 256, 0, gp->stream>>>(o.dev, o.n, dst);
+      TB_LAUNCHED();
+      if (!dev) TB_CUDA(cudaMemcpyAsync(o.user, tmp, sizeof(float) * o.n, cudaMemcpyDeviceToHost, gp->stream));
+    }
+    TB_CUDA(cudaStreamSynchronize(gp->stream));
+    TB_CUDA(cudaGetLastError());
+    return 0;
+  }
+};
+
+}  // namespace tb
+
+extern "C" {
+
+int tb_gp_set_data(tb_gp* gp, const void* X, const void* y, int64_t N, int D) {
+  TB_CHECK(gp && X && y, "tb_gp_set_data: null argument");
+  if (gp->dtype == TB_F64) return tb_gp_set_data_f64(gp, X, y, N, D);
+  TB_CHECK(N > 0 && D > 0, "tb_gp_set_data: dataset must be populated (N > 0)");
+  TB_CUDA(cudaSetDevice(gp->device));
+  tb::F32Bridge br(gp);
+  const double *Xd, *yd;
+  TB_TRY(br.in(X, N * D, &Xd));
+  TB_TRY(br.in(y, N, &yd));
+  return tb_gp_set_data_f64(gp, Xd, yd, N, D);
+}
+
+int tb_gp_get_cholesky(tb_gp* gp, void* L_out) {
+  TB_CHECK(gp && L_out, "tb_gp_get_cholesky: null argument");
+  if (gp->dtype == TB_F64) return tb_gp_get_cholesky_f64(gp, L_out);
+  TB_CUDA(cudaSetDevice(gp->device));
+  tb::F32Bridge br(gp);
+  double* Ld;
+  TB_TRY(br.out(L_out, gp->N * gp->N, &Ld));
+  TB_TRY(tb_gp_get_cholesky_f64(gp, Ld));
+  return br.finish();
+}
+
+int tb_gp_predict(tb_gp* gp, const void* Xc, int64_t M, void* mean, void* var) {
+  TB_CHECK(gp && (M == 0 || (Xc && mean && var)), "tb_gp_predict: null argument");
+  if (gp->dtype == TB_F64) return tb_gp_predict_f64(gp, Xc, M, mean, var);
+  if (M == 0) return 0;
+  TB_CUDA(cudaSetDevice(gp->device));
+  tb::F32Bridge br(gp);
+  const double* xd;
+  double *md, *vd;
+  TB_TRY(br.in(Xc, M * gp->D, &xd));
+  TB_TRY(br.out(mean, M, &md));
+  TB_TRY(br.out(var, M, &vd));
+  TB_TRY(tb_gp_predict_f64(gp, xd, M, md, vd));
+  return br.finish();
+}
+
+int tb_acq_eval(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* grad) {
+  TB_CHECK(gp && (M == 0 || (Xc && out)), "tb_acq_eval: null argument");
+  if (gp->dtype == TB_F64) return tb_acq_eval_f64(gp, acq, param, Xc, M, out, grad);
+  if (M == 0) return 0;
+  TB_CUDA(cudaSetDevice(gp->device));
+  tb::F32Bridge br(gp);
+  const double* xd;
+  double *od, *gd;
+  TB_TRY(br.in(Xc, M * gp->D, &xd));
+  TB_TRY(br.out(out, M, &od));
+  TB_TRY(br.out(grad, M * gp->D, &gd));
+  TB_TRY(tb_acq_eval_f64(gp, acq, param, xd, M, od, gd));
+  return br.finish();
+}
+
+int tb_acq_argmax(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* best_value,
+                  int64_t* best_index) {
+  TB_CHECK(gp && Xc && best_value && best_index, "tb_acq_argmax: null argument");
+  if (gp->dtype == TB_F64) return tb_acq_argmax_f64(gp, acq, param, Xc, M, out, best_value, best_index);
+  TB_CUDA(cudaSetDevice(gp->device));
+  tb::F32Bridge br(gp);
+  const double* xd;
+  double* od;
+  double best = 0.0;
+  TB_TRY(br.in(Xc, M * gp->D, &xd));
+  TB_TRY(br.out(out, M, &od));
+  TB_TRY(tb_acq_argmax_f64(gp, acq, param, xd, M, od, &best, best_index));
+  *(float*)best_value = (float)best;
+  return br.finish();
+}
+
+int tb_gp_predict_joint(tb_gp* gp, const void* Xc, int64_t B, int q, void* mean, void* cov) {
+  TB_CHECK(gp && (B == 0 || (Xc && mean && cov)), "tb_gp_predict_joint: null argument");
+  if (gp->dtype == TB_F64) return tb_gp_predict_joint_f64(gp, Xc, B, q, mean, cov);
+  if (B == 0) return 0;
+  TB_CHECK(q >= 1 && q <= 32, "batch size q must be in [1, 32]");
+  TB_CUDA(cudaSetDevice(gp->device));
+  tb::F32Bridge br(gp);
+  const double* xd;
+  double *md, *cd;
+  TB_TRY(br.in(Xc, B * q * gp->D, &xd));
+  TB_TRY(br.out(mean, B * q, &md));
+  TB_TRY(br.out(cov, B * q * q, &cd));
+  TB_TRY(tb_gp_predict_joint_f64(gp, xd, B, q, md, cd));
+  return br.finish();
+}
+
+int tb_acq_batch_mc_ei(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S, double eta,
+                       double jitter, void* out) {
+  TB_CHECK(gp && (B == 0 || (Xc && eps && out)), "tb_acq_batch_mc_ei: null argument");
+  if (gp->dtype == TB_F64) return tb_acq_batch_mc_ei_f64(gp, Xc, B, q, eps, S, eta, jitter, out);
+  if (B == 0) return 0;
+  TB_CHECK(q >= 1 && q <= 32 && S >= 1, "batch size q must be in [1, 32] and S >= 1");
+  TB_CUDA(cudaSetDevice(gp->device));
+  tb::F32Bridge br(gp);
+  const double *xd, *ed;
+  double* od;
+  TB_TRY(br.in(Xc, B * q * gp->D, &xd));
+  TB_TRY(br.in(eps, (int64_t)q * S, &ed));
+  TB_TRY(br.out(out, B, &od));
+  TB_TRY(tb_acq_batch_mc_ei_f64(gp, xd, B, q, ed, S, eta, jitter, od));
+  return br.finish();
+}
+
+int tb_gp_reparam_sample(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S, double jitter,
+                         void* samples) {
+  TB_CHECK(gp && (B == 0 || (Xc && eps && samples)), "tb_gp_reparam_sample: null argument");
+  if (gp->dtype == TB_F64) return tb_gp_reparam_sample_f64(gp, Xc, B, q, eps, S, jitter, samples);
+  if (B == 0) return 0;
+  TB_CHECK(q >= 1 && q <= 32 && S >= 1, "batch size q must be in [1, 32] and S >= 1");
+  TB_CUDA(cudaSetDevice(gp->device));
+  tb::F32Bridge br(gp);
+  const double *xd, *ed;
+  double* sd;
+  TB_TRY(br.in(Xc, B * q * gp->D, &xd));
+  TB_TRY(br.in(eps, (int64_t)q * S, &ed));
+  TB_TRY(br.out(samples, B * S * q, &sd));
+  TB_TRY(tb_gp_reparam_sample_f64(gp, xd, B, q, ed, S, jitter, sd));
+  return br.finish();
 }
 
 }  // extern "C"

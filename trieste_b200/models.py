@@ -32,8 +32,12 @@ class GPRSpec:
     def __init__(self, data, kernel: Stationary, mean_function: Optional[Constant] = None, noise_variance: float = 1.0):
         if isinstance(data, Dataset):
             data = data.astuple()
-        self.X = np.ascontiguousarray(np.asarray(data[0], dtype=np.float64))
-        self.Y = np.ascontiguousarray(np.asarray(data[1], dtype=np.float64))
+        # dtype follows the model data (fp64 default, fp32 supported end to end: builders.py:41,
+        # tests/integration/test_bayesian_optimization.py:641-658)
+        x0 = data[0].detach().cpu().numpy() if _lib.is_torch(data[0]) else np.asarray(data[0])
+        self.dtype = np.float32 if x0.dtype == np.float32 else np.float64
+        self.X = np.ascontiguousarray(np.asarray(x0, dtype=self.dtype))
+        self.Y = np.ascontiguousarray(np.asarray(data[1], dtype=self.dtype))
         self.kernel = kernel
         self.mean_function = mean_function if mean_function is not None else Constant(0.0)
         self.noise_variance = float(noise_variance)
@@ -51,7 +55,8 @@ def build_gpr(
     = mean(y), kernel variance = Var(y), lengthscales 0.2 * (upper - lower) * sqrt(D) (:413-423),
     noise = Var(y) / 10^2 unless given (:432-443).  Priors only matter for hyper-parameter
     training, which is out of scope here."""
-    X, Y = np.asarray(data.query_points, dtype=np.float64), np.asarray(data.observations, dtype=np.float64)
+    dt = np.float32 if np.asarray(data.query_points).dtype == np.float32 else np.float64
+    X, Y = np.asarray(data.query_points, dtype=dt), np.asarray(data.observations, dtype=dt)
     if X.shape[0] == 0:
         raise ValueError("Dataset must be populated.")
     variance = float(np.var(Y))
@@ -96,7 +101,8 @@ class GaussianProcessRegression:
         if use_decoupled_sampler:
             raise NotImplementedError("DecoupledTrajectorySampler is listed as 'next' (SURVEY.md §8f-2)")
         h = C.c_void_p()
-        _lib.check(_lib.lib().tb_gp_create(C.byref(h), device, _lib.TB_F64))
+        self._dtype = model.dtype
+        _lib.check(_lib.lib().tb_gp_create(C.byref(h), device, _lib.TB_F32 if self._dtype == np.float32 else _lib.TB_F64))
         self._h = h
         self._push_data()
         self._push_hyper()
@@ -119,6 +125,10 @@ class GaussianProcessRegression:
     @property
     def device(self) -> int:
         return self._device
+
+    @property
+    def dtype(self):
+        return self._dtype
 
     def _push_data(self) -> None:
         X, Y = self._spec.X, self._spec.Y
@@ -152,26 +162,26 @@ class GaussianProcessRegression:
     def predict(self, query_points) -> Tuple[np.ndarray, np.ndarray]:
         """[..., D] -> (mean [..., 1], var [..., 1]), variance clipped to >= 1e-12
         (interfaces.py:55-64; interface.py:119-124)."""
-        x, _ = _lib.as_f64_contiguous(query_points)
+        x, _ = _lib.as_contiguous(query_points, self._dtype)
         self._check_dim(x)
         flat, lead = _flatten_leading(x, 1)
         M = flat.shape[0]
-        mean, pm = _lib.empty_like_kind(flat, (M, 1))
-        var, pv = _lib.empty_like_kind(flat, (M, 1))
+        mean, pm = _lib.empty_like_kind(flat, (M, 1), self._dtype)
+        var, pv = _lib.empty_like_kind(flat, (M, 1), self._dtype)
         _lib.check(_lib.lib().tb_gp_predict(self._h, _ptr(flat), M, pm, pv))
         return mean.reshape(lead + (1,)), var.reshape(lead + (1,))
 
     def predict_joint(self, query_points) -> Tuple[np.ndarray, np.ndarray]:
         """[..., B, D] -> (mean [..., B, 1], cov [..., 1, B, B]) (interfaces.py:133-140;
         interface.py:126-133)."""
-        x, _ = _lib.as_f64_contiguous(query_points)
+        x, _ = _lib.as_contiguous(query_points, self._dtype)
         if x.ndim < 2:
             raise ValueError(f"predict_joint needs query points of rank >= 2, got shape {tuple(x.shape)}")
         self._check_dim(x)
         flat, lead = _flatten_leading(x, 2)
         nb, q = flat.shape[0], flat.shape[1]
-        mean, pm = _lib.empty_like_kind(flat, (nb, q, 1))
-        cov, pc = _lib.empty_like_kind(flat, (nb, 1, q, q))
+        mean, pm = _lib.empty_like_kind(flat, (nb, q, 1), self._dtype)
+        cov, pc = _lib.empty_like_kind(flat, (nb, 1, q, q), self._dtype)
         _lib.check(_lib.lib().tb_gp_predict_joint(self._h, _ptr(flat), nb, q, pm, pc))
         return mean.reshape(lead + (q, 1)), cov.reshape(lead + (1, q, q))
 
@@ -185,7 +195,7 @@ class GaussianProcessRegression:
         (interface.py:135-138 -> gpflow predict_f_samples)."""
         if num_samples <= 0:
             raise ValueError(f"num_samples must be positive, got {num_samples}")
-        x = np.asarray(query_points, dtype=np.float64)
+        x = np.asarray(query_points, dtype=self._dtype)
         q = x.shape[-2]
         eps = np.random.default_rng(seed).standard_normal((q, num_samples))
         from .sampler import _reparam_sample
@@ -198,8 +208,8 @@ class GaussianProcessRegression:
     # ---- TrainableProbabilisticModel -----------------------------------------------------------
     def update(self, dataset: Dataset) -> None:
         """models.py:171-186: swap the data, refresh the posterior cache."""
-        X = np.ascontiguousarray(np.asarray(dataset.query_points, dtype=np.float64))
-        Y = np.ascontiguousarray(np.asarray(dataset.observations, dtype=np.float64))
+        X = np.ascontiguousarray(np.asarray(dataset.query_points, dtype=self._dtype))
+        Y = np.ascontiguousarray(np.asarray(dataset.observations, dtype=self._dtype))
         if X.ndim != 2 or X.shape[-1] != self._spec.X.shape[-1]:
             raise ValueError(f"new query points must be [N, {self._spec.X.shape[-1]}], got {X.shape}")
         self._spec.X, self._spec.Y = X, Y
@@ -239,7 +249,7 @@ class GaussianProcessRegression:
 
     def get_cholesky(self) -> np.ndarray:
         N = self._spec.X.shape[0]
-        out = np.empty((N, N))
+        out = np.empty((N, N), dtype=self._dtype)
         _lib.check(_lib.lib().tb_gp_get_cholesky(self._h, out.ctypes.data))
         return out
 

@@ -17,12 +17,12 @@ JITTER = 1e-6
 
 def _reparam_sample(model: GaussianProcessRegression, at, eps: np.ndarray, jitter: float):
     """at [..., q, D], eps [q, S] -> samples [..., S, q, 1]."""
-    x, _ = _lib.as_f64_contiguous(at)
+    x, _ = _lib.as_contiguous(at, model.dtype)
     flat, lead = _flatten_leading(x, 2)
     nb, q = flat.shape[0], flat.shape[1]
     S = eps.shape[1]
-    eps = np.ascontiguousarray(eps, dtype=np.float64)
-    out, po = _lib.empty_like_kind(flat, (nb, S, q))
+    eps = np.ascontiguousarray(eps, dtype=model.dtype)
+    out, po = _lib.empty_like_kind(flat, (nb, S, q), model.dtype)
     _lib.check(_lib.lib().tb_gp_reparam_sample(model.handle, _ptr(flat), nb, q, eps.ctypes.data, S, jitter, po))
     return out.reshape(lead + (S, q, 1))
 
