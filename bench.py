@@ -145,6 +145,12 @@ def cpu_reference_rate(sample_target_s=12.0, chunk=8192, seed=1):
     """Oracle (CPU restatement of the reference path: predict + EI + argmax) on a bounded sample of the
     same workload, all host threads (NumPy/SciPy BLAS).  Returns (candidates/s, candidates, seconds)."""
     o, om, eta = _oracle_model()
+    try:  # torchrun exports OMP_NUM_THREADS=1: give the BLAS pool every host core back
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     rng = np.random.default_rng(seed)
     Xc = rng.uniform(size=(chunk, DIM))
     t0 = time.perf_counter()

@@ -126,6 +126,9 @@ int tb_rff_eval(tb_rff* r, const void* Xc, int64_t M, void* out, double* min_val
  * profiling is enabled. */
 int64_t tb_launch_count(void);
 void tb_launch_count_reset(void);
+/* engine of the variance GEMM: 0 = native fp64 (DMMA), 1 = fp64-accurate emulation on the INT8 tensor cores
+ * (Ozaki splitting, tcgen05 kind::i8; same stated tolerances).  Gradient / joint paths always use engine 0. */
+int tb_gp_set_engine(tb_gp* gp, int engine);
 int tb_gp_profile(tb_gp* gp, int enable);
 /* the handle's CUDA stream (cudaStream_t as void*), so callers can record CUDA events on the stream the
  * kernels are launched on (torch.cuda.ExternalStream in bench.py). */

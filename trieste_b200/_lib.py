@@ -47,6 +47,7 @@ SIGNATURES = {
     "tb_rff_eval": (_i32, [_vp, _vp, _i64, _vp, C.POINTER(_f64), C.POINTER(_i64)]),
     "tb_launch_count": (_i64, []),
     "tb_launch_count_reset": (None, []),
+    "tb_gp_set_engine": (_i32, [_vp, _i32]),
     "tb_gp_profile": (_i32, [_vp, _i32]),
     "tb_gp_stream": (_i32, [_vp, C.POINTER(_vp)]),
     "tb_gp_profile_read": (_i32, [_vp, C.POINTER(_f64), C.POINTER(_i64), C.POINTER(_f64)]),

@@ -78,6 +78,12 @@ struct tb_gp {
   tb::DevBuf dLinvP;            // packed lower panels
   tb::DevBuf dLinvTP;           // packed upper panels of Linv^T (lazy; gradient path)
   bool upper_valid = false;
+  // int8 (Ozaki) engine: digit tiles of Linv, per-row scales, K* scale
+  int engine = 0;  // 0 = fp64 DMMA, 1 = int8 tensor cores
+  tb::DevBuf dAS, dRowScale;
+  bool oz_valid = false;
+  int nst = 0, oz_bscale_exp = 0;
+  double oz_out_scale = 1.0;
   tb::DevBuf dWork, dInfo;      // cusolver workspace
 
   // per-call scratch

@@ -1,0 +1,388 @@
+// fp64-accurate triangular GEMM on the INT8 tensor cores (Ozaki error-free splitting, tcgen05 kind::i8).
+//
+//   A = Linv · K*  is needed to ~2^-46 relative to |row scale|·|K* scale| for the 1e-9·σ_f² variance bar.
+//   Each fp64 operand is split into S = 7 balanced base-128 digits (int8 in [-64, 64]) under a power-of-two
+//   scale (per row of Linv; one global scale for K*):   x = 2^e · Σ_p d_p · 2^(1-7p).
+//   Products of digit matrices are EXACT in the int32 TMEM accumulators, and all pairs with the same
+//   p + q = r share one accumulator T_r, so
+//        A[n,t] = 2^(e_n + f + 2) · Σ_{r=2..R} 2^(-7r) · T_r[n,t],        R = 8  (28 digit products).
+//   TMEM holds 512 columns = four 128x128 int32 accumulators, so each row-block runs two passes:
+//        pass LO: r = 6,7,8 (18 products, digits 1..7 of both operands), kept as fp64 in registers,
+//        pass HI: r = 2..5  (10 products, digits 1..4), then scale, square and column-reduce.
+//   Operands are pre-packed in the UMMA no-swizzle K-major core-matrix layout, so each pipeline stage is two
+//   contiguous 1-D bulk-TMA copies.  Warp roles: 8 epilogue warps, 1 TMA producer, 1 MMA issuer.
+#pragma once
+#include "common.cuh"
+#include <cfloat>
+
+namespace tb {
+namespace oz {
+
+constexpr int S = 7;                         // digits per operand
+constexpr int KST = 64;                      // K bytes (= k columns) per pipeline stage
+constexpr int TILE = 128 * KST;              // one digit tile: 128 rows x 64 k-bytes = 8 KB
+constexpr uint32_t LBO = 128;                // core matrices adjacent in K
+constexpr uint32_t SBO = (KST / 16) * 128;   // 8-row groups
+constexpr int HI_DIG = 4;                    // pass HI uses digits 1..4, pass LO digits 1..7
+constexpr int STAGES_HI = 3, STAGES_LO = 2;
+constexpr int STAGE_BYTES_HI = 2 * HI_DIG * TILE;   // 64 KB
+constexpr int STAGE_BYTES_LO = 2 * S * TILE;        // 112 KB
+constexpr size_t SMEM_BYTES = (size_t)STAGES_LO * STAGE_BYTES_LO + 256;   // 224 KB + barriers
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr int DIGIT_BITS = 48;               // v = rint(x / 2^e * 2^48) = Σ d_p 128^(7-p)
+
+__host__ __device__ inline int64_t a_stage_offset(int I) {  // stages before row-block I: Σ 2(i+1)
+  return (int64_t)I * (I + 1);
+}
+
+// balanced base-128 digits of v (|v| <= 2^47): d[0] most significant
+__device__ __forceinline__ void digits7(long long v, int d[S]) {
+#pragma unroll
+  for (int p = S - 1; p >= 0; --p) {
+    int lo = (int)(((v + 64) & 127) - 64);
+    d[p] = lo;
+    v = (v - lo) >> 7;
+  }
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((LBO >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((SBO >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+               "l"(da), "l"(db), "r"(IDESC), "r"(acc)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// once per BO step: digit tiles of Linv.  grid = (stage kc, row-block I), 256 threads.
+//   rowscale[n] = 2^e_n with 2^e_n > 2 max_k |Linv[n,k]|  (so |x|/2^e < 1/2 and the top digit fits)
+// ------------------------------------------------------------------------------------------------
+__global__ void linv_rowscale_kernel(const double* __restrict__ Linv, int64_t N, int64_t rows, double* __restrict__ rowscale) {
+  const int64_t n = blockIdx.x;
+  double mx = 0.0;
+  if (n < N)
+    for (int64_t k = threadIdx.x; k <= n; k += blockDim.x) mx = fmax(mx, fabs(Linv[n + k * N]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, sm[w]);
+    int e = 0;
+    if (mx > 0.0) {
+      frexp(mx, &e);  // mx = m 2^e, m in [0.5, 1)
+      e += 1;         // |x| / 2^e < 1/2
+    }
+    if (n < rows) rowscale[n] = ldexp(1.0, e);
+  }
+}
+
+__global__ void linv_digits_kernel(const double* __restrict__ Linv, int64_t N, const double* __restrict__ rowscale,
+                                   int8_t* __restrict__ AS) {
+  const int I = blockIdx.y, kc = blockIdx.x;
+  if (kc >= 2 * (I + 1)) return;
+  int8_t* dst = AS + (a_stage_offset(I) + kc) * (int64_t)(S * TILE);
+  for (int e = threadIdx.x; e < 128 * KST; e += blockDim.x) {
+    const int r = e % 128, kin = e / 128;  // r fastest: column-major source is contiguous in n
+    const int64_t n = (int64_t)I * 128 + r, k = (int64_t)kc * KST + kin;
+    long long v = 0;
+    if (n < N && k <= n) v = __double2ll_rn(Linv[n + k * N] / rowscale[n] * 281474976710656.0);  // 2^48
+    int d[S];
+    digits7(v, d);
+    const int off = (r >> 3) * SBO + (kin >> 4) * LBO + (r & 7) * 16 + (kin & 15);
+#pragma unroll
+    for (int p = 0; p < S; ++p) dst[p * TILE + off] = (int8_t)d[p];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K* digit tiles + posterior mean.  grid = candidate tiles, 512 threads = 16 warps; warp w owns candidates
+// [8w, 8w+8); lane l <-> (candidate l % 8, 16-wide k chunk l / 8): every digit store of a warp is 512
+// contiguous bytes (four adjacent core matrices).
+// ------------------------------------------------------------------------------------------------
+template <int KIND, int DP>
+__global__ void __launch_bounds__(512)
+kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha, const double* __restrict__ Xc,
+                    const double* __restrict__ inv_ls, int N, int nst, int D, int64_t M, double variance,
+                    double inv_bscale_2p48, double mean_const, int8_t* __restrict__ BS, double* __restrict__ mean_out) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cl = lane & 7, ch = lane >> 3;
+  const int t_local = w * 8 + cl;
+  const int64_t t = (int64_t)blockIdx.x * 128 + t_local;
+  const bool valid = t < M;
+  double xc[DP];
+#pragma unroll
+  for (int d = 0; d < DP; ++d) xc[d] = (valid && d < D) ? Xc[t * D + d] * inv_ls[d] : 0.0;
+  int8_t* tile = BS + (int64_t)blockIdx.x * nst * (S * TILE) + w * SBO + ch * LBO + cl * 16;
+  double macc = 0.0;
+  for (int kc = 0; kc < nst; ++kc) {
+    uint32_t pk[S][4];
+#pragma unroll
+    for (int p = 0; p < S; ++p) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int k = kc * KST + ch * 16 + j;
+      const double* xr = Xs + (int64_t)k * DP;
+      double r2 = 0.0;
+#pragma unroll
+      for (int d = 0; d < DP; d += 2) {
+        double2 v = __ldg(reinterpret_cast<const double2*>(xr + d));
+        double d0 = xc[d] - v.x, d1 = xc[d + 1] - v.y;
+        r2 = fma(d0, d0, r2);
+        r2 = fma(d1, d1, r2);
+      }
+      const double kval = (valid && k < N) ? kernel_from_r2<KIND>(r2, variance) : 0.0;
+      macc = fma(kval, __ldg(alpha + k), macc);
+      int dg[S];
+      digits7(__double2ll_rn(kval * inv_bscale_2p48), dg);
+#pragma unroll
+      for (int p = 0; p < S; ++p) pk[p][j >> 2] |= (uint32_t)(dg[p] & 0xff) << (8 * (j & 3));
+    }
+#pragma unroll
+    for (int p = 0; p < S; ++p)
+      *reinterpret_cast<uint4*>(tile + (int64_t)kc * (S * TILE) + p * TILE) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+  }
+  macc += __shfl_xor_sync(0xffffffffu, macc, 8);
+  macc += __shfl_xor_sync(0xffffffffu, macc, 16);
+  if (ch == 0) mean_out[(int64_t)blockIdx.x * 128 + t_local] = macc + mean_const;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the GEMM: grid = (candidate tiles, G); partial[g][t] = Σ_{rows n of group g} A[n,t]^2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1)
+trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, const double* __restrict__ rowscale,
+                  int NB, int nst, int G, int64_t McPad, double out_scale, double* __restrict__ partial) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES_LO * STAGE_BYTES_LO);
+  uint64_t* full_hi = bars;            // [3]
+  uint64_t* empty_hi = bars + 3;       // [3]
+  uint64_t* full_lo = bars + 6;        // [2]
+  uint64_t* empty_lo = bars + 8;       // [2]
+  uint64_t* acc_full = bars + 10;      // MMA -> epilogue (and producer: all MMAs of the pass retired)
+  uint64_t* acc_empty = bars + 11;     // epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, g = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 3; ++s) { mbar_init(&full_hi[s], 1); mbar_init(&empty_hi[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&full_lo[s], 1); mbar_init(&empty_lo[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == EPI_WARPS) {  // TMEM allocation: all 512 columns (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const int8_t* bTile = BS + (int64_t)tile * nst * (S * TILE);
+
+  if (warp == EPI_WARPS) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int st_hi = 0, st_lo = 0;
+      uint32_t ph_hi = 0, ph_lo = 0, ph_acc = 0;
+      bool first = true;
+      for (int i = 0;; ++i) {
+        const int I = serpentine_rowblock(i, g, G);
+        if (I >= NB) break;
+        const int nk = min(2 * (I + 1), nst);
+        const int8_t* aRow = AS + a_stage_offset(I) * (int64_t)(S * TILE);
+        for (int pass = 0; pass < 2; ++pass) {  // 0 = LO (digits 1..7), 1 = HI (digits 1..4)
+          if (!first) {  // the two passes use different stage geometries over the same bytes:
+            mbar_wait(acc_full, ph_acc);  // wait until every MMA of the previous pass has retired
+            ph_acc ^= 1;
+          }
+          first = false;
+          for (int kc = 0; kc < nk; ++kc) {
+            const int8_t* a = aRow + (int64_t)kc * (S * TILE);
+            const int8_t* b = bTile + (int64_t)kc * (S * TILE);
+            if (pass == 0) {
+              mbar_wait(&empty_lo[st_lo], ph_lo ^ 1);
+              unsigned char* dst = smem + (size_t)st_lo * STAGE_BYTES_LO;
+              mbar_expect_tx(&full_lo[st_lo], STAGE_BYTES_LO);
+              bulk_g2s(dst, a, S * TILE, &full_lo[st_lo]);
+              bulk_g2s(dst + S * TILE, b, S * TILE, &full_lo[st_lo]);
+              if (++st_lo == STAGES_LO) { st_lo = 0; ph_lo ^= 1; }
+            } else {
+              mbar_wait(&empty_hi[st_hi], ph_hi ^ 1);
+              unsigned char* dst = smem + (size_t)st_hi * STAGE_BYTES_HI;
+              mbar_expect_tx(&full_hi[st_hi], STAGE_BYTES_HI);
+              bulk_g2s(dst, a, HI_DIG * TILE, &full_hi[st_hi]);
+              bulk_g2s(dst + HI_DIG * TILE, b, HI_DIG * TILE, &full_hi[st_hi]);
+              if (++st_hi == STAGES_HI) { st_hi = 0; ph_hi ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int st_hi = 0, st_lo = 0;
+      uint32_t ph_hi = 0, ph_lo = 0, ph_aempty = 0;
+      bool first = true;
+      for (int i = 0;; ++i) {
+        const int I = serpentine_rowblock(i, g, G);
+        if (I >= NB) break;
+        const int nk = min(2 * (I + 1), nst);
+        for (int pass = 0; pass < 2; ++pass) {
+          if (!first) {  // accumulators must have been drained by the epilogue warps
+            mbar_wait(acc_empty, ph_aempty);
+            ph_aempty ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          first = false;
+          const int ndig = pass == 0 ? S : HI_DIG;
+          const int rlo = pass == 0 ? 6 : 2, rhi = pass == 0 ? 8 : 5;
+          for (int kc = 0; kc < nk; ++kc) {
+            uint32_t base;
+            if (pass == 0) {
+              mbar_wait(&full_lo[st_lo], ph_lo);
+              base = smem_u32(smem + (size_t)st_lo * STAGE_BYTES_LO);
+            } else {
+              mbar_wait(&full_hi[st_hi], ph_hi);
+              base = smem_u32(smem + (size_t)st_hi * STAGE_BYTES_HI);
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t aB = base, bB = base + ndig * TILE;
+            for (int p = 1; p <= ndig; ++p)
+              for (int q = 1; q <= ndig; ++q) {
+                const int r = p + q;
+                if (r < rlo || r > rhi) continue;
+                const uint32_t acc = tmem + (uint32_t)(r - rlo) * 128u;
+#pragma unroll
+                for (int kk = 0; kk < KST / 32; ++kk) {
+                  const uint64_t da = make_desc(aB + (p - 1) * TILE + kk * 2 * LBO);
+                  const uint64_t db = make_desc(bB + (q - 1) * TILE + kk * 2 * LBO);
+                  // first MMA into this accumulator in this pass: (kc == 0, kk == 0) and first pair of group r,
+                  // i.e. p == max(1, r - ndig)
+                  const bool fresh = (kc == 0) && (kk == 0) && (p == (r - ndig > 1 ? r - ndig : 1));
+                  umma_i8(acc, da, db, fresh ? 0u : 1u);
+                }
+              }
+            if (pass == 0) {
+              umma_commit(&empty_lo[st_lo]);
+              if (++st_lo == STAGES_LO) { st_lo = 0; ph_lo ^= 1; }
+            } else {
+              umma_commit(&empty_hi[st_hi]);
+              if (++st_hi == STAGES_HI) { st_hi = 0; ph_hi ^= 1; }
+            }
+          }
+          umma_commit(acc_full);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    // warp w reads TMEM lanes [32 (w%4), +32) (rows) and columns [64 (w/4), +64) of every accumulator
+    const int lq = warp & 3, ch = warp >> 2;
+    const uint32_t lane_base = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * 64);
+    double vlo[64];
+    double colsum0 = 0.0, colsum1 = 0.0;  // lane owns columns ch*64 + lane and ch*64 + 32 + lane
+    uint32_t ph_acc = 0;
+    for (int i = 0;; ++i) {
+      const int I = serpentine_rowblock(i, g, G);
+      if (I >= NB) break;
+      const double rs = rowscale[(int64_t)I * 128 + lq * 32 + lane] * out_scale;
+      for (int pass = 0; pass < 2; ++pass) {
+        mbar_wait(acc_full, ph_acc);
+        ph_acc ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (pass == 0) {
+          // v_lo = Σ_{r=6..8} 2^(-7r) T_r   (smallest terms first)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t t8[32], t7[32], t6[32];
+            tmem_ld32(lane_base + 2 * 128 + h * 32, t8);
+            tmem_ld32(lane_base + 1 * 128 + h * 32, t7);
+            tmem_ld32(lane_base + 0 * 128 + h * 32, t6);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              double v = (double)(int)t8[c] * 0x1p-56;
+              v = fma((double)(int)t7[c], 0x1p-49, v);
+              v = fma((double)(int)t6[c], 0x1p-42, v);
+              vlo[h * 32 + c] = v;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t t5[32], t4[32], t3[32], t2[32];
+            tmem_ld32(lane_base + 3 * 128 + h * 32, t5);
+            tmem_ld32(lane_base + 2 * 128 + h * 32, t4);
+            tmem_ld32(lane_base + 1 * 128 + h * 32, t3);
+            tmem_ld32(lane_base + 0 * 128 + h * 32, t2);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              double v = fma((double)(int)t5[c], 0x1p-35, vlo[h * 32 + c]);
+              v = fma((double)(int)t4[c], 0x1p-28, v);
+              v = fma((double)(int)t3[c], 0x1p-21, v);
+              v = fma((double)(int)t2[c], 0x1p-14, v);
+              v *= rs;          // A[n, t]
+              double sq = v * v;
+              // column sum over the 32 rows of this warp: butterfly
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+              if (lane == c) {
+                if (h == 0) colsum0 += sq; else colsum1 += sq;
+              }
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+    }
+    // combine the four row-quarters (warps lq = 0..3 of the same column half) through shared memory
+    // (every MMA has retired, so the stage buffers are free to hold the 4 KB of partial column sums)
+    double (*redbuf)[64] = reinterpret_cast<double (*)[64]>(smem);
+    redbuf[warp][lane] = colsum0;
+    redbuf[warp][32 + lane] = colsum1;
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32));
+    if (warp < 2) {  // warp 0 -> columns 0..63 (ch = 0: warps 0..3), warp 1 -> columns 64..127 (warps 4..7)
+      const int c0 = lane, c1 = 32 + lane, wb = warp * 4;
+      double a0 = redbuf[wb][c0] + redbuf[wb + 1][c0] + redbuf[wb + 2][c0] + redbuf[wb + 3][c0];
+      double a1 = redbuf[wb][c1] + redbuf[wb + 1][c1] + redbuf[wb + 2][c1] + redbuf[wb + 3][c1];
+      double* out = partial + (int64_t)g * McPad + (int64_t)tile * 128 + warp * 64;
+      out[c0] = a0;
+      out[c1] = a1;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+}  // namespace oz
+}  // namespace tb

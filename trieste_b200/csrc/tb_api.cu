@@ -2,6 +2,7 @@
 // runs in the kernels of kernels_f64.cuh / kernels_extra.cuh.
 #include "gp_handle.cuh"
 #include "kernels_extra.cuh"
+#include "ozaki.cuh"
 
 using namespace tb;
 namespace tb {
@@ -146,7 +147,7 @@ int tb_gp_destroy(tb_gp* gp) {
   cudaSetDevice(gp->device);
   cudaStreamSynchronize(gp->stream);
   for (tb::DevBuf* b : {&gp->dX, &gp->dy, &gp->dXs, &gp->dInvLs, &gp->dAlpha, &gp->dL, &gp->dLinv,
-                        &gp->dLinvP, &gp->dLinvTP, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
+                        &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
                         &gp->sVals, &gp->sVar, &gp->sXc, &gp->sBlkBest, &gp->sBlkIdx, &gp->sRun,
                         &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc})
     b->release();
@@ -212,7 +213,7 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
   TB_CUDA(cudaSetDevice(gp->device));
   const int64_t N = gp->N;
   const int D = gp->D, DP = gp->DP;
-  const int64_t rows = (int64_t)gp->nkc * BK;
+  const int64_t rows = (int64_t)gp->NB * BM;  // >= nkc*16 and >= nst*64
   cudaStream_t st = gp->stream;
 
   std::vector<double> inv_ls(DP, 0.0);
@@ -287,6 +288,7 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
   TB_CUDA(cudaGetLastError());
   gp->cache_valid = true;
   gp->upper_valid = false;
+  gp->oz_valid = false;
   return 0;
 }
 
@@ -377,6 +379,7 @@ static int pick_groups(const tb_gp* gp, int tiles) {
 }
 
 int kernels_init() {
+  TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
@@ -455,6 +458,67 @@ static int gradient_chunk(tb_gp* gp, int acq, double param, const double* xc, in
   return 0;
 }
 
+// Ozaki engine state: digit tiles of Linv + row scales, built lazily after each cache refresh
+static int ensure_ozaki(tb_gp* gp) {
+  if (gp->oz_valid) return 0;
+  TB_CHECK(gp->N <= 32768, "the int8 engine supports N <= 32768 (int32 accumulator headroom)");
+  cudaStream_t st = gp->stream;
+  const int64_t rows = (int64_t)gp->NB * BM;
+  gp->nst = (int)((gp->N + oz::KST - 1) / oz::KST);
+  TB_TRY(gp->dRowScale.reserve(sizeof(double) * rows));
+  oz::linv_rowscale_kernel<<<(unsigned)rows, 256, 0, st>>>(gp->dLinv.as<double>(), gp->N, rows, gp->dRowScale.as<double>());
+  TB_LAUNCHED();
+  const int64_t nstages = oz::a_stage_offset(gp->NB);
+  TB_TRY(gp->dAS.reserve((size_t)nstages * oz::S * oz::TILE));
+  TB_CUDA(cudaMemsetAsync(gp->dAS.p, 0, (size_t)nstages * oz::S * oz::TILE, st));
+  oz::linv_digits_kernel<<<dim3(2 * gp->NB, gp->NB), 256, 0, st>>>(gp->dLinv.as<double>(), gp->N, gp->dRowScale.as<double>(),
+                                                                   gp->dAS.as<int8_t>());
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  int e = 0;
+  std::frexp(gp->variance, &e);  // variance = m 2^e, m in [0.5, 1)  ->  K* / 2^(e+1) < 1/2
+  gp->oz_bscale_exp = e + 1;
+  gp->oz_out_scale = std::ldexp(1.0, gp->oz_bscale_exp + 2);
+  gp->oz_valid = true;
+  return 0;
+}
+
+static int launch_kstar_digits(tb_gp* gp, const double* Xc_dev, int64_t mc, int tiles, int8_t* BS, double* mean) {
+  const double* Xs = gp->dXs.as<double>();
+  const double* al = gp->dAlpha.as<double>();
+  const double* il = gp->dInvLs.as<double>();
+  const int N = (int)gp->N, nst = gp->nst, D = gp->D;
+  const double var = gp->variance, mc0 = gp->mean_const;
+  const double inv_b = std::ldexp(1.0, 48 - gp->oz_bscale_exp);
+  cudaStream_t st = gp->stream;
+#define TB_KD(KIND, DPV) \
+  oz::kstar_digits_kernel<KIND, DPV><<<tiles, 512, 0, st>>>(Xs, al, Xc_dev, il, N, nst, D, mc, var, inv_b, mc0, BS, mean)
+#define TB_KD_DP(KIND)                                   \
+  switch (gp->DP) {                                      \
+    case 2: TB_KD(KIND, 2); break;                       \
+    case 4: TB_KD(KIND, 4); break;                       \
+    case 6: TB_KD(KIND, 6); break;                       \
+    case 8: TB_KD(KIND, 8); break;                       \
+    case 10: TB_KD(KIND, 10); break;                     \
+    case 12: TB_KD(KIND, 12); break;                     \
+    case 16: TB_KD(KIND, 16); break;                     \
+    case 20: TB_KD(KIND, 20); break;                     \
+    case 24: TB_KD(KIND, 24); break;                     \
+    default: TB_KD(KIND, 32); break;                     \
+  }
+  switch (gp->kernel) {
+    case TB_RBF: TB_KD_DP(TB_RBF); break;
+    case TB_MATERN12: TB_KD_DP(TB_MATERN12); break;
+    case TB_MATERN32: TB_KD_DP(TB_MATERN32); break;
+    default: TB_KD_DP(TB_MATERN52); break;
+  }
+#undef TB_KD_DP
+#undef TB_KD
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int run_eval(tb_gp* gp, EvalRequest& rq) {
   TB_CHECK(gp->cache_valid, "posterior cache is not built: call tb_gp_update_posterior_cache first");
   TB_CHECK(rq.M >= 0, "negative candidate count");
@@ -480,7 +544,10 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
   const int64_t tiles_cap = chunk_cap / BT;
   const int Gmax = pick_groups(gp, (int)std::min<int64_t>(tiles_cap, 1 << 30));
 
-  TB_TRY(gp->sKs.reserve((size_t)tiles_cap * gp->nkc * PANEL * sizeof(double)));
+  const bool ozaki = gp->engine == 1 && !rq.out_grad;
+  if (ozaki) TB_TRY(ensure_ozaki(gp));
+  TB_TRY(gp->sKs.reserve(std::max((size_t)tiles_cap * gp->nkc * PANEL * sizeof(double),
+                                  (size_t)tiles_cap * gp->nst * oz::S * oz::TILE)));
   TB_TRY(gp->sPartial.reserve(sizeof(double) * (size_t)Gmax * chunk_cap));
   TB_TRY(gp->sMean.reserve(sizeof(double) * chunk_cap));
   if (!xc_dev) TB_TRY(gp->sXc.reserve(sizeof(double) * chunk_cap * D));
@@ -513,7 +580,11 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
       TB_CUDA(cudaMemcpyAsync(gp->sXc.p, rq.Xc + c0 * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, st));
       xc_chunk = gp->sXc.as<double>();
     }
-    TB_TRY(launch_kstar(gp, xc_chunk, mc, tiles, gp->sKs.as<double>(), gp->sMean.as<double>()));
+    const bool use_oz = ozaki && !rq.out_grad;
+    if (use_oz)
+      TB_TRY(launch_kstar_digits(gp, xc_chunk, mc, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
+    else
+      TB_TRY(launch_kstar(gp, xc_chunk, mc, tiles, gp->sKs.as<double>(), gp->sMean.as<double>()));
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (gp->profile) {
@@ -521,7 +592,11 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
       TB_CUDA(cudaEventCreate(&e1));
       TB_CUDA(cudaEventRecord(e0, st));
     }
-    if (rq.out_grad)
+    if (use_oz)
+      oz::trigemm_i8_kernel<<<dim3(tiles, G), oz::THREADS, oz::SMEM_BYTES, st>>>(
+          gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad,
+          gp->oz_out_scale, gp->sPartial.as<double>());
+    else if (rq.out_grad)
       trigemm_kernel<false, EPI_SUMSQ_PACKED><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
           gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, gp->sPartial.as<double>(),
           gp->sA.as<double>(), nullptr, 0);
@@ -640,6 +715,12 @@ int tb_gp_profile(tb_gp* gp, int enable) {
   gp->prof_ms = 0.0;
   gp->prof_flops = 0.0;
   gp->prof_launches = 0;
+  return 0;
+}
+int tb_gp_set_engine(tb_gp* gp, int engine) {
+  TB_CHECK(gp, "tb_gp_set_engine: null handle");
+  TB_CHECK(engine == 0 || engine == 1, "tb_gp_set_engine: engine must be 0 (fp64 DMMA) or 1 (int8 Ozaki)");
+  gp->engine = engine;
   return 0;
 }
 int tb_gp_stream(tb_gp* gp, void** stream) {

@@ -154,6 +154,18 @@ class GaussianProcessRegression:
             )
         )
 
+    def set_engine(self, engine: str) -> None:
+        """Engine of the variance GEMM (predict / EI / LCB / log-EI / argmax): ``"fp64"`` = native DMMA,
+        ``"int8"`` = fp64-accurate Ozaki splitting on the INT8 tensor cores (same stated tolerances)."""
+        if engine not in ("fp64", "int8"):
+            raise ValueError(f"engine must be 'fp64' or 'int8', got {engine!r}")
+        _lib.check(_lib.lib().tb_gp_set_engine(self._h, 1 if engine == "int8" else 0))
+        self._engine = engine
+
+    @property
+    def engine(self) -> str:
+        return getattr(self, "_engine", "fp64")
+
     def update_posterior_cache(self) -> None:
         """interface.py:108-112 — must follow any change of data or hyper-parameters."""
         _lib.check(_lib.lib().tb_gp_update_posterior_cache(self._h))
