@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--candidates", type=int, default=M_PER_GPU, help="candidates per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default="int8", choices=["int8", "fp64"],
+                    help="variance GEMM engine: int8 = fp64-accurate Ozaki split on the INT8 tensor cores (default), fp64 = native DMMA")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
 
@@ -232,6 +234,7 @@ def main():
     ds = tb.Dataset(X, y)
     spec = tb.build_gpr(ds, tb.Box([0.0] * DIM, [1.0] * DIM))
     model = tb.GaussianProcessRegression(spec, device=local_rank)
+    model.set_engine(args.engine)
     fn = ExpectedImprovement().prepare_acquisition_function(model, ds)
     lib = _lib.lib()
     h = model.handle
@@ -325,23 +328,41 @@ def main():
     e2e_value = world * M * args.steps / (ms_e2e * 1e-3)
 
     if rank == 0:
-        peak_tf = dgemm_peak_tflops()
-        achieved_tf = tg_fl.value / (tg_ms.value * 1e-3) / 1e12 if tg_ms.value > 0 else 0.0
+        dgemm_tf = dgemm_peak_tflops()
+        fp64_eq_tf = tg_fl.value / (tg_ms.value * 1e-3) / 1e12 if tg_ms.value > 0 else 0.0
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # algorithmic HBM bytes per candidate for the dominant kernel: the Ks tile is written
-        # once and re-read once per row-block above it; Linv panels are shared by all CTAs (L2 resident)
         nb = N_TRAIN // 128
-        bytes_per_cand = 8.0 * N_TRAIN * (nb + 1) / 2.0
         cand_per_launch = tg_fl.value / max(tg_n.value, 1) / (N_TRAIN**2)
         avg_launch_s = tg_ms.value * 1e-3 / max(tg_n.value, 1)
+        if args.engine == "int8":
+            # 28 exact int8 digit products per fp64 product: algorithmic int8 ops = 28 N^2 / candidate.
+            # int8 dense rate = 2x the bf16 dense rate on this part (4.5 vs 2.25 POP/s nominal): peak = 2 x the measured
+            # cuBLAS bf16 figure of MEASURED_PEAKS.json (sustained: the kernel is timed inside a long step)
+            ops_per_cand = 28.0 * N_TRAIN**2
+            achieved = ops_per_cand * cand_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0
+            bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+            peak = 2.0 * bf16
+            roof_unit = "TOP/s"
+            kernel_name = "oz::trigemm_i8_kernel (tcgen05 kind::i8, TMEM accumulators)"
+            peak_src = ("of measured: 2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 dense = 2 x bf16 dense on B200); "
+                        "tools/i8_umma_test.cu measured 3838 TOP/s burst for the same 128x128 SS MMA shape")
+            # digit tiles: 7 B per K* element, re-read once per row-block above the diagonal, both passes (11/7 of one read)
+            bytes_per_cand = 7.0 * N_TRAIN * (nb + 1) / 2.0 * (11.0 / 7.0)
+            traffic_key = "trigemm_i8_dram_bytes_per_launch"
+        else:
+            achieved, peak, roof_unit = fp64_eq_tf, dgemm_tf, "TFLOP/s"
+            kernel_name = "trigemm_kernel<false, EPI_SUMSQ> (fp64 DMMA)"
+            peak_src = "of measured: cuBLAS DGEMM 6144^3 in this process (MEASURED_PEAKS.json has no fp64 figure)"
+            bytes_per_cand = 8.0 * N_TRAIN * (nb + 1) / 2.0
+            traffic_key = "trigemm_dram_bytes_per_launch"
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("trigemm_dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(traffic_key)
         except Exception:
             pass
         cpu = None
@@ -354,21 +375,25 @@ def main():
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
+                "engine": ("int8: fp64 operands split error-free into 7 base-128 int8 digits, 28 exact digit GEMMs on tcgen05 "
+                           "kind::i8 with int32 TMEM accumulators, fp64 recombination; parity to the fp64 oracle at 1e-9 sigma_f^2"
+                           if args.engine == "int8" else "fp64: native DMMA triangular GEMM"),
                 "workload": f"headline: EI on GPR N={N_TRAIN} D={DIM} Matern52 fp64, Ackley-10 synthetic (SURVEY.md §8d)",
                 "candidates_per_gpu_per_step": M, "parallelism": f"candidate-sharded x{world}, 1 NCCL all-gather/step",
                 "l2": "256 MiB L2 flush between timed iterations; per-chunk Ks scratch (1.2 GB) also exceeds L2",
             },
             "roofline": {
-                "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": traffic,
-                "kernel": "trigemm_sumsq_kernel (fp64 DMMA)", "launches_timed": tg_n.value,
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": roof_unit,
+                "frac": achieved / peak if peak > 0 else None, "traffic": traffic,
+                "kernel": kernel_name, "launches_timed": tg_n.value,
                 "avg_launch_ms": avg_launch_s * 1e3, "candidates_per_launch": cand_per_launch,
-                "peak_source": "of measured: cuBLAS DGEMM 6144^3 in this process (MEASURED_PEAKS.json has no fp64 figure)",
+                "peak_source": peak_src,
+                "fp64_equivalent_tflops": fp64_eq_tf, "fp64_dgemm_peak_tflops": dgemm_tf,
                 "hbm": {"algorithmic_bytes_per_candidate": bytes_per_cand,
                         "achieved_gbs": bytes_per_cand * cand_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else None,
                         "peak_gbs": hbm_peak,
                         "frac": (bytes_per_cand * cand_per_launch / avg_launch_s / 1e9) / hbm_peak if avg_launch_s > 0 else None,
-                        "note": "kernel is fp64-tensor-pipe bound (arithmetic intensity ~64 flop/B vs ridge ~6); HBM fraction reported for completeness"},
+                        "note": "tensor-pipe bound (N^2 multiply-adds per candidate); HBM fraction reported as the north-star asks"},
             },
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * M * DIM * 8, "d2h_bytes_per_step": world * (M * 8 + 16),

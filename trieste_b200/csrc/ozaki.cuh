@@ -124,7 +124,7 @@ __global__ void linv_digits_kernel(const double* __restrict__ Linv, int64_t N, c
 // contiguous bytes (four adjacent core matrices).
 // ------------------------------------------------------------------------------------------------
 template <int KIND, int DP>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha, const double* __restrict__ Xc,
                     const double* __restrict__ inv_ls, int N, int nst, int D, int64_t M, double variance,
                     double inv_bscale_2p48, double mean_const, int8_t* __restrict__ BS, double* __restrict__ mean_out) {
@@ -187,7 +187,7 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x, g = blockIdx.y;
+  const int g = blockIdx.x, tile = blockIdx.y;  // g fastest: co-resident CTAs share few candidate tiles -> K* digits stay in L2
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 3; ++s) { mbar_init(&full_hi[s], 1); mbar_init(&empty_hi[s], 1); }

@@ -542,7 +542,7 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
   const int64_t Mc_max = max_tiles * BT;
   const int64_t chunk_cap = std::min<int64_t>(Mc_max, ((rq.M + BT - 1) / BT) * BT);
   const int64_t tiles_cap = chunk_cap / BT;
-  const int Gmax = pick_groups(gp, (int)std::min<int64_t>(tiles_cap, 1 << 30));
+  const int Gmax = std::max(pick_groups(gp, (int)std::min<int64_t>(tiles_cap, 1 << 30)), (gp->NB + 1) / 2);
 
   const bool ozaki = gp->engine == 1 && !rq.out_grad;
   if (ozaki) TB_TRY(ensure_ozaki(gp));
@@ -571,7 +571,9 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
     const int64_t mc = std::min<int64_t>(chunk_cap, rq.M - c0);
     const int tiles = (int)((mc + BT - 1) / BT);
     const int64_t McPad = (int64_t)tiles * BT;
-    const int G = pick_groups(gp, tiles);
+    // int8 engine: one serpentine PAIR of row-blocks per CTA, so the ~150 co-resident CTAs touch only ~9 candidate tiles
+    // and their K* digit tiles are re-read from L2 instead of HBM (ncu: 28 GB -> ~1 GB of DRAM reads per launch)
+    const int G = (ozaki && !rq.out_grad) ? std::max(1, (gp->NB + 1) / 2) : pick_groups(gp, tiles);
 
     const double* xc_chunk;
     if (xc_dev) {
@@ -593,7 +595,7 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
       TB_CUDA(cudaEventRecord(e0, st));
     }
     if (use_oz)
-      oz::trigemm_i8_kernel<<<dim3(tiles, G), oz::THREADS, oz::SMEM_BYTES, st>>>(
+      oz::trigemm_i8_kernel<<<dim3(G, tiles), oz::THREADS, oz::SMEM_BYTES, st>>>(
           gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad,
           gp->oz_out_scale, gp->sPartial.as<double>());
     else if (rq.out_grad)
