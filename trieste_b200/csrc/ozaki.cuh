@@ -1,13 +1,14 @@
 // fp64-accurate triangular GEMM on the INT8 tensor cores (Ozaki error-free splitting, tcgen05 kind::i8).
 //
 //   A = Linv · K*  is needed to ~2^-46 relative to |row scale|·|K* scale| for the 1e-9·σ_f² variance bar.
-//   Each fp64 operand is split into S = 7 balanced base-128 digits (int8 in [-64, 64]) under a power-of-two
-//   scale (per row of Linv; one global scale for K*):   x = 2^e · Σ_p d_p · 2^(1-7p).
+//   Each fp64 operand is split into S = 6 balanced base-256 digits (int8 in [-128, 127]) under a power-of-two
+//   scale (per row of Linv; one global scale for K*):   x = 2^e · Σ_p d_p · 2^(-8p)   (48 bits kept).
 //   Products of digit matrices are EXACT in the int32 TMEM accumulators, and all pairs with the same
 //   p + q = r share one accumulator T_r, so
-//        A[n,t] = 2^(e_n + f + 2) · Σ_{r=2..R} 2^(-7r) · T_r[n,t],        R = 8  (28 digit products).
+//        A[n,t] = 2^(e_n + f) · Σ_{r=2..R} 2^(-8r) · T_r[n,t],        R = 7  (21 digit products);
+//   |T_r| <= 6 · K · 2^14 < 2^31 for K <= 16384.
 //   TMEM holds 512 columns = four 128x128 int32 accumulators, so each row-block runs two passes:
-//        pass LO: r = 6,7,8 (18 products, digits 1..7 of both operands), kept as fp64 in registers,
+//        pass LO: r = 6,7   (11 products, digits 1..6 of both operands), kept as fp64 in registers,
 //        pass HI: r = 2..5  (10 products, digits 1..4), then scale, square and column-reduce.
 //   Operands are pre-packed in the UMMA no-swizzle K-major core-matrix layout, so each pipeline stage is two
 //   contiguous 1-D bulk-TMA copies.  Warp roles: 8 epilogue warps, 1 TMA producer, 1 MMA issuer.
@@ -18,31 +19,31 @@
 namespace tb {
 namespace oz {
 
-constexpr int S = 7;                         // digits per operand
+constexpr int S = 6;                         // digits per operand
 constexpr int KST = 64;                      // K bytes (= k columns) per pipeline stage
 constexpr int TILE = 128 * KST;              // one digit tile: 128 rows x 64 k-bytes = 8 KB
 constexpr uint32_t LBO = 128;                // core matrices adjacent in K
 constexpr uint32_t SBO = (KST / 16) * 128;   // 8-row groups
-constexpr int HI_DIG = 4;                    // pass HI uses digits 1..4, pass LO digits 1..7
+constexpr int HI_DIG = 4;                    // pass HI uses digits 1..4, pass LO digits 1..6
 constexpr int STAGES_HI = 3, STAGES_LO = 2;
 constexpr int STAGE_BYTES_HI = 2 * HI_DIG * TILE;   // 64 KB
 constexpr int STAGE_BYTES_LO = 2 * S * TILE;        // 112 KB
 constexpr size_t SMEM_BYTES = (size_t)STAGES_LO * STAGE_BYTES_LO + 256;   // 224 KB + barriers
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
-constexpr int DIGIT_BITS = 48;               // v = rint(x / 2^e * 2^48) = Σ d_p 128^(7-p)
+constexpr int DIGIT_BITS = 48;               // v = rint(x / 2^e * 2^48) = Σ d_p 256^(6-p)
 
 __host__ __device__ inline int64_t a_stage_offset(int I) {  // stages before row-block I: Σ 2(i+1)
   return (int64_t)I * (I + 1);
 }
 
-// balanced base-128 digits of v (|v| <= 2^47): d[0] most significant
+// balanced base-256 digits of v (|v| <= 2^46, so the top digit stays below 128): d[0] most significant
 __device__ __forceinline__ void digits7(long long v, int d[S]) {
 #pragma unroll
   for (int p = S - 1; p >= 0; --p) {
-    int lo = (int)(((v + 64) & 127) - 64);
+    int lo = (int)(((v + 128) & 255) - 128);
     d[p] = lo;
-    v = (v - lo) >> 7;
+    v = (v - lo) >> 8;
   }
 }
 
@@ -94,7 +95,7 @@ __global__ void linv_rowscale_kernel(const double* __restrict__ Linv, int64_t N,
     int e = 0;
     if (mx > 0.0) {
       frexp(mx, &e);  // mx = m 2^e, m in [0.5, 1)
-      e += 1;         // |x| / 2^e < 1/2
+      e += 2;         // |x| / 2^e < 1/4
     }
     if (n < rows) rowscale[n] = ldexp(1.0, e);
   }
@@ -263,7 +264,7 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
           }
           first = false;
           const int ndig = pass == 0 ? S : HI_DIG;
-          const int rlo = pass == 0 ? 6 : 2, rhi = pass == 0 ? 8 : 5;
+          const int rlo = pass == 0 ? 6 : 2, rhi = pass == 0 ? 7 : 5;
           for (int kc = 0; kc < nk; ++kc) {
             uint32_t base;
             if (pass == 0) {
@@ -319,18 +320,16 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
         ph_acc ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (pass == 0) {
-          // v_lo = Σ_{r=6..8} 2^(-7r) T_r   (smallest terms first)
+          // v_lo = Σ_{r=6,7} 2^(-8r) T_r   (smallest terms first)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            uint32_t t8[32], t7[32], t6[32];
-            tmem_ld32(lane_base + 2 * 128 + h * 32, t8);
+            uint32_t t7[32], t6[32];
             tmem_ld32(lane_base + 1 * 128 + h * 32, t7);
             tmem_ld32(lane_base + 0 * 128 + h * 32, t6);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              double v = (double)(int)t8[c] * 0x1p-56;
-              v = fma((double)(int)t7[c], 0x1p-49, v);
-              v = fma((double)(int)t6[c], 0x1p-42, v);
+              double v = (double)(int)t7[c] * 0x1p-56;
+              v = fma((double)(int)t6[c], 0x1p-48, v);
               vlo[h * 32 + c] = v;
             }
           }
@@ -344,10 +343,10 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
             tmem_ld32(lane_base + 0 * 128 + h * 32, t2);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              double v = fma((double)(int)t5[c], 0x1p-35, vlo[h * 32 + c]);
-              v = fma((double)(int)t4[c], 0x1p-28, v);
-              v = fma((double)(int)t3[c], 0x1p-21, v);
-              v = fma((double)(int)t2[c], 0x1p-14, v);
+              double v = fma((double)(int)t5[c], 0x1p-40, vlo[h * 32 + c]);
+              v = fma((double)(int)t4[c], 0x1p-32, v);
+              v = fma((double)(int)t3[c], 0x1p-24, v);
+              v = fma((double)(int)t2[c], 0x1p-16, v);
               v *= rs;          // A[n, t]
               double sq = v * v;
               // column sum over the 32 rows of this warp: butterfly

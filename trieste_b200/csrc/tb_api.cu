@@ -461,7 +461,7 @@ static int gradient_chunk(tb_gp* gp, int acq, double param, const double* xc, in
 // Ozaki engine state: digit tiles of Linv + row scales, built lazily after each cache refresh
 static int ensure_ozaki(tb_gp* gp) {
   if (gp->oz_valid) return 0;
-  TB_CHECK(gp->N <= 32768, "the int8 engine supports N <= 32768 (int32 accumulator headroom)");
+  TB_CHECK(gp->N <= 16384, "the int8 engine supports N <= 16384 (int32 accumulator headroom)");
   cudaStream_t st = gp->stream;
   const int64_t rows = (int64_t)gp->NB * BM;
   gp->nst = (int)((gp->N + oz::KST - 1) / oz::KST);
@@ -476,9 +476,9 @@ static int ensure_ozaki(tb_gp* gp) {
   TB_LAUNCHED();
   TB_CUDA(cudaGetLastError());
   int e = 0;
-  std::frexp(gp->variance, &e);  // variance = m 2^e, m in [0.5, 1)  ->  K* / 2^(e+1) < 1/2
-  gp->oz_bscale_exp = e + 1;
-  gp->oz_out_scale = std::ldexp(1.0, gp->oz_bscale_exp + 2);
+  std::frexp(gp->variance, &e);  // variance = m 2^e, m in [0.5, 1)  ->  K* / 2^(e+2) < 1/4
+  gp->oz_bscale_exp = e + 2;
+  gp->oz_out_scale = std::ldexp(1.0, gp->oz_bscale_exp);
   gp->oz_valid = true;
   return 0;
 }
