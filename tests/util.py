@@ -16,9 +16,12 @@ def native_from_oracle(om, **kw):
     return tb.GaussianProcessRegression(spec, **kw)
 
 
-def model_pair(objective, N, D, kind="matern52", seed=0, noise=None):
+def model_pair(objective, N, D, kind="matern52", seed=0, noise=None, engine=None):
     om = o.synthetic_model(objective, N, D, kind=kind, seed=seed, noise=noise)
-    return om, native_from_oracle(om)
+    nm = native_from_oracle(om)
+    if engine is not None:
+        nm.set_engine(engine)
+    return om, nm
 
 
 def candidates(M, D, seed=1):

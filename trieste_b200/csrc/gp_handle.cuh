@@ -6,6 +6,7 @@
 #include <vector>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace tb {
 
@@ -79,8 +80,14 @@ struct tb_gp {
   tb::DevBuf dLinvTP;           // packed upper panels of Linv^T (lazy; gradient path)
   bool upper_valid = false;
   // int8 (Ozaki) engine: digit tiles of Linv, per-row scales, K* scale
-  int engine = 0;  // 0 = fp64 DMMA, 1 = int8 tensor cores
+  int engine = 1;  // 0 = fp64 DMMA, 1 = int8 tensor cores (default; same stated tolerances, ~3x faster)
   tb::DevBuf dAS, dRowScale;
+  tb::DevBuf sKs2, sMean2, sPartial2;  // second scratch slot of the pipelined driver
+  // dynamic smem requested by the K* digit CTAs only to bound how many of them share an SM with a GEMM CTA (2 by default)
+  size_t kstar_smem = 0;
+  int kstar_threads = 512;
+  cudaStream_t stream2 = nullptr;      // K* digit generation stream (overlaps the digit GEMM)
+  cudaEvent_t evK[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr};
   bool oz_valid = false;
   int nst = 0, oz_bscale_exp = 0;
   double oz_out_scale = 1.0;

@@ -76,6 +76,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // once per BO step: digit tiles of Linv.  grid = (stage kc, row-block I), 256 threads.
 //   rowscale[n] = 2^e_n with 2^e_n > 2 max_k |Linv[n,k]|  (so |x|/2^e < 1/2 and the top digit fits)
@@ -120,7 +129,7 @@ __global__ void linv_digits_kernel(const double* __restrict__ Linv, int64_t N, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// K* digit tiles + posterior mean.  grid = candidate tiles, 512 threads = 16 warps; warp w owns candidates
+// K* digit tiles + posterior mean.  grid = candidate tiles x (512 / blockDim); warp w (0..15 within a tile) owns candidates
 // [8w, 8w+8); lane l <-> (candidate l % 8, 16-wide k chunk l / 8): every digit store of a warp is 512
 // contiguous bytes (four adjacent core matrices).
 // ------------------------------------------------------------------------------------------------
@@ -129,15 +138,17 @@ __global__ void __launch_bounds__(512, 2)
 kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha, const double* __restrict__ Xc,
                     const double* __restrict__ inv_ls, int N, int nst, int D, int64_t M, double variance,
                     double inv_bscale_2p48, double mean_const, int8_t* __restrict__ BS, double* __restrict__ mean_out) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // CTA size is free (any multiple of 32 dividing 512): each warp owns one 8-candidate row group of a tile
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), w = wg & 15, tile_id = wg >> 4;
   const int cl = lane & 7, ch = lane >> 3;
   const int t_local = w * 8 + cl;
-  const int64_t t = (int64_t)blockIdx.x * 128 + t_local;
+  const int64_t t = (int64_t)tile_id * 128 + t_local;
   const bool valid = t < M;
   double xc[DP];
 #pragma unroll
   for (int d = 0; d < DP; ++d) xc[d] = (valid && d < D) ? Xc[t * D + d] * inv_ls[d] : 0.0;
-  int8_t* tile = BS + (int64_t)blockIdx.x * nst * (S * TILE) + w * SBO + ch * LBO + cl * 16;
+  int8_t* tile = BS + (int64_t)tile_id * nst * (S * TILE) + w * SBO + ch * LBO + cl * 16;
   double macc = 0.0;
   for (int kc = 0; kc < nst; ++kc) {
     uint32_t pk[S][4];
@@ -168,7 +179,38 @@ kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ al
   }
   macc += __shfl_xor_sync(0xffffffffu, macc, 8);
   macc += __shfl_xor_sync(0xffffffffu, macc, 16);
-  if (ch == 0) mean_out[(int64_t)blockIdx.x * 128 + t_local] = macc + mean_const;
+  if (ch == 0) mean_out[(int64_t)tile_id * 128 + t_local] = macc + mean_const;
+}
+
+// all MMAs of one pipeline stage, fully unrolled at compile time: per MMA two 32-bit adds on precomputed descriptors
+// (the issuing thread shares its scheduler with co-resident K*-generation warps, so its instruction count matters)
+__device__ __forceinline__ void umma_i8_desc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\nsetp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(IDESC), "r"(acc)
+      : "memory");
+}
+template <int NDIG, int RLO, int RHI>
+__device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t stage_base, uint32_t not_first_kc) {
+  // descriptor = [hi: SBO | version][lo: LBO | start>>4]
+  constexpr uint32_t HI = ((SBO >> 4) & 0x3FFF) | (1u << 14);
+  const uint32_t a0 = ((stage_base >> 4) & 0x3FFF) | (((LBO >> 4) & 0x3FFF) << 16);
+  const uint32_t b0 = a0 + ((NDIG * TILE) >> 4);
+#pragma unroll
+  for (int p = 1; p <= NDIG; ++p)
+#pragma unroll
+    for (int q = 1; q <= NDIG; ++q) {
+      const int r = p + q;
+      if (r < RLO || r > RHI) continue;
+      const uint32_t acc = tmem + (uint32_t)(r - RLO) * 128u;
+      const bool first_pair = (p == (r - NDIG > 1 ? r - NDIG : 1));
+#pragma unroll
+      for (int kk = 0; kk < KST / 32; ++kk) {
+        const uint32_t flag = (first_pair && kk == 0) ? not_first_kc : 1u;
+        umma_i8_desc(acc, a0 + (((p - 1) * TILE + kk * 2 * (int)LBO) >> 4), b0 + (((q - 1) * TILE + kk * 2 * (int)LBO) >> 4), HI, flag);
+      }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -263,8 +305,6 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
           first = false;
-          const int ndig = pass == 0 ? S : HI_DIG;
-          const int rlo = pass == 0 ? 6 : 2, rhi = pass == 0 ? 7 : 5;
           for (int kc = 0; kc < nk; ++kc) {
             uint32_t base;
             if (pass == 0) {
@@ -275,22 +315,10 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
               base = smem_u32(smem + (size_t)st_hi * STAGE_BYTES_HI);
             }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t aB = base, bB = base + ndig * TILE;
-            for (int p = 1; p <= ndig; ++p)
-              for (int q = 1; q <= ndig; ++q) {
-                const int r = p + q;
-                if (r < rlo || r > rhi) continue;
-                const uint32_t acc = tmem + (uint32_t)(r - rlo) * 128u;
-#pragma unroll
-                for (int kk = 0; kk < KST / 32; ++kk) {
-                  const uint64_t da = make_desc(aB + (p - 1) * TILE + kk * 2 * LBO);
-                  const uint64_t db = make_desc(bB + (q - 1) * TILE + kk * 2 * LBO);
-                  // first MMA into this accumulator in this pass: (kc == 0, kk == 0) and first pair of group r,
-                  // i.e. p == max(1, r - ndig)
-                  const bool fresh = (kc == 0) && (kk == 0) && (p == (r - ndig > 1 ? r - ndig : 1));
-                  umma_i8(acc, da, db, fresh ? 0u : 1u);
-                }
-              }
+            if (pass == 0)
+              issue_stage<S, 6, 7>(tmem, base, kc != 0 ? 1u : 0u);
+            else
+              issue_stage<HI_DIG, 2, 5>(tmem, base, kc != 0 ? 1u : 0u);
             if (pass == 0) {
               umma_commit(&empty_lo[st_lo]);
               if (++st_lo == STAGES_LO) { st_lo = 0; ph_lo ^= 1; }
@@ -320,30 +348,30 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
         ph_acc ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (pass == 0) {
-          // v_lo = Σ_{r=6,7} 2^(-8r) T_r   (smallest terms first)
+          // v_lo = Σ_{r=6,7} 2^(-8r) T_r   (smallest terms first); 16 columns at a time keeps registers low
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t t7[32], t6[32];
-            tmem_ld32(lane_base + 1 * 128 + h * 32, t7);
-            tmem_ld32(lane_base + 0 * 128 + h * 32, t6);
+          for (int h = 0; h < 4; ++h) {
+            uint32_t t7[16], t6[16];
+            tmem_ld16(lane_base + 1 * 128 + h * 16, t7);
+            tmem_ld16(lane_base + 0 * 128 + h * 16, t6);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
+            for (int c = 0; c < 16; ++c) {
               double v = (double)(int)t7[c] * 0x1p-56;
               v = fma((double)(int)t6[c], 0x1p-48, v);
-              vlo[h * 32 + c] = v;
+              vlo[h * 16 + c] = v;
             }
           }
         } else {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t t5[32], t4[32], t3[32], t2[32];
-            tmem_ld32(lane_base + 3 * 128 + h * 32, t5);
-            tmem_ld32(lane_base + 2 * 128 + h * 32, t4);
-            tmem_ld32(lane_base + 1 * 128 + h * 32, t3);
-            tmem_ld32(lane_base + 0 * 128 + h * 32, t2);
+          for (int h = 0; h < 4; ++h) {
+            uint32_t t5[16], t4[16], t3[16], t2[16];
+            tmem_ld16(lane_base + 3 * 128 + h * 16, t5);
+            tmem_ld16(lane_base + 2 * 128 + h * 16, t4);
+            tmem_ld16(lane_base + 1 * 128 + h * 16, t3);
+            tmem_ld16(lane_base + 0 * 128 + h * 16, t2);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              double v = fma((double)(int)t5[c], 0x1p-40, vlo[h * 32 + c]);
+            for (int c = 0; c < 16; ++c) {
+              double v = fma((double)(int)t5[c], 0x1p-40, vlo[h * 16 + c]);
               v = fma((double)(int)t4[c], 0x1p-32, v);
               v = fma((double)(int)t3[c], 0x1p-24, v);
               v = fma((double)(int)t2[c], 0x1p-16, v);
@@ -352,8 +380,8 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
               // column sum over the 32 rows of this warp: butterfly
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-              if (lane == c) {
-                if (h == 0) colsum0 += sq; else colsum1 += sq;
+              if (lane == (h & 1) * 16 + c) {
+                if (h < 2) colsum0 += sq; else colsum1 += sq;
               }
             }
           }

@@ -132,7 +132,19 @@ int tb_gp_create(tb_gp** out, int device, int dtype) {
   tb_gp* gp = new tb_gp();
   gp->device = device;
   gp->dtype = dtype;
-  TB_CUDA(cudaStreamCreateWithFlags(&gp->stream, cudaStreamNonBlocking));
+  if (const char* e = std::getenv("TB_ENGINE")) gp->engine = (std::string(e) == "fp64") ? 0 : 1;
+  if (const char* e = std::getenv("TB_KSTAR_SMEM")) gp->kstar_smem = (size_t)std::atol(e);
+  if (const char* e = std::getenv("TB_KSTAR_THREADS")) {
+    int t = std::atoi(e);
+    if (t == 128 || t == 256 || t == 512) gp->kstar_threads = t;
+  }
+  {
+    // main stream at the highest priority: when the K*-generation stream (lowest) runs concurrently, GEMM CTAs are placed
+    // first and the generation CTAs only fill the register / thread slots a GEMM CTA leaves free
+    int least = 0, greatest = 0;
+    TB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    TB_CUDA(cudaStreamCreateWithPriority(&gp->stream, cudaStreamNonBlocking, greatest));
+  }
   TB_CUBLAS(cublasCreate(&gp->cublas));
   TB_CUBLAS(cublasSetStream(gp->cublas, gp->stream));
   TB_CUSOLVER(cusolverDnCreate(&gp->cusolver));
@@ -147,13 +159,21 @@ int tb_gp_destroy(tb_gp* gp) {
   cudaSetDevice(gp->device);
   cudaStreamSynchronize(gp->stream);
   for (tb::DevBuf* b : {&gp->dX, &gp->dy, &gp->dXs, &gp->dInvLs, &gp->dAlpha, &gp->dL, &gp->dLinv,
-                        &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
+                        &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->sKs2, &gp->sMean2, &gp->sPartial2, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
                         &gp->sVals, &gp->sVar, &gp->sXc, &gp->sBlkBest, &gp->sBlkIdx, &gp->sRun,
                         &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc})
     b->release();
   for (auto& ev : gp->prof_events) {
     cudaEventDestroy(ev.first);
     cudaEventDestroy(ev.second);
+  }
+  if (gp->stream2) {
+    cudaStreamSynchronize(gp->stream2);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(gp->evK[i]);
+      cudaEventDestroy(gp->evDone[i]);
+    }
+    cudaStreamDestroy(gp->stream2);
   }
   if (gp->cusolver) cusolverDnDestroy(gp->cusolver);
   if (gp->cublas) cublasDestroy(gp->cublas);
@@ -492,7 +512,7 @@ static int launch_kstar_digits(tb_gp* gp, const double* Xc_dev, int64_t mc, int 
   const double inv_b = std::ldexp(1.0, 48 - gp->oz_bscale_exp);
   cudaStream_t st = gp->stream;
 #define TB_KD(KIND, DPV) \
-  oz::kstar_digits_kernel<KIND, DPV><<<tiles, 512, 0, st>>>(Xs, al, Xc_dev, il, N, nst, D, mc, var, inv_b, mc0, BS, mean)
+  oz::kstar_digits_kernel<KIND, DPV><<<tiles * (512 / gp->kstar_threads), gp->kstar_threads, gp->kstar_smem, st>>>(Xs, al, Xc_dev, il, N, nst, D, mc, var, inv_b, mc0, BS, mean)
 #define TB_KD_DP(KIND)                                   \
   switch (gp->DP) {                                      \
     case 2: TB_KD(KIND, 2); break;                       \
@@ -519,9 +539,158 @@ static int launch_kstar_digits(tb_gp* gp, const double* Xc_dev, int64_t mc, int 
   return 0;
 }
 
+// Pipelined driver of the int8 engine: K* digit generation of chunk c+1 (fp64 / integer pipes, stream B) overlaps the
+// digit GEMM of chunk c (tensor pipe, stream A); scratch is double-buffered and nothing synchronises with the host until
+// the end of the call.
+static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
+  TB_CUDA(cudaSetDevice(gp->device));
+  cudaStream_t sa = gp->stream;
+  if (!gp->stream2) {
+    int lo = 0, hi = 0;
+    TB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    TB_CUDA(cudaStreamCreateWithPriority(&gp->stream2, cudaStreamNonBlocking, lo));  // lowest priority
+    for (int i = 0; i < 2; ++i) {
+      TB_CUDA(cudaEventCreateWithFlags(&gp->evK[i], cudaEventDisableTiming));
+      TB_CUDA(cudaEventCreateWithFlags(&gp->evDone[i], cudaEventDisableTiming));
+    }
+  }
+  // K* generation on a second stream is an experiment switch (TB_OZ_OVERLAP=1): measured on B200 it does not pay, because the
+  // generation kernel needs >= 8 resident warps per SM to keep pace and a resident GEMM CTA leaves room for fewer
+  cudaStream_t sb = std::getenv("TB_OZ_OVERLAP") ? gp->stream2 : sa;
+  const int D = gp->D;
+  if (rq.want_argmax) {
+    TB_CHECK(rq.M > 0, "argmax over an empty candidate set");
+    TB_TRY(gp->sRun.reserve(16));
+    double init_v = -DBL_MAX;
+    int64_t init_i = INT64_MAX;
+    TB_CUDA(cudaMemcpyAsync(gp->sRun.p, &init_v, 8, cudaMemcpyHostToDevice, sa));
+    TB_CUDA(cudaMemcpyAsync((char*)gp->sRun.p + 8, &init_i, 8, cudaMemcpyHostToDevice, sa));
+  }
+  if (rq.M == 0) return 0;
+  TB_TRY(ensure_ozaki(gp));
+  TB_CUDA(cudaStreamSynchronize(sa));  // digit tiles of Linv are built on stream A; stream B reads model state too
+
+  const bool xc_dev = is_device_ptr(rq.Xc);
+  const bool vals_dev = is_device_ptr(rq.out_vals), mean_dev = is_device_ptr(rq.out_mean), var_dev = is_device_ptr(rq.out_var);
+  // half the usual scratch budget per slot (two slots are live)
+  const size_t per_tile = (size_t)gp->nst * oz::S * oz::TILE;
+  int64_t max_tiles = std::max<int64_t>(1, (int64_t)(((size_t)1024 << 20) / per_tile));
+  if (max_tiles >= 148) max_tiles = (max_tiles / 148) * 148;
+  max_tiles = std::min<int64_t>(max_tiles, 148 * 8);
+  const int64_t chunk_cap = std::min<int64_t>(max_tiles * BT, ((rq.M + BT - 1) / BT) * BT);
+  const int64_t tiles_cap = chunk_cap / BT;
+  const int G = std::max(1, (gp->NB + 1) / 2);
+  tb::DevBuf* ks[2] = {&gp->sKs, &gp->sKs2};
+  tb::DevBuf* mean[2] = {&gp->sMean, &gp->sMean2};
+  tb::DevBuf* part[2] = {&gp->sPartial, &gp->sPartial2};
+  const int nslots = rq.M > chunk_cap ? 2 : 1;
+  for (int i = 0; i < nslots; ++i) {
+    TB_TRY(ks[i]->reserve((size_t)tiles_cap * per_tile));
+    TB_TRY(mean[i]->reserve(sizeof(double) * chunk_cap));
+    TB_TRY(part[i]->reserve(sizeof(double) * (size_t)G * chunk_cap));
+  }
+  if (!xc_dev) TB_TRY(gp->sXc.reserve(sizeof(double) * chunk_cap * D));
+  if (rq.out_vals && !vals_dev) TB_TRY(gp->sVals.reserve(sizeof(double) * chunk_cap));
+  if (rq.out_var && !var_dev) TB_TRY(gp->sVar.reserve(sizeof(double) * chunk_cap));
+  const int tail_blocks_cap = (int)((chunk_cap + 255) / 256);
+  if (rq.want_argmax) {
+    TB_TRY(gp->sBlkBest.reserve(sizeof(double) * tail_blocks_cap));
+    TB_TRY(gp->sBlkIdx.reserve(sizeof(int64_t) * tail_blocks_cap));
+  }
+
+  int64_t c = 0;
+  for (int64_t c0 = 0; c0 < rq.M; c0 += chunk_cap, ++c) {
+    const int slot = (int)(c & 1);
+    const int64_t mc = std::min<int64_t>(chunk_cap, rq.M - c0);
+    const int tiles = (int)((mc + BT - 1) / BT);
+    const int64_t McPad = (int64_t)tiles * BT;
+    // ---- stream B: candidates in, K* digits + mean out ----
+    if (c >= 2) TB_CUDA(cudaStreamWaitEvent(sb, gp->evDone[slot], 0));
+    const double* xc_chunk;
+    if (xc_dev) {
+      xc_chunk = rq.Xc + c0 * D;
+    } else {
+      TB_CUDA(cudaMemcpyAsync(gp->sXc.p, rq.Xc + c0 * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, sb));
+      xc_chunk = gp->sXc.as<double>();
+    }
+    {
+      cudaStream_t keep = gp->stream;
+      gp->stream = sb;  // launch_kstar_digits launches on gp->stream
+      int rc = launch_kstar_digits(gp, xc_chunk, mc, tiles, ks[slot]->as<int8_t>(), mean[slot]->as<double>());
+      gp->stream = keep;
+      TB_TRY(rc);
+    }
+    TB_CUDA(cudaEventRecord(gp->evK[slot], sb));
+    // ---- stream A: digit GEMM, tail, reductions, results out ----
+    TB_CUDA(cudaStreamWaitEvent(sa, gp->evK[slot], 0));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (gp->profile) {
+      TB_CUDA(cudaEventCreate(&e0));
+      TB_CUDA(cudaEventCreate(&e1));
+      TB_CUDA(cudaEventRecord(e0, sa));
+    }
+    oz::trigemm_i8_kernel<<<dim3(G, tiles), oz::THREADS, oz::SMEM_BYTES, sa>>>(
+        gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
+        part[slot]->as<double>());
+    TB_LAUNCHED();
+    if (gp->profile) {
+      TB_CUDA(cudaEventRecord(e1, sa));
+      gp->prof_events.emplace_back(e0, e1);
+      gp->prof_event_flops.push_back((double)McPad * (double)gp->N * (double)gp->N);
+    }
+    TB_CUDA(cudaGetLastError());
+    double* d_vals = rq.out_vals ? (vals_dev ? rq.out_vals + c0 : gp->sVals.as<double>()) : nullptr;
+    double* d_mean = rq.out_mean ? (mean_dev ? rq.out_mean + c0 : nullptr) : nullptr;
+    double* d_var = rq.out_var ? (var_dev ? rq.out_var + c0 : gp->sVar.as<double>()) : nullptr;
+    const int tb_blocks = (int)((mc + 255) / 256);
+    tail_kernel<<<tb_blocks, 256, 0, sa>>>(part[slot]->as<double>(), G, McPad, mean[slot]->as<double>(), mc, c0, gp->variance,
+                                           rq.acq, rq.param, d_vals, d_mean, d_var,
+                                           rq.want_argmax ? gp->sBlkBest.as<double>() : nullptr,
+                                           rq.want_argmax ? gp->sBlkIdx.as<int64_t>() : nullptr);
+    TB_LAUNCHED();
+    if (rq.want_argmax) {
+      argmax_fold_kernel<<<1, 256, 0, sa>>>(gp->sBlkBest.as<double>(), gp->sBlkIdx.as<int64_t>(), tb_blocks,
+                                            gp->sRun.as<double>(), reinterpret_cast<int64_t*>((char*)gp->sRun.p + 8));
+      TB_LAUNCHED();
+    }
+    if (rq.out_vals && !vals_dev)
+      TB_CUDA(cudaMemcpyAsync(rq.out_vals + c0, gp->sVals.p, sizeof(double) * mc, cudaMemcpyDeviceToHost, sa));
+    if (rq.out_mean && !mean_dev)
+      TB_CUDA(cudaMemcpyAsync(rq.out_mean + c0, mean[slot]->p, sizeof(double) * mc, cudaMemcpyDeviceToHost, sa));
+    if (rq.out_var && !var_dev)
+      TB_CUDA(cudaMemcpyAsync(rq.out_var + c0, gp->sVar.p, sizeof(double) * mc, cudaMemcpyDeviceToHost, sa));
+    TB_CUDA(cudaEventRecord(gp->evDone[slot], sa));
+    // the host staging of the candidates is single-buffered: the next H2D (stream B) must not overtake this chunk's kstar,
+    // which stream order on B already guarantees
+  }
+  if (rq.want_argmax) {
+    TB_CUDA(cudaMemcpyAsync(&rq.best_value, gp->sRun.p, 8, cudaMemcpyDeviceToHost, sa));
+    TB_CUDA(cudaMemcpyAsync(&rq.best_index, (char*)gp->sRun.p + 8, 8, cudaMemcpyDeviceToHost, sa));
+  }
+  TB_CUDA(cudaStreamSynchronize(sb));
+  TB_CUDA(cudaStreamSynchronize(sa));
+  TB_CUDA(cudaGetLastError());
+  if (gp->profile) {
+    for (size_t i = 0; i < gp->prof_events.size(); ++i) {
+      float ms = 0.f;
+      TB_CUDA(cudaEventElapsedTime(&ms, gp->prof_events[i].first, gp->prof_events[i].second));
+      gp->prof_ms += ms;
+      gp->prof_flops += gp->prof_event_flops[i];
+      gp->prof_launches += 1;
+      cudaEventDestroy(gp->prof_events[i].first);
+      cudaEventDestroy(gp->prof_events[i].second);
+    }
+    gp->prof_events.clear();
+    gp->prof_event_flops.clear();
+  }
+  return 0;
+}
+
 static int run_eval(tb_gp* gp, EvalRequest& rq) {
   TB_CHECK(gp->cache_valid, "posterior cache is not built: call tb_gp_update_posterior_cache first");
   TB_CHECK(rq.M >= 0, "negative candidate count");
+  // int32 accumulators of the int8 engine are exact up to K = 16384; larger models use the native fp64 engine
+  if (gp->engine == 1 && !rq.out_grad && gp->N <= 16384) return run_eval_oz(gp, rq);
   TB_CUDA(cudaSetDevice(gp->device));
   cudaStream_t st = gp->stream;
   const int D = gp->D;

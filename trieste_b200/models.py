@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -164,7 +165,7 @@ class GaussianProcessRegression:
 
     @property
     def engine(self) -> str:
-        return getattr(self, "_engine", "fp64")
+        return getattr(self, "_engine", "int8" if os.environ.get("TB_ENGINE", "int8") != "fp64" else "fp64")
 
     def update_posterior_cache(self) -> None:
         """interface.py:108-112 — must follow any change of data or hyper-parameters."""
