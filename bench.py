@@ -340,10 +340,10 @@ def main():
         cand_per_launch = tg_fl.value / max(tg_n.value, 1) / (N_TRAIN**2)
         avg_launch_s = tg_ms.value * 1e-3 / max(tg_n.value, 1)
         if args.engine == "int8":
-            # 28 exact int8 digit products per fp64 product: algorithmic int8 ops = 28 N^2 / candidate.
+            # 21 exact int8 digit products per fp64 product: algorithmic int8 ops = 21 N^2 / candidate.
             # int8 dense rate = 2x the bf16 dense rate on this part (4.5 vs 2.25 POP/s nominal): peak = 2 x the measured
             # cuBLAS bf16 figure of MEASURED_PEAKS.json (sustained: the kernel is timed inside a long step)
-            ops_per_cand = 28.0 * N_TRAIN**2
+            ops_per_cand = 21.0 * N_TRAIN**2
             achieved = ops_per_cand * cand_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0
             bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
             peak = 2.0 * bf16
@@ -351,8 +351,8 @@ def main():
             kernel_name = "oz::trigemm_i8_kernel (tcgen05 kind::i8, TMEM accumulators)"
             peak_src = ("of measured: 2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 dense = 2 x bf16 dense on B200); "
                         "tools/i8_umma_test.cu measured 3838 TOP/s burst for the same 128x128 SS MMA shape")
-            # digit tiles: 7 B per K* element, re-read once per row-block above the diagonal, both passes (11/7 of one read)
-            bytes_per_cand = 7.0 * N_TRAIN * (nb + 1) / 2.0 * (11.0 / 7.0)
+            # HBM: the K* digit tiles (6 B / element) are written once and, with the L2-friendly CTA order, read ~once
+            bytes_per_cand = 2.0 * 6.0 * N_TRAIN
             traffic_key = "trigemm_i8_dram_bytes_per_launch"
         else:
             achieved, peak, roof_unit = fp64_eq_tf, dgemm_tf, "TFLOP/s"
@@ -375,7 +375,7 @@ def main():
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "engine": ("int8: fp64 operands split error-free into 7 base-128 int8 digits, 28 exact digit GEMMs on tcgen05 "
+                "engine": ("int8: fp64 operands split error-free into 6 base-256 int8 digits, 21 exact digit GEMMs on tcgen05 "
                            "kind::i8 with int32 TMEM accumulators, fp64 recombination; parity to the fp64 oracle at 1e-9 sigma_f^2"
                            if args.engine == "int8" else "fp64: native DMMA triangular GEMM"),
                 "workload": f"headline: EI on GPR N={N_TRAIN} D={DIM} Matern52 fp64, Ackley-10 synthetic (SURVEY.md §8d)",

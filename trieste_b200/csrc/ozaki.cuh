@@ -47,6 +47,54 @@ __device__ __forceinline__ void digits7(long long v, int d[S]) {
   }
 }
 
+// The same 6 digits without a carry chain: v = Σ d_p 256^(6-p) with d_p in [-128,127]  <=>  the ordinary base-256 digits of
+// u = v + Σ 128·256^i are d_p + 128, so the int8 digits are the bytes of (u ^ 0x808080808080); byte 0 = least significant = d_6.
+__device__ __forceinline__ void digit_bytes6(long long v, uint32_t& lo, uint32_t& hi) {
+  const unsigned long long K = 0x0000808080808080ULL;
+  const unsigned long long w = ((unsigned long long)v + K) ^ K;
+  lo = (uint32_t)w;
+  hi = (uint32_t)(w >> 32);
+}
+// insert byte SRC (0..3) of w into byte POS (0..3) of acc: one PRMT
+template <int POS, int SRC>
+__device__ __forceinline__ uint32_t put_byte(uint32_t acc, uint32_t w) {
+  constexpr uint32_t sel = (POS == 0 ? (4u + SRC) : 0u) | ((POS == 1 ? (4u + SRC) : 1u) << 4) | ((POS == 2 ? (4u + SRC) : 2u) << 8) |
+                           ((POS == 3 ? (4u + SRC) : 3u) << 12);
+  return __byte_perm(acc, w, sel);
+}
+// scatter the six digit bytes of one element into the six digit planes: element index JJ (0..15) within the lane's 16-byte rows
+template <int JJ>
+__device__ __forceinline__ void scatter_digits(uint32_t (&pk)[S][4], uint32_t lo, uint32_t hi) {
+  // plane p (0 = most significant digit d_1) takes byte (5 - p) of w
+  pk[0][JJ >> 2] = put_byte<JJ & 3, 1>(pk[0][JJ >> 2], hi);
+  pk[1][JJ >> 2] = put_byte<JJ & 3, 0>(pk[1][JJ >> 2], hi);
+  pk[2][JJ >> 2] = put_byte<JJ & 3, 3>(pk[2][JJ >> 2], lo);
+  pk[3][JJ >> 2] = put_byte<JJ & 3, 2>(pk[3][JJ >> 2], lo);
+  pk[4][JJ >> 2] = put_byte<JJ & 3, 1>(pk[4][JJ >> 2], lo);
+  pk[5][JJ >> 2] = put_byte<JJ & 3, 0>(pk[5][JJ >> 2], lo);
+}
+
+__device__ __forceinline__ void scatter_digits_rt(uint32_t (&pk)[S][4], int jj, uint32_t lo, uint32_t hi) {
+  switch (jj) {  // jj is a compile-time constant after unrolling: the switch folds away
+    case 0: scatter_digits<0>(pk, lo, hi); break;
+    case 1: scatter_digits<1>(pk, lo, hi); break;
+    case 2: scatter_digits<2>(pk, lo, hi); break;
+    case 3: scatter_digits<3>(pk, lo, hi); break;
+    case 4: scatter_digits<4>(pk, lo, hi); break;
+    case 5: scatter_digits<5>(pk, lo, hi); break;
+    case 6: scatter_digits<6>(pk, lo, hi); break;
+    case 7: scatter_digits<7>(pk, lo, hi); break;
+    case 8: scatter_digits<8>(pk, lo, hi); break;
+    case 9: scatter_digits<9>(pk, lo, hi); break;
+    case 10: scatter_digits<10>(pk, lo, hi); break;
+    case 11: scatter_digits<11>(pk, lo, hi); break;
+    case 12: scatter_digits<12>(pk, lo, hi); break;
+    case 13: scatter_digits<13>(pk, lo, hi); break;
+    case 14: scatter_digits<14>(pk, lo, hi); break;
+    default: scatter_digits<15>(pk, lo, hi); break;
+  }
+}
+
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((LBO >> 4) & 0x3FFF) << 16;
@@ -168,10 +216,9 @@ kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ al
       }
       const double kval = (valid && k < N) ? kernel_from_r2<KIND>(r2, variance) : 0.0;
       macc = fma(kval, __ldg(alpha + k), macc);
-      int dg[S];
-      digits7(__double2ll_rn(kval * inv_bscale_2p48), dg);
-#pragma unroll
-      for (int p = 0; p < S; ++p) pk[p][j >> 2] |= (uint32_t)(dg[p] & 0xff) << (8 * (j & 3));
+      uint32_t wl, wh;
+      digit_bytes6(__double2ll_rn(kval * inv_bscale_2p48), wl, wh);
+      scatter_digits_rt(pk, j, wl, wh);
     }
 #pragma unroll
     for (int p = 0; p < S; ++p)
@@ -180,6 +227,85 @@ kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ al
   macc += __shfl_xor_sync(0xffffffffu, macc, 8);
   macc += __shfl_xor_sync(0xffffffffu, macc, 16);
   if (ch == 0) mean_out[(int64_t)tile_id * 128 + t_local] = macc + mean_const;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K* digit tiles, distances on the DMMA pipe.  Same output as kstar_digits_kernel, but the D-dimensional dot
+// products x~* . x~_k of a warp's 8 candidates x 64 training points run as 8 x ceil(D/4) m8n8k4 DMMAs per stage
+// (GPflow's own expansion r^2 = |a|^2 + |b|^2 - 2 a.b), instead of 2 D scalar fp64 ops per pair.  The training
+// point fed into column c of n-tile j is k = 16 (c >> 1) + 2 j + (c & 1), so that lane (cand = l / 4, m = l % 4)
+// receives exactly the 16 consecutive k of its 16-byte digit row.
+// ------------------------------------------------------------------------------------------------
+template <int KIND, int DP4>
+__global__ void __launch_bounds__(512, 2)
+kstar_digits_mma_kernel(const double* __restrict__ Xs, int DP, const double* __restrict__ xn2, const double* __restrict__ alpha,
+                        const double* __restrict__ Xc, const double* __restrict__ inv_ls, int N, int nst, int D, int64_t M,
+                        double variance, double inv_bscale_2p48, double mean_const, int8_t* __restrict__ BS,
+                        double* __restrict__ mean_out) {
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), w = wg & 15, tile_id = wg >> 4;
+  const int cl = lane >> 2, m = lane & 3;
+  const int t_local = w * 8 + cl;
+  const int64_t t = (int64_t)tile_id * 128 + t_local;
+  const bool valid = t < M;
+  double afr[DP4];
+  double cn2 = 0.0;
+#pragma unroll
+  for (int s = 0; s < DP4; ++s) {
+    const int d = 4 * s + m;
+    afr[s] = (valid && d < D) ? Xc[t * D + d] * inv_ls[d] : 0.0;
+    cn2 = fma(afr[s], afr[s], cn2);
+  }
+  cn2 += __shfl_xor_sync(0xffffffffu, cn2, 1);
+  cn2 += __shfl_xor_sync(0xffffffffu, cn2, 2);
+  int8_t* tile = BS + (int64_t)tile_id * nst * (S * TILE) + w * SBO + m * LBO + cl * 16;
+  // B-fragment source row of this lane for n-tile j: k = kc*64 + 16 (cl >> 1) + 2 j + (cl & 1)
+  const int kb = 16 * (cl >> 1) + (cl & 1);
+  double macc = 0.0;
+  for (int kc = 0; kc < nst; ++kc) {
+    const int k0 = kc * KST + 16 * m;  // this lane's 16 output columns: k0 .. k0+15
+    uint32_t pk[S][4];
+#pragma unroll
+    for (int p = 0; p < S; ++p) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double c0 = 0.0, c1 = 0.0;
+      const double* xr = Xs + (int64_t)(kc * KST + kb + 2 * j) * DP;
+#pragma unroll
+      for (int s = 0; s < DP4; ++s) {
+        const int d = 4 * s + m;
+        const double bfr = d < DP ? __ldg(xr + d) : 0.0;
+        dmma_m8n8k4(c0, c1, afr[s], bfr);
+      }
+      const double2 xn = __ldg(reinterpret_cast<const double2*>(xn2 + k0 + 2 * j));
+      const double2 al = __ldg(reinterpret_cast<const double2*>(alpha + k0 + 2 * j));
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = k0 + 2 * j + e;
+        const double r2 = fmax(fma(-2.0, e ? c1 : c0, cn2 + (e ? xn.y : xn.x)), 0.0);
+        const double kval = (valid && k < N) ? kernel_from_r2<KIND>(r2, variance) : 0.0;
+        macc = fma(kval, e ? al.y : al.x, macc);
+        uint32_t wl, wh;
+        digit_bytes6(__double2ll_rn(kval * inv_bscale_2p48), wl, wh);
+        scatter_digits_rt(pk, 2 * j + e, wl, wh);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < S; ++p)
+      *reinterpret_cast<uint4*>(tile + (int64_t)kc * (S * TILE) + p * TILE) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+  }
+  macc += __shfl_xor_sync(0xffffffffu, macc, 1);
+  macc += __shfl_xor_sync(0xffffffffu, macc, 2);
+  if (m == 0) mean_out[(int64_t)tile_id * 128 + t_local] = macc + mean_const;
+}
+
+// |x~_k|^2 of the scaled training inputs (zero rows beyond N)
+__global__ void rownorm2_kernel(const double* __restrict__ Xs, int DP, int64_t rows, double* __restrict__ xn2) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= rows) return;
+  double s = 0.0;
+  for (int d = 0; d < DP; ++d) s = fma(Xs[k * DP + d], Xs[k * DP + d], s);
+  xn2[k] = s;
 }
 
 // all MMAs of one pipeline stage, fully unrolled at compile time: per MMA two 32-bit adds on precomputed descriptors
@@ -191,6 +317,9 @@ __device__ __forceinline__ void umma_i8_desc(uint32_t tmem_d, uint32_t a_lo, uin
       "r"(a_lo), "r"(b_lo), "r"(hi), "r"(IDESC), "r"(acc)
       : "memory");
 }
+// pass order inside a CTA: LO HI | HI LO | LO HI ... so that consecutive row-blocks meet on the same stage geometry
+__device__ __forceinline__ bool pass_is_lo(int i, int j) { return ((i & 1) == 0) == (j == 0); }
+
 template <int NDIG, int RLO, int RHI>
 __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t stage_base, uint32_t not_first_kc) {
   // descriptor = [hi: SBO | version][lo: LBO | start>>4]
@@ -252,24 +381,26 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
   if (warp == EPI_WARPS) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int st_hi = 0, st_lo = 0;
-      uint32_t ph_hi = 0, ph_lo = 0, ph_acc = 0;
-      bool first = true;
+      int st_hi = 0, st_lo = 0, n = 0, seen = 0;  // seen = completions of acc_full already observed
+      uint32_t ph_hi = 0, ph_lo = 0;
+      bool prev_lo = false;
       for (int i = 0;; ++i) {
         const int I = serpentine_rowblock(i, g, G);
         if (I >= NB) break;
         const int nk = min(2 * (I + 1), nst);
         const int8_t* aRow = AS + a_stage_offset(I) * (int64_t)(S * TILE);
-        for (int pass = 0; pass < 2; ++pass) {  // 0 = LO (digits 1..7), 1 = HI (digits 1..4)
-          if (!first) {  // the two passes use different stage geometries over the same bytes:
-            mbar_wait(acc_full, ph_acc);  // wait until every MMA of the previous pass has retired
-            ph_acc ^= 1;
-          }
-          first = false;
+        for (int j = 0; j < 2; ++j, ++n) {
+          const bool lo = pass_is_lo(i, j);
+          // the two pass types lay different stage geometries over the same bytes: on a type change wait until every MMA
+          // of the previous pass has retired (completion #n of acc_full); same-type passes just keep streaming
+          // (completions are consumed one by one: a parity wait cannot tell completion #k from #k+2)
+          if (n > 0 && lo != prev_lo)
+            for (; seen < n; ++seen) mbar_wait(acc_full, (uint32_t)(seen & 1));
+          prev_lo = lo;
           for (int kc = 0; kc < nk; ++kc) {
             const int8_t* a = aRow + (int64_t)kc * (S * TILE);
             const int8_t* b = bTile + (int64_t)kc * (S * TILE);
-            if (pass == 0) {
+            if (lo) {
               mbar_wait(&empty_lo[st_lo], ph_lo ^ 1);
               unsigned char* dst = smem + (size_t)st_lo * STAGE_BYTES_LO;
               mbar_expect_tx(&full_lo[st_lo], STAGE_BYTES_LO);
@@ -291,38 +422,29 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
   } else if (warp == EPI_WARPS + 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int st_hi = 0, st_lo = 0;
-      uint32_t ph_hi = 0, ph_lo = 0, ph_aempty = 0;
-      bool first = true;
+      int st_hi = 0, st_lo = 0, n = 0;
+      uint32_t ph_hi = 0, ph_lo = 0;
       for (int i = 0;; ++i) {
         const int I = serpentine_rowblock(i, g, G);
         if (I >= NB) break;
         const int nk = min(2 * (I + 1), nst);
-        for (int pass = 0; pass < 2; ++pass) {
-          if (!first) {  // accumulators must have been drained by the epilogue warps
-            mbar_wait(acc_empty, ph_aempty);
-            ph_aempty ^= 1;
+        for (int j = 0; j < 2; ++j, ++n) {
+          const bool lo = pass_is_lo(i, j);
+          if (n > 0) {  // accumulators must have been read out by the epilogue warps (completion #n of acc_empty)
+            mbar_wait(acc_empty, (uint32_t)((n - 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
-          first = false;
           for (int kc = 0; kc < nk; ++kc) {
-            uint32_t base;
-            if (pass == 0) {
+            if (lo) {
               mbar_wait(&full_lo[st_lo], ph_lo);
-              base = smem_u32(smem + (size_t)st_lo * STAGE_BYTES_LO);
-            } else {
-              mbar_wait(&full_hi[st_hi], ph_hi);
-              base = smem_u32(smem + (size_t)st_hi * STAGE_BYTES_HI);
-            }
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (pass == 0)
-              issue_stage<S, 6, 7>(tmem, base, kc != 0 ? 1u : 0u);
-            else
-              issue_stage<HI_DIG, 2, 5>(tmem, base, kc != 0 ? 1u : 0u);
-            if (pass == 0) {
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              issue_stage<S, 6, 7>(tmem, smem_u32(smem + (size_t)st_lo * STAGE_BYTES_LO), kc != 0 ? 1u : 0u);
               umma_commit(&empty_lo[st_lo]);
               if (++st_lo == STAGES_LO) { st_lo = 0; ph_lo ^= 1; }
             } else {
+              mbar_wait(&full_hi[st_hi], ph_hi);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              issue_stage<HI_DIG, 2, 5>(tmem, smem_u32(smem + (size_t)st_hi * STAGE_BYTES_HI), kc != 0 ? 1u : 0u);
               umma_commit(&empty_hi[st_hi]);
               if (++st_hi == STAGES_HI) { st_hi = 0; ph_hi ^= 1; }
             }
@@ -333,22 +455,23 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
     }
   } else {
     // ===================== epilogue warps =====================
-    // warp w reads TMEM lanes [32 (w%4), +32) (rows) and columns [64 (w/4), +64) of every accumulator
+    // warp w reads TMEM lanes [32 (w%4), +32) (rows) and columns [64 (w/4), +64) of every accumulator.
+    // Per pass: TMEM -> fp64 partial sums (cheap), release the accumulators immediately, and only on the second pass of a
+    // row-block do the expensive part (scale, square, cross-lane column sums) while the tensor pipe already runs on.
     const int lq = warp & 3, ch = warp >> 2;
     const uint32_t lane_base = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * 64);
-    double vlo[64];
-    double colsum0 = 0.0, colsum1 = 0.0;  // lane owns columns ch*64 + lane and ch*64 + 32 + lane
-    uint32_t ph_acc = 0;
+    double vacc[64];
+    double colsum[4] = {0.0, 0.0, 0.0, 0.0};  // even lanes: column ch*64 + h*16 + (lane >> 1)
+    int n = 0;
     for (int i = 0;; ++i) {
       const int I = serpentine_rowblock(i, g, G);
       if (I >= NB) break;
       const double rs = rowscale[(int64_t)I * 128 + lq * 32 + lane] * out_scale;
-      for (int pass = 0; pass < 2; ++pass) {
-        mbar_wait(acc_full, ph_acc);
-        ph_acc ^= 1;
+      for (int j = 0; j < 2; ++j, ++n) {
+        const bool lo = pass_is_lo(i, j);
+        mbar_wait(acc_full, (uint32_t)(n & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (pass == 0) {
-          // v_lo = Σ_{r=6,7} 2^(-8r) T_r   (smallest terms first); 16 columns at a time keeps registers low
+        if (lo) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             uint32_t t7[16], t6[16];
@@ -358,7 +481,7 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
             for (int c = 0; c < 16; ++c) {
               double v = (double)(int)t7[c] * 0x1p-56;
               v = fma((double)(int)t6[c], 0x1p-48, v);
-              vlo[h * 16 + c] = v;
+              vacc[h * 16 + c] = (j == 0) ? v : vacc[h * 16 + c] + v;
             }
           }
         } else {
@@ -371,31 +494,62 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
             tmem_ld16(lane_base + 0 * 128 + h * 16, t2);
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-              double v = fma((double)(int)t5[c], 0x1p-40, vlo[h * 16 + c]);
+              double v = (double)(int)t5[c] * 0x1p-40;
               v = fma((double)(int)t4[c], 0x1p-32, v);
               v = fma((double)(int)t3[c], 0x1p-24, v);
               v = fma((double)(int)t2[c], 0x1p-16, v);
-              v *= rs;          // A[n, t]
-              double sq = v * v;
-              // column sum over the 32 rows of this warp: butterfly
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-              if (lane == (h & 1) * 16 + c) {
-                if (h < 2) colsum0 += sq; else colsum1 += sq;
-              }
+              vacc[h * 16 + c] = (j == 0) ? v : vacc[h * 16 + c] + v;
             }
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty);
+        if (lane == 0) mbar_arrive(acc_empty);  // accumulators are free again: the next pass starts now
+        if (j == 1) {
+          // A[n,t] = rowscale * 2^f * v; column sums of A^2 over the warp's 32 rows by recursive halving
+          // (16 + 8 + 4 + 2 + 2 shuffles per 16 columns instead of 160)
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            double a[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const double v = vacc[h * 16 + c] * rs;
+              a[c] = v * v;
+            }
+            double b8[8], b4[4], b2[2];
+            bool up = (lane & 16) != 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const double mine = up ? a[8 + c] : a[c], theirs = up ? a[c] : a[8 + c];
+              b8[c] = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
+            }
+            up = (lane & 8) != 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const double mine = up ? b8[4 + c] : b8[c], theirs = up ? b8[c] : b8[4 + c];
+              b4[c] = mine + __shfl_xor_sync(0xffffffffu, theirs, 8);
+            }
+            up = (lane & 4) != 0;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const double mine = up ? b4[2 + c] : b4[c], theirs = up ? b4[c] : b4[2 + c];
+              b2[c] = mine + __shfl_xor_sync(0xffffffffu, theirs, 4);
+            }
+            up = (lane & 2) != 0;
+            double e = (up ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, up ? b2[0] : b2[1], 2);
+            e += __shfl_xor_sync(0xffffffffu, e, 1);
+            colsum[h] += e;  // lane holds column h*16 + (lane >> 1) (both lanes of a pair hold the same sum)
+          }
+        }
       }
     }
     // combine the four row-quarters (warps lq = 0..3 of the same column half) through shared memory
     // (every MMA has retired, so the stage buffers are free to hold the 4 KB of partial column sums)
     double (*redbuf)[64] = reinterpret_cast<double (*)[64]>(smem);
-    redbuf[warp][lane] = colsum0;
-    redbuf[warp][32 + lane] = colsum1;
+    if ((lane & 1) == 0) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) redbuf[warp][h * 16 + (lane >> 1)] = colsum[h];
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32));
     if (warp < 2) {  // warp 0 -> columns 0..63 (ch = 0: warps 0..3), warp 1 -> columns 64..127 (warps 4..7)
       const int c0 = lane, c1 = 32 + lane, wb = warp * 4;

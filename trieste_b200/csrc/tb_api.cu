@@ -133,6 +133,7 @@ int tb_gp_create(tb_gp** out, int device, int dtype) {
   gp->device = device;
   gp->dtype = dtype;
   if (const char* e = std::getenv("TB_ENGINE")) gp->engine = (std::string(e) == "fp64") ? 0 : 1;
+  if (const char* e = std::getenv("TB_KSTAR_MMA")) gp->kstar_mma = std::atoi(e) != 0;
   if (const char* e = std::getenv("TB_KSTAR_SMEM")) gp->kstar_smem = (size_t)std::atol(e);
   if (const char* e = std::getenv("TB_KSTAR_THREADS")) {
     int t = std::atoi(e);
@@ -159,7 +160,7 @@ int tb_gp_destroy(tb_gp* gp) {
   cudaSetDevice(gp->device);
   cudaStreamSynchronize(gp->stream);
   for (tb::DevBuf* b : {&gp->dX, &gp->dy, &gp->dXs, &gp->dInvLs, &gp->dAlpha, &gp->dL, &gp->dLinv,
-                        &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->sKs2, &gp->sMean2, &gp->sPartial2, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
+                        &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->dXn2, &gp->sKs2, &gp->sMean2, &gp->sPartial2, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
                         &gp->sVals, &gp->sVar, &gp->sXc, &gp->sBlkBest, &gp->sBlkIdx, &gp->sRun,
                         &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc})
     b->release();
@@ -488,6 +489,9 @@ static int ensure_ozaki(tb_gp* gp) {
   TB_TRY(gp->dRowScale.reserve(sizeof(double) * rows));
   oz::linv_rowscale_kernel<<<(unsigned)rows, 256, 0, st>>>(gp->dLinv.as<double>(), gp->N, rows, gp->dRowScale.as<double>());
   TB_LAUNCHED();
+  TB_TRY(gp->dXn2.reserve(sizeof(double) * rows));
+  oz::rownorm2_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(gp->dXs.as<double>(), gp->DP, rows, gp->dXn2.as<double>());
+  TB_LAUNCHED();
   const int64_t nstages = oz::a_stage_offset(gp->NB);
   TB_TRY(gp->dAS.reserve((size_t)nstages * oz::S * oz::TILE));
   TB_CUDA(cudaMemsetAsync(gp->dAS.p, 0, (size_t)nstages * oz::S * oz::TILE, st));
@@ -511,6 +515,35 @@ static int launch_kstar_digits(tb_gp* gp, const double* Xc_dev, int64_t mc, int 
   const double var = gp->variance, mc0 = gp->mean_const;
   const double inv_b = std::ldexp(1.0, 48 - gp->oz_bscale_exp);
   cudaStream_t st = gp->stream;
+  if (gp->kstar_mma) {
+    const int dp4 = (D + 3) / 4;
+    const double* xn2 = gp->dXn2.as<double>();
+#define TB_KM(KIND, Q)                                                                                                      \
+  oz::kstar_digits_mma_kernel<KIND, Q><<<tiles * (512 / gp->kstar_threads), gp->kstar_threads, gp->kstar_smem, st>>>(        \
+      Xs, gp->DP, xn2, al, Xc_dev, il, N, nst, D, mc, var, inv_b, mc0, BS, mean)
+#define TB_KM_Q(KIND)              \
+  switch (dp4) {                   \
+    case 1: TB_KM(KIND, 1); break; \
+    case 2: TB_KM(KIND, 2); break; \
+    case 3: TB_KM(KIND, 3); break; \
+    case 4: TB_KM(KIND, 4); break; \
+    case 5: TB_KM(KIND, 5); break; \
+    case 6: TB_KM(KIND, 6); break; \
+    case 7: TB_KM(KIND, 7); break; \
+    default: TB_KM(KIND, 8); break; \
+  }
+    switch (gp->kernel) {
+      case TB_RBF: TB_KM_Q(TB_RBF); break;
+      case TB_MATERN12: TB_KM_Q(TB_MATERN12); break;
+      case TB_MATERN32: TB_KM_Q(TB_MATERN32); break;
+      default: TB_KM_Q(TB_MATERN52); break;
+    }
+#undef TB_KM_Q
+#undef TB_KM
+    TB_LAUNCHED();
+    TB_CUDA(cudaGetLastError());
+    return 0;
+  }
 #define TB_KD(KIND, DPV) \
   oz::kstar_digits_kernel<KIND, DPV><<<tiles * (512 / gp->kstar_threads), gp->kstar_threads, gp->kstar_smem, st>>>(Xs, al, Xc_dev, il, N, nst, D, mc, var, inv_b, mc0, BS, mean)
 #define TB_KD_DP(KIND)                                   \
@@ -579,7 +612,14 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
   max_tiles = std::min<int64_t>(max_tiles, 148 * 8);
   const int64_t chunk_cap = std::min<int64_t>(max_tiles * BT, ((rq.M + BT - 1) / BT) * BT);
   const int64_t tiles_cap = chunk_cap / BT;
-  const int G = std::max(1, (gp->NB + 1) / 2);
+  // row-block groups per candidate tile: ~4 row-blocks per CTA amortise the CTA prologue while the co-resident CTAs still
+  // share few enough candidate tiles for the K* digits to live in L2; small batches get more groups to fill the GPU
+  int G = std::max(1, (gp->NB + 3) / 4);
+  {
+    const int64_t tiles_all = std::min<int64_t>(tiles_cap, (rq.M + BT - 1) / BT);
+    if (tiles_all * G < 2 * 148) G = (int)std::min<int64_t>(gp->NB, (2 * 148 + tiles_all - 1) / tiles_all);
+  }
+  if (const char* e = std::getenv("TB_OZ_G")) G = std::max(1, std::min(std::atoi(e), gp->NB));  // experiment knob
   tb::DevBuf* ks[2] = {&gp->sKs, &gp->sKs2};
   tb::DevBuf* mean[2] = {&gp->sMean, &gp->sMean2};
   tb::DevBuf* part[2] = {&gp->sPartial, &gp->sPartial2};
