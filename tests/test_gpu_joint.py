@@ -8,10 +8,11 @@ from tests.util import candidates, model_pair
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("engine", ["int8", "fp64"])
 @pytest.mark.parametrize("N,D,q", [(20, 2, 1), (20, 2, 3), (300, 6, 8), (300, 6, 5), (128, 6, 16), (300, 10, 11)])
-def test_predict_joint_matches_oracle(N, D, q):
+def test_predict_joint_matches_oracle(N, D, q, engine):
     obj = o.branin if D == 2 else (o.hartmann_6 if D == 6 else o.ackley)
-    om, nm = model_pair(obj, N, D)
+    om, nm = model_pair(obj, N, D, engine=engine)
     X = candidates(37 * q, D).reshape(37, q, D)
     mean, cov = nm.predict_joint(X)
     omean, ocov = o.predict_joint(om, X)
@@ -62,13 +63,14 @@ def test_reparam_sampler_moments():
     np.testing.assert_allclose(np.cov(s.T), cov[0, 0] + 1e-6 * np.eye(3), atol=0.04 * om.variance)
 
 
+@pytest.mark.parametrize("engine", ["int8", "fp64"])
 @pytest.mark.parametrize("N,D,q,S", [(300, 6, 8, 512), (300, 6, 3, 100), (1024, 10, 8, 512)])
-def test_batch_monte_carlo_expected_improvement(N, D, q, S):
+def test_batch_monte_carlo_expected_improvement(N, D, q, S, engine):
     from trieste_b200 import Dataset
     from trieste_b200.acquisition import BatchMonteCarloExpectedImprovement
 
     obj = o.hartmann_6 if D == 6 else o.ackley
-    om, nm = model_pair(obj, N, D)
+    om, nm = model_pair(obj, N, D, engine=engine)
     builder = BatchMonteCarloExpectedImprovement(S, jitter=1e-6)
     fn = builder.prepare_acquisition_function(nm, Dataset(om.X, om.y))
     eps = np.random.default_rng(3).standard_normal((q, S))

@@ -345,9 +345,13 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t stage_base, 
 // ------------------------------------------------------------------------------------------------
 // the GEMM: grid = (candidate tiles, G); partial[g][t] = Σ_{rows n of group g} A[n,t]^2
 // ------------------------------------------------------------------------------------------------
+// OZ_SUMSQ: partial column sums of A^2 (variance path).  OZ_STORE: A itself, fp64, candidate-major [t][lda] (joint path)
+enum { OZ_SUMSQ = 0, OZ_STORE = 1 };
+template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, const double* __restrict__ rowscale,
-                  int NB, int nst, int G, int64_t McPad, double out_scale, double* __restrict__ partial) {
+                  int NB, int nst, int G, int64_t McPad, double out_scale, double* __restrict__ partial,
+                  double* __restrict__ Aplain, int64_t lda) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES_LO * STAGE_BYTES_LO);
   uint64_t* full_hi = bars;            // [3]
@@ -505,7 +509,14 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty);  // accumulators are free again: the next pass starts now
-        if (j == 1) {
+        if (j == 1 && EPI == OZ_STORE) {
+          // A[n,t] = rowscale * 2^f * v, stored candidate-major: the 32 lanes of a warp write 32 consecutive rows (256 B)
+          const int64_t nrow = (int64_t)I * 128 + lq * 32 + lane;
+          double* dstA = Aplain + ((int64_t)tile * 128 + ch * 64) * lda + nrow;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) dstA[(int64_t)c * lda] = vacc[c] * rs;
+        }
+        if (j == 1 && EPI == OZ_SUMSQ) {
           // A[n,t] = rowscale * 2^f * v; column sums of A^2 over the warp's 32 rows by recursive halving
           // (16 + 8 + 4 + 2 + 2 shuffles per 16 columns instead of 160)
 #pragma unroll
@@ -543,6 +554,7 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
         }
       }
     }
+    if (EPI == OZ_SUMSQ) {
     // combine the four row-quarters (warps lq = 0..3 of the same column half) through shared memory
     // (every MMA has retired, so the stage buffers are free to hold the 4 KB of partial column sums)
     double (*redbuf)[64] = reinterpret_cast<double (*)[64]>(smem);
@@ -558,6 +570,7 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
       double* out = partial + (int64_t)g * McPad + (int64_t)tile * 128 + warp * 64;
       out[c0] = a0;
       out[c1] = a1;
+    }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -400,7 +400,8 @@ static int pick_groups(const tb_gp* gp, int tiles) {
 }
 
 int kernels_init() {
-  TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
+  TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
+  TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
@@ -669,9 +670,9 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
       TB_CUDA(cudaEventCreate(&e1));
       TB_CUDA(cudaEventRecord(e0, sa));
     }
-    oz::trigemm_i8_kernel<<<dim3(G, tiles), oz::THREADS, oz::SMEM_BYTES, sa>>>(
+    oz::trigemm_i8_kernel<oz::OZ_SUMSQ><<<dim3(G, tiles), oz::THREADS, oz::SMEM_BYTES, sa>>>(
         gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
-        part[slot]->as<double>());
+        part[slot]->as<double>(), nullptr, 0);
     TB_LAUNCHED();
     if (gp->profile) {
       TB_CUDA(cudaEventRecord(e1, sa));
@@ -804,9 +805,9 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
       TB_CUDA(cudaEventRecord(e0, st));
     }
     if (use_oz)
-      oz::trigemm_i8_kernel<<<dim3(G, tiles), oz::THREADS, oz::SMEM_BYTES, st>>>(
+      oz::trigemm_i8_kernel<oz::OZ_SUMSQ><<<dim3(G, tiles), oz::THREADS, oz::SMEM_BYTES, st>>>(
           gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad,
-          gp->oz_out_scale, gp->sPartial.as<double>());
+          gp->oz_out_scale, gp->sPartial.as<double>(), nullptr, 0);
     else if (rq.out_grad)
       trigemm_kernel<false, EPI_SUMSQ_PACKED><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
           gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, gp->sPartial.as<double>(),
@@ -1011,7 +1012,12 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
   nbc_cap = std::min<int64_t>(nbc_cap, rq.B);
   const int64_t cand_cap = nbc_cap * q;
   const int64_t tiles_cap = (cand_cap + BT - 1) / BT;
-  TB_TRY(gp->sKs.reserve((size_t)tiles_cap * gp->nkc * PANEL * sizeof(double)));
+  const bool oz_joint = gp->engine == 1 && gp->N <= 16384;
+  if (oz_joint) {
+    TB_TRY(ensure_ozaki(gp));
+    TB_CUDA(cudaStreamSynchronize(st));
+  }
+  TB_TRY(gp->sKs.reserve(std::max((size_t)tiles_cap * gp->nkc * PANEL * sizeof(double), (size_t)tiles_cap * gp->nst * oz::S * oz::TILE)));
   TB_TRY(gp->sV.reserve((size_t)tiles_cap * BT * lda * sizeof(double)));  // A plain
   TB_TRY(gp->sMean.reserve(sizeof(double) * tiles_cap * BT));
   const bool xc_dev = is_device_ptr(rq.Xc);
@@ -1054,10 +1060,19 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
       TB_CUDA(cudaMemcpyAsync(gp->sXc.p, rq.Xc + b0 * q * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, st));
       xc_chunk = gp->sXc.as<double>();
     }
-    TB_TRY(launch_kstar(gp, xc_chunk, mc, tiles, gp->sKs.as<double>(), gp->sMean.as<double>()));
-    trigemm_kernel<false, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
-        gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, nullptr, nullptr,
-        gp->sV.as<double>(), lda);
+    if (oz_joint) {
+      // A = Linv K* on the int8 tensor cores (fp64-accurate digit GEMM), stored for the per-batch Gram kernel
+      TB_TRY(launch_kstar_digits(gp, xc_chunk, mc, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
+      const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
+      oz::trigemm_i8_kernel<oz::OZ_STORE><<<dim3(Goz, tiles), oz::THREADS, oz::SMEM_BYTES, st>>>(
+          gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, Goz, McPad,
+          gp->oz_out_scale, nullptr, gp->sV.as<double>(), lda);
+    } else {
+      TB_TRY(launch_kstar(gp, xc_chunk, mc, tiles, gp->sKs.as<double>(), gp->sMean.as<double>()));
+      trigemm_kernel<false, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
+          gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, nullptr, nullptr,
+          gp->sV.as<double>(), lda);
+    }
     TB_LAUNCHED();
     TB_CUDA(cudaGetLastError());
     double* dptr[4];
