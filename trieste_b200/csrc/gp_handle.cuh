@@ -82,6 +82,7 @@ struct tb_gp {
   // int8 (Ozaki) engine: digit tiles of Linv, per-row scales, K* scale
   int engine = 1;  // 0 = fp64 DMMA, 1 = int8 tensor cores (default; same stated tolerances, ~3x faster)
   tb::DevBuf dAS, dRowScale, dXn2;
+  int oz_epi_warps = 8;    // epilogue warps of the int8 GEMM (4 leaves register room for co-resident K* CTAs)
   bool kstar_mma = false;  // distances of the K* digit kernel on the DMMA pipe (expansion form)
   tb::DevBuf sKs2, sMean2, sPartial2;  // second scratch slot of the pipelined driver
   // dynamic smem requested by the K* digit CTAs only to bound how many of them share an SM with a GEMM CTA (2 by default)

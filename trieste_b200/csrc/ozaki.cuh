@@ -29,8 +29,6 @@ constexpr int STAGES_HI = 3, STAGES_LO = 2;
 constexpr int STAGE_BYTES_HI = 2 * HI_DIG * TILE;   // 64 KB
 constexpr int STAGE_BYTES_LO = 2 * S * TILE;        // 112 KB
 constexpr size_t SMEM_BYTES = (size_t)STAGES_LO * STAGE_BYTES_LO + 256;   // 224 KB + barriers
-constexpr int EPI_WARPS = 8;
-constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int DIGIT_BITS = 48;               // v = rint(x / 2^e * 2^48) = Σ d_p 256^(6-p)
 
 __host__ __device__ inline int64_t a_stage_offset(int I) {  // stages before row-block I: Σ 2(i+1)
@@ -347,8 +345,9 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t stage_base, 
 // ------------------------------------------------------------------------------------------------
 // OZ_SUMSQ: partial column sums of A^2 (variance path).  OZ_STORE: A itself, fp64, candidate-major [t][lda] (joint path)
 enum { OZ_SUMSQ = 0, OZ_STORE = 1 };
-template <int EPI>
-__global__ void __launch_bounds__(THREADS, 1)
+// EW = number of epilogue warps (8: 64 columns each; 4: 128 columns each, which leaves registers for co-resident K* CTAs)
+template <int EPI, int EW>
+__global__ void __launch_bounds__((EW + 2) * 32, EW == 4 ? 2 : 1)  // EW == 4: cap registers at 168 so that K* CTAs fit beside it
 trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, const double* __restrict__ rowscale,
                   int NB, int nst, int G, int64_t McPad, double out_scale, double* __restrict__ partial,
                   double* __restrict__ Aplain, int64_t lda) {
@@ -369,10 +368,10 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
     for (int s = 0; s < 3; ++s) { mbar_init(&full_hi[s], 1); mbar_init(&empty_hi[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&full_lo[s], 1); mbar_init(&empty_lo[s], 1); }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, EPI_WARPS);
+    mbar_init(acc_empty, EW);
     fence_barrier_init();
   }
-  if (warp == EPI_WARPS) {  // TMEM allocation: all 512 columns (one CTA per SM)
+  if (warp == EW) {  // TMEM allocation: all 512 columns (one CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -382,7 +381,7 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
   const uint32_t tmem = *tmem_slot;
   const int8_t* bTile = BS + (int64_t)tile * nst * (S * TILE);
 
-  if (warp == EPI_WARPS) {
+  if (warp == EW) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int st_hi = 0, st_lo = 0, n = 0, seen = 0;  // seen = completions of acc_full already observed
@@ -423,7 +422,7 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
         }
       }
     }
-  } else if (warp == EPI_WARPS + 1) {
+  } else if (warp == EW + 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       int st_hi = 0, st_lo = 0, n = 0;
@@ -463,9 +462,12 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
     // Per pass: TMEM -> fp64 partial sums (cheap), release the accumulators immediately, and only on the second pass of a
     // row-block do the expensive part (scale, square, cross-lane column sums) while the tensor pipe already runs on.
     const int lq = warp & 3, ch = warp >> 2;
-    const uint32_t lane_base = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * 64);
-    double vacc[64];
-    double colsum[4] = {0.0, 0.0, 0.0, 0.0};  // even lanes: column ch*64 + h*16 + (lane >> 1)
+    constexpr int CW = 512 / EW;  // accumulator columns per epilogue warp
+    const uint32_t lane_base = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * CW);
+    double vacc[CW];
+    double colsum[CW / 16];  // even lanes: column ch*CW + h*16 + (lane >> 1)
+#pragma unroll
+    for (int h = 0; h < CW / 16; ++h) colsum[h] = 0.0;
     int n = 0;
     for (int i = 0;; ++i) {
       const int I = serpentine_rowblock(i, g, G);
@@ -477,7 +479,7 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lo) {
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
+          for (int h = 0; h < CW / 16; ++h) {
             uint32_t t7[16], t6[16];
             tmem_ld16(lane_base + 1 * 128 + h * 16, t7);
             tmem_ld16(lane_base + 0 * 128 + h * 16, t6);
@@ -490,7 +492,7 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
           }
         } else {
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
+          for (int h = 0; h < CW / 16; ++h) {
             uint32_t t5[16], t4[16], t3[16], t2[16];
             tmem_ld16(lane_base + 3 * 128 + h * 16, t5);
             tmem_ld16(lane_base + 2 * 128 + h * 16, t4);
@@ -512,15 +514,15 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
         if (j == 1 && EPI == OZ_STORE) {
           // A[n,t] = rowscale * 2^f * v, stored candidate-major: the 32 lanes of a warp write 32 consecutive rows (256 B)
           const int64_t nrow = (int64_t)I * 128 + lq * 32 + lane;
-          double* dstA = Aplain + ((int64_t)tile * 128 + ch * 64) * lda + nrow;
+          double* dstA = Aplain + ((int64_t)tile * 128 + ch * CW) * lda + nrow;
 #pragma unroll
-          for (int c = 0; c < 64; ++c) dstA[(int64_t)c * lda] = vacc[c] * rs;
+          for (int c = 0; c < CW; ++c) dstA[(int64_t)c * lda] = vacc[c] * rs;
         }
         if (j == 1 && EPI == OZ_SUMSQ) {
           // A[n,t] = rowscale * 2^f * v; column sums of A^2 over the warp's 32 rows by recursive halving
           // (16 + 8 + 4 + 2 + 2 shuffles per 16 columns instead of 160)
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
+          for (int h = 0; h < CW / 16; ++h) {
             double a[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
@@ -557,25 +559,22 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
     if (EPI == OZ_SUMSQ) {
     // combine the four row-quarters (warps lq = 0..3 of the same column half) through shared memory
     // (every MMA has retired, so the stage buffers are free to hold the 4 KB of partial column sums)
-    double (*redbuf)[64] = reinterpret_cast<double (*)[64]>(smem);
+    double (*redbuf)[CW] = reinterpret_cast<double (*)[CW]>(smem);
     if ((lane & 1) == 0) {
 #pragma unroll
-      for (int h = 0; h < 4; ++h) redbuf[warp][h * 16 + (lane >> 1)] = colsum[h];
+      for (int h = 0; h < CW / 16; ++h) redbuf[warp][h * 16 + (lane >> 1)] = colsum[h];
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32));
-    if (warp < 2) {  // warp 0 -> columns 0..63 (ch = 0: warps 0..3), warp 1 -> columns 64..127 (warps 4..7)
-      const int c0 = lane, c1 = 32 + lane, wb = warp * 4;
-      double a0 = redbuf[wb][c0] + redbuf[wb + 1][c0] + redbuf[wb + 2][c0] + redbuf[wb + 3][c0];
-      double a1 = redbuf[wb][c1] + redbuf[wb + 1][c1] + redbuf[wb + 2][c1] + redbuf[wb + 3][c1];
-      double* out = partial + (int64_t)g * McPad + (int64_t)tile * 128 + warp * 64;
-      out[c0] = a0;
-      out[c1] = a1;
+    asm volatile("bar.sync 1, %0;" ::"n"(EW * 32));
+    for (int col = threadIdx.x; col < 128; col += EW * 32) {  // warps of one column group are ch*4 .. ch*4+3
+      const int cg = col / CW, cc = col % CW, wb = cg * 4;
+      partial[(int64_t)g * McPad + (int64_t)tile * 128 + col] =
+          redbuf[wb][cc] + redbuf[wb + 1][cc] + redbuf[wb + 2][cc] + redbuf[wb + 3][cc];
     }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  if (warp == EW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 }  // namespace oz

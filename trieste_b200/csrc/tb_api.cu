@@ -133,6 +133,7 @@ int tb_gp_create(tb_gp** out, int device, int dtype) {
   gp->device = device;
   gp->dtype = dtype;
   if (const char* e = std::getenv("TB_ENGINE")) gp->engine = (std::string(e) == "fp64") ? 0 : 1;
+  if (const char* e = std::getenv("TB_OZ_EW")) gp->oz_epi_warps = std::atoi(e) == 4 ? 4 : 8;
   if (const char* e = std::getenv("TB_KSTAR_MMA")) gp->kstar_mma = std::atoi(e) != 0;
   if (const char* e = std::getenv("TB_KSTAR_SMEM")) gp->kstar_smem = (size_t)std::atol(e);
   if (const char* e = std::getenv("TB_KSTAR_THREADS")) {
@@ -400,8 +401,9 @@ static int pick_groups(const tb_gp* gp, int tiles) {
 }
 
 int kernels_init() {
-  TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
-  TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
+  TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
+  TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
+  TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_STORE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
@@ -670,9 +672,14 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
       TB_CUDA(cudaEventCreate(&e1));
       TB_CUDA(cudaEventRecord(e0, sa));
     }
-    oz::trigemm_i8_kernel<oz::OZ_SUMSQ><<<dim3(G, tiles), oz::THREADS, oz::SMEM_BYTES, sa>>>(
-        gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
-        part[slot]->as<double>(), nullptr, 0);
+    if (gp->oz_epi_warps == 4)
+      oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 4><<<dim3(G, tiles), 6 * 32, oz::SMEM_BYTES, sa>>>(
+          gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
+          part[slot]->as<double>(), nullptr, 0);
+    else
+      oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8><<<dim3(G, tiles), 10 * 32, oz::SMEM_BYTES, sa>>>(
+          gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
+          part[slot]->as<double>(), nullptr, 0);
     TB_LAUNCHED();
     if (gp->profile) {
       TB_CUDA(cudaEventRecord(e1, sa));
@@ -805,7 +812,7 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
       TB_CUDA(cudaEventRecord(e0, st));
     }
     if (use_oz)
-      oz::trigemm_i8_kernel<oz::OZ_SUMSQ><<<dim3(G, tiles), oz::THREADS, oz::SMEM_BYTES, st>>>(
+      oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8><<<dim3(G, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
           gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad,
           gp->oz_out_scale, gp->sPartial.as<double>(), nullptr, 0);
     else if (rq.out_grad)
@@ -1064,7 +1071,7 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
       // A = Linv K* on the int8 tensor cores (fp64-accurate digit GEMM), stored for the per-batch Gram kernel
       TB_TRY(launch_kstar_digits(gp, xc_chunk, mc, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
       const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
-      oz::trigemm_i8_kernel<oz::OZ_STORE><<<dim3(Goz, tiles), oz::THREADS, oz::SMEM_BYTES, st>>>(
+      oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Goz, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
           gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, Goz, McPad,
           gp->oz_out_scale, nullptr, gp->sV.as<double>(), lda);
     } else {
