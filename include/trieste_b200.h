@@ -40,7 +40,9 @@ enum tb_acq {
   TB_ACQ_EI = 0,      /* expected_improvement.__call__, acquisition/function/function.py:215-223 */
   TB_ACQ_LOG_EI = 1,  /* log of the above; ABSENT in the reference */
   TB_ACQ_NEG_LCB = 2, /* NegativeLowerConfidenceBound, function.py:358-359 (−lower_confidence_bound :415-416) */
-  TB_ACQ_LCB = 3      /* lower_confidence_bound, function.py:389-418 */
+  TB_ACQ_LCB = 3,     /* lower_confidence_bound, function.py:389-418 */
+  TB_ACQ_PBT = 4      /* probability_below_threshold.__call__, function.py:501-509 (ProbabilityOfImprovement :47-93,
+                         ProbabilityOfFeasibility :421-478): Normal(mean, sqrt(var)).cdf(param) */
 };
 
 /* ---- errors / build info ------------------------------------------------------------------ */
@@ -119,6 +121,13 @@ int tb_rff_set_theta(tb_rff* r, const double* theta, int nb);
  * (either may be NULL). */
 int tb_rff_eval(tb_rff* r, const void* Xc, int64_t M, void* out, double* min_value,
                 int64_t* min_index);
+/* DecoupledTrajectorySampler (models/gpflow/sampler.py:594-738) / ResampleableDecoupledFeatureFunctions (:809-855):
+ * adds the canonical features  sum_j v[b][j] k(x, X_j)  to trajectory b.  X [N,D] raw training inputs (host),
+ * v [nb,N] column layout [trajectory][training point] (host or device).  N = 0 switches the term off. */
+int tb_rff_set_canonical(tb_rff* r, int kernel, const double* X, int64_t N, const double* v, int nb);
+/* (K(X,X) + noise I)^-1 B through the cached Cholesky factor: B, out [nrhs][N] (each right-hand side contiguous);
+ * the v-weights of a decoupled trajectory (sampler.py:716, gpflux compute_A_inv_b).  fp64, host or device. */
+int tb_gp_kinv_apply(tb_gp* gp, const double* B, int nrhs, double* out);
 
 /* ---- instrumentation (bench / tests) ---------------------------------------------------------
  * kernels launched by this library in this process since the last reset; device time (ms) of the

@@ -442,3 +442,34 @@ def synthetic_model(objective, N, D, kind="matern52", dtype=np.float64, seed=0, 
     ls = np.full(D, 0.2 * math.sqrt(D))
     nz = var / 100.0 if noise is None else noise
     return build_model(kind, X.astype(dtype), y.astype(dtype), var, ls, nz, float(np.mean(y)))
+
+
+# --------------------------------------------------------------------------------------------
+# Decoupled (pathwise) trajectory sampler — trieste/models/gpflow/sampler.py:594-738, 809-855
+# (exact-GP branch :668-677): f(x) = phi(x) w + sum_j v_j k(x, x_j) + m(x),
+#   u = (y - m) + sqrt(noise) eps,   v = (K + noise I)^-1 (u - phi(X) w)
+# --------------------------------------------------------------------------------------------
+def decoupled_weights(m: GPRModel, W, b, prior_w, eps):
+    """prior_w [B, F] ~ N(0, I), eps [B, N] ~ N(0, I)  ->  canonical weights v [B, N]."""
+    phi_Z = rff_features(m.X, W, b, m.variance, m.lengthscales)  # [N, F]
+    u = (m.y - m.mean_const)[:, 0][None, :] + math.sqrt(m.noise) * eps  # [B, N]
+    diff = u - prior_w @ phi_Z.T  # [B, N]
+    return sla.cho_solve((m.L, True), diff.T, check_finite=False).T
+
+
+def decoupled_trajectory(m: GPRModel, Xq, W, b, prior_w, v, chunk: int = 32768):
+    """Xq [M, B, D] -> [M, B, 1]."""
+    M, B, D = Xq.shape
+    out = np.empty((M, B, 1))
+    for s in range(0, M, chunk):
+        x = Xq[s : s + chunk]
+        for bb in range(B):
+            phi = rff_features(x[:, bb], W, b, m.variance, m.lengthscales)  # [m, F]
+            kx = kernel_matrix(m.kind, x[:, bb], m.X, m.variance, m.lengthscales)  # [m, N]
+            out[s : s + chunk, bb, 0] = phi @ prior_w[bb] + kx @ v[bb] + m.mean_const
+    return out
+
+
+def probability_below_threshold(mean, var, threshold):
+    """trieste/acquisition/function/function.py:507-509: Normal(mean, sqrt(var)).cdf(threshold)."""
+    return ndtr((threshold - mean) / np.sqrt(var))

@@ -163,3 +163,26 @@ def test_device_resident_torch_io():
     omean, ovar = o.predict(om, Xq)
     np.testing.assert_allclose(mean.cpu().numpy(), omean, rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(var.cpu().numpy(), ovar, rtol=0, atol=1e-9 * om.variance)
+
+
+def test_probability_of_improvement_and_feasibility():
+    from trieste_b200 import Dataset
+    from trieste_b200.acquisition import ProbabilityOfFeasibility, ProbabilityOfImprovement
+
+    om, nm = model_pair(o.hartmann_6, 200, 6)
+    Xq = candidates(3000, 6)
+    omean, ovar = o.predict(om, Xq)
+    ds = Dataset(om.X, om.y)
+    b = ProbabilityOfImprovement()
+    fn = b.prepare_acquisition_function(nm, ds)
+    np.testing.assert_allclose(fn(Xq[:, None, :]), o.probability_below_threshold(omean, ovar, o.ei_eta(om)), rtol=1e-7, atol=1e-15)
+    assert b.update_acquisition_function(fn, nm, ds) is fn
+    pof = ProbabilityOfFeasibility(-0.5).prepare_acquisition_function(nm)
+    ref = o.probability_below_threshold(omean, ovar, -0.5)
+    val, grad = pof.value_and_gradient(Xq[:100, None, :])
+    np.testing.assert_allclose(val, ref[:100], rtol=1e-7, atol=1e-15)
+    h = 1e-6
+    e = np.zeros(6)
+    e[2] = h
+    fd = (pof((Xq[:100] + e)[:, None, :]) - pof((Xq[:100] - e)[:, None, :])) / (2 * h)
+    np.testing.assert_allclose(grad[:, 0, 2], fd[:, 0], rtol=2e-4, atol=1e-6 * np.abs(grad).max())

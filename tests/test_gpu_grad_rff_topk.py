@@ -193,3 +193,48 @@ def test_efficient_global_optimization_rule_branin():
     model.update(ds2)
     q2 = rule.acquire_single(space, model, ds2)
     assert rule.acquisition_function is fn and q2.shape == (1, 2)
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern52"])
+def test_decoupled_trajectory_matches_oracle(kind):
+    # DecoupledTrajectorySampler (sampler.py:594-738) with injected W, b, prior weights and noise draws
+    from trieste_b200.sampler import DecoupledTrajectorySampler
+
+    om, nm = model_pair(o.hartmann_6, 150, 6, kind=kind)
+    F, B = 256, 3
+    s = DecoupledTrajectorySampler(nm, F, seed=0)
+    W, b = o.rff_draw(kind, F, 6, np.random.default_rng(4))
+    s._feature_functions.set_weights(W, b)
+    rng = np.random.default_rng(7)
+    pw, eps = rng.standard_normal((B, F)), rng.standard_normal((B, 150))
+    v = s.canonical_weights(pw, eps)
+    ov = o.decoupled_weights(om, W, b, pw, eps)
+    np.testing.assert_allclose(v, ov, rtol=1e-7, atol=1e-9 * np.abs(ov).max())
+    traj = s.get_trajectory()
+    traj._weight_sampler = lambda nb: (pw, v)
+    Xq = candidates(3000, 6)
+    X3 = np.stack([Xq, Xq[::-1], Xq], axis=1)
+    out = traj(X3)
+    ref = o.decoupled_trajectory(om, X3, W, b, pw, ov)
+    assert out.shape == (3000, 3, 1)
+    np.testing.assert_allclose(out, ref, rtol=1e-8, atol=1e-8 * np.sqrt(om.variance))
+    mv, mi = traj.argmin_over(Xq)
+    full = o.decoupled_trajectory(om, np.repeat(Xq[:, None, :], 3, 1), W, b, pw, ov)
+    np.testing.assert_array_equal(mi, np.argmin(full[:, :, 0], axis=0))
+    # default trajectory sampler of the model is the decoupled one (models.py:342-345)
+    assert isinstance(nm.trajectory_sampler(), DecoupledTrajectorySampler)
+
+
+def test_decoupled_trajectory_moments():
+    # trajectory moments vs predict (tests/unit/models/gpflow/test_models.py:638-681 restated, use_decoupled_sampler=True)
+    om, nm = model_pair(o.hartmann_6, 60, 6, kind="rbf")
+    from trieste_b200.sampler import DecoupledTrajectorySampler
+
+    s = DecoupledTrajectorySampler(nm, 2000, seed=3)
+    traj = s.get_trajectory()
+    Xq = candidates(8, 6)
+    S = 300
+    f = traj(np.repeat(Xq[:, None, :], S, 1))[:, :, 0]
+    mean, var = nm.predict(Xq)
+    np.testing.assert_allclose(f.mean(1), mean[:, 0], atol=0.2 * np.sqrt(om.variance))
+    np.testing.assert_allclose(f.var(1), var[:, 0], rtol=0.5, atol=0.02 * om.variance)

@@ -149,3 +149,19 @@ def test_objectives_known_minima():
     np.testing.assert_allclose(o.hartmann_6(np.array([[0.20169, 0.150011, 0.476874, 0.275332, 0.311652, 0.6573]])), [[-3.32237]], atol=1e-5)
     np.testing.assert_allclose(o.ackley(np.full((1, 5), 0.5)), [[0.0]], atol=1e-12)
     np.testing.assert_allclose(o.branin(np.array([[0.5427728, 0.1516667]])), [[0.397887]], atol=1e-5)
+
+
+def test_decoupled_sampler_moments():
+    # DecoupledTrajectorySampler restatement: trajectory moments reproduce the exact posterior
+    # (tests/unit/models/gpflow/test_models.py:638-681 with use_decoupled_sampler=True)
+    om = o.synthetic_model(o.hartmann_6, 60, 6, kind="rbf")
+    rng = np.random.default_rng(0)
+    W, b = o.rff_draw("rbf", 3000, 6, rng)
+    S = 400
+    pw, eps = rng.standard_normal((S, 3000)), rng.standard_normal((S, 60))
+    v = o.decoupled_weights(om, W, b, pw, eps)
+    Xq = rng.uniform(size=(10, 6))
+    f = o.decoupled_trajectory(om, np.repeat(Xq[:, None, :], S, 1), W, b, pw, v)[:, :, 0]
+    mean, var = o.predict(om, Xq)
+    np.testing.assert_allclose(f.mean(1), mean[:, 0], atol=0.15 * math.sqrt(om.variance))
+    np.testing.assert_allclose(f.var(1), var[:, 0], rtol=0.5, atol=0.02 * om.variance)

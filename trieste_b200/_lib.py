@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libtrieste_b200.so")
 
 TB_F64, TB_F32 = 0, 1
 KERNEL_IDS = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3}
-ACQ_EI, ACQ_LOG_EI, ACQ_NEG_LCB, ACQ_LCB = 0, 1, 2, 3
+ACQ_EI, ACQ_LOG_EI, ACQ_NEG_LCB, ACQ_LCB, ACQ_PBT = 0, 1, 2, 3, 4
 
 _lib: Optional[C.CDLL] = None
 
@@ -45,6 +45,8 @@ SIGNATURES = {
     "tb_rff_set": (_i32, [_vp, C.POINTER(_f64), C.POINTER(_f64), _i32, _i32, C.POINTER(_f64), _f64, _f64]),
     "tb_rff_set_theta": (_i32, [_vp, C.POINTER(_f64), _i32]),
     "tb_rff_eval": (_i32, [_vp, _vp, _i64, _vp, C.POINTER(_f64), C.POINTER(_i64)]),
+    "tb_rff_set_canonical": (_i32, [_vp, _i32, C.POINTER(_f64), _i64, _vp, _i32]),
+    "tb_gp_kinv_apply": (_i32, [_vp, _vp, _i32, _vp]),
     "tb_launch_count": (_i64, []),
     "tb_launch_count_reset": (None, []),
     "tb_gp_set_engine": (_i32, [_vp, _i32]),

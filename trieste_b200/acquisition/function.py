@@ -130,6 +130,60 @@ def _eta_from_model(model, dataset: Dataset, search_space=None) -> float:
     return float(np.min(mean, axis=0)[0])
 
 
+class probability_below_threshold(_FusedSingleQuery):
+    """function.py:481-513: ``Normal(mean, sqrt(var)).cdf(threshold)``."""
+
+    _acq = _lib.ACQ_PBT
+
+    def __init__(self, model, threshold):
+        if np.ndim(threshold) != 0 and np.size(threshold) != 1:
+            raise ValueError("threshold must be a scalar")
+        super().__init__(model, float(np.asarray(threshold).reshape(-1)[0]))
+
+    def update(self, threshold) -> None:
+        self._param = float(np.asarray(threshold).reshape(-1)[0])
+
+
+class ProbabilityOfImprovement(SingleModelAcquisitionBuilder):
+    """function.py:47-93: probability of improving on eta = min posterior mean at the observed points."""
+
+    def __repr__(self) -> str:
+        return "ProbabilityOfImprovement()"
+
+    def prepare_acquisition_function(self, model, dataset: Optional[Dataset] = None):
+        dataset = _check_populated(dataset)
+        return probability_below_threshold(model, _eta_from_model(model, dataset))
+
+    def update_acquisition_function(self, function, model, dataset: Optional[Dataset] = None):
+        dataset = _check_populated(dataset)
+        if not isinstance(function, probability_below_threshold):
+            raise ValueError(f"expected a probability_below_threshold function, got {function!r}")
+        function.update(_eta_from_model(model, dataset))
+        return function
+
+
+class ProbabilityOfFeasibility(SingleModelAcquisitionBuilder):
+    """function.py:421-478: probability that the constraint model is below ``threshold``."""
+
+    def __init__(self, threshold: float):
+        if np.ndim(threshold) != 0:
+            raise ValueError("threshold must be a scalar")
+        self._threshold = float(threshold)
+
+    def __repr__(self) -> str:
+        return f"ProbabilityOfFeasibility({self._threshold!r})"
+
+    @property
+    def threshold(self) -> float:
+        return self._threshold
+
+    def prepare_acquisition_function(self, model, dataset: Optional[Dataset] = None):
+        return probability_below_threshold(model, self._threshold)
+
+    def update_acquisition_function(self, function, model, dataset: Optional[Dataset] = None):
+        return function  # no need to update anything (function.py:470-478)
+
+
 class ExpectedImprovement(SingleModelAcquisitionBuilder):
     """function.py:96-187."""
 

@@ -237,8 +237,8 @@ rff_eval_kernel(const double* __restrict__ Wp,     // [F][DP] (zero padded)
                 const double* __restrict__ bias,   // [F]
                 const double* __restrict__ theta,  // [nb][F]
                 const double* __restrict__ Xc, const double* __restrict__ inv_ls, int D, int F, int nb,
-                int b0, int64_t M, int64_t idx0, double scale, double mean_const, double* __restrict__ out,
-                double* __restrict__ blk_best, int64_t* __restrict__ blk_idx) {
+                int b0, int64_t M, int64_t idx0, double scale, double mean_const, const double* __restrict__ addend,
+                double* __restrict__ out, double* __restrict__ blk_best, int64_t* __restrict__ blk_idx) {
   extern __shared__ __align__(16) unsigned char rsm[];
   double* sW = reinterpret_cast<double*>(rsm);   // [RFF_FCHUNK][DP]
   double* sb = sW + RFF_FCHUNK * DP;             // [RFF_FCHUNK]
@@ -279,7 +279,8 @@ rff_eval_kernel(const double* __restrict__ Wp,     // [F][DP] (zero padded)
 #pragma unroll
   for (int b = 0; b < NBT; ++b) {
     if (b0 + b >= nb) break;
-    const double v = fma(acc[b], scale, mean_const);
+    double v = fma(acc[b], scale, mean_const);
+    if (valid && addend) v += addend[t * nb + b0 + b];  // canonical (pathwise-update) part of a decoupled trajectory
     if (valid && out) out[t * nb + b0 + b] = v;
     if (blk_best) {
       double bv = valid ? -v : -DBL_MAX;  // argmin == first-max of the negated trajectory
@@ -302,6 +303,42 @@ rff_eval_kernel(const double* __restrict__ Wp,     // [F][DP] (zero padded)
         blk_idx[(int64_t)(b0 + b) * gridDim.x + blockIdx.x] = bi;
       }
     }
+  }
+}
+
+// canonical part of a decoupled trajectory (sampler.py:809-855): out[t][b] = sum_j v[b][j] k(x_t, x_j).
+// One thread per candidate; the training rows and weights are warp-uniform loads.
+template <int KIND, int DP, int NBT>
+__global__ void __launch_bounds__(256)
+kdot_kernel(const double* __restrict__ Xs, const double* __restrict__ V, int64_t ldv, const double* __restrict__ Xc,
+            const double* __restrict__ inv_ls, int N, int D, int nb, int b0, int64_t M, double variance,
+            double* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = t < M;
+  double x[DP], acc[NBT];
+#pragma unroll
+  for (int d = 0; d < DP; ++d) x[d] = (valid && d < D) ? Xc[t * D + d] * inv_ls[d] : 0.0;
+#pragma unroll
+  for (int b = 0; b < NBT; ++b) acc[b] = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const double* xr = Xs + (int64_t)k * DP;
+    double r2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; d += 2) {
+      const double2 xv = __ldg(reinterpret_cast<const double2*>(xr + d));
+      const double d0 = x[d] - xv.x, d1 = x[d + 1] - xv.y;
+      r2 = fma(d0, d0, r2);
+      r2 = fma(d1, d1, r2);
+    }
+    const double kv = kernel_from_r2<KIND>(r2, variance);
+#pragma unroll
+    for (int b = 0; b < NBT; ++b)
+      if (b0 + b < nb) acc[b] = fma(kv, __ldg(V + (int64_t)(b0 + b) * ldv + k), acc[b]);
+  }
+  if (valid) {
+#pragma unroll
+    for (int b = 0; b < NBT; ++b)
+      if (b0 + b < nb) out[t * nb + b0 + b] = acc[b];
   }
 }
 

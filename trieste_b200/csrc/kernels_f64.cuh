@@ -312,6 +312,7 @@ __device__ __forceinline__ double acq_value(int acq, double param, double mean, 
   if (acq == TB_ACQ_LCB) return mean - param * sigma;
   if (acq == TB_ACQ_NEG_LCB) return -(mean - param * sigma);
   const double z = (param - mean) / sigma;
+  if (acq == TB_ACQ_PBT) return ndtr_tfp(z);
   if (acq == TB_ACQ_EI) {
     const double pdf_term = sigma * exp(-0.5 * z * z) * 0.3989422804014327;  // variance * N(eta; mean, sigma)
     return (param - mean) * ndtr_tfp(z) + pdf_term;
@@ -346,6 +347,11 @@ __device__ __forceinline__ void acq_partials(int acq, double param, double mean,
   const double z = (param - mean) / sigma;
   const double pdf = exp(-0.5 * z * z) * 0.3989422804014327;
   const double cdf = ndtr_tfp(z);
+  if (acq == TB_ACQ_PBT) {
+    dmu = -pdf / sigma;
+    dvar = clipped ? 0.0 : -pdf * z / (2.0 * var);
+    return;
+  }
   if (acq == TB_ACQ_EI) {
     dmu = -cdf;
     dvar = clipped ? 0.0 : pdf / (2.0 * sigma);

@@ -896,7 +896,7 @@ static int tb_gp_predict_f64(tb_gp* gp, const void* Xc, int64_t M, void* mean, v
 
 static int tb_acq_eval_f64(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* grad) {
   TB_CHECK(gp && (M == 0 || (Xc && out)), "tb_acq_eval: null argument");
-  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_LCB, "tb_acq_eval: unknown acquisition kind");
+  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_PBT, "tb_acq_eval: unknown acquisition kind");
   if (acq == TB_ACQ_LCB || acq == TB_ACQ_NEG_LCB)
     TB_CHECK(param >= 0.0, "Standard deviation scaling parameter beta must not be negative");
   tb::EvalRequest rq;
@@ -912,7 +912,7 @@ static int tb_acq_eval_f64(tb_gp* gp, int acq, double param, const void* Xc, int
 static int tb_acq_argmax_f64(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* best_value,
                   int64_t* best_index) {
   TB_CHECK(gp && Xc && best_value && best_index, "tb_acq_argmax: null argument");
-  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_LCB, "tb_acq_argmax: unknown acquisition kind");
+  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_PBT, "tb_acq_argmax: unknown acquisition kind");
   if (acq == TB_ACQ_LCB || acq == TB_ACQ_NEG_LCB)
     TB_CHECK(param >= 0.0, "Standard deviation scaling parameter beta must not be negative");
   tb::EvalRequest rq;
@@ -940,6 +940,22 @@ int tb_gp_set_engine(tb_gp* gp, int engine) {
   TB_CHECK(gp, "tb_gp_set_engine: null handle");
   TB_CHECK(engine == 0 || engine == 1, "tb_gp_set_engine: engine must be 0 (fp64 DMMA) or 1 (int8 Ozaki)");
   gp->engine = engine;
+  return 0;
+}
+int tb_gp_kinv_apply(tb_gp* gp, const double* B, int nrhs, double* out) {
+  TB_CHECK(gp && B && out, "tb_gp_kinv_apply: null argument");
+  TB_CHECK(gp->cache_valid, "tb_gp_kinv_apply: posterior cache is not built");
+  TB_CHECK(nrhs >= 1, "tb_gp_kinv_apply: need at least one right-hand side");
+  TB_CUDA(cudaSetDevice(gp->device));
+  const int64_t N = gp->N;
+  TB_TRY(gp->sMisc.reserve(sizeof(double) * N * nrhs));
+  TB_CUDA(cudaMemcpyAsync(gp->sMisc.p, B, sizeof(double) * N * nrhs, cudaMemcpyDefault, gp->stream));
+  // (K + noise I)^-1 B through the cached Cholesky factor (cuSOLVER potrs: once per trajectory, off the candidate path)
+  cusolverStatus_t st = cusolverDnDpotrs(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, nrhs, gp->dL.as<double>(), (int)N,
+                                         gp->sMisc.as<double>(), (int)N, gp->dInfo.as<int>());
+  TB_CHECK(st == CUSOLVER_STATUS_SUCCESS, "tb_gp_kinv_apply: cusolverDnDpotrs failed");
+  TB_CUDA(cudaMemcpyAsync(out, gp->sMisc.p, sizeof(double) * N * nrhs, cudaMemcpyDefault, gp->stream));
+  TB_CUDA(cudaStreamSynchronize(gp->stream));
   return 0;
 }
 int tb_gp_stream(tb_gp* gp, void** stream) {
@@ -1217,6 +1233,10 @@ struct tb_rff {
   int F = 0, D = 0, DP = 0, nb = 0;
   double variance = 1.0, mean_const = 0.0;
   tb::DevBuf dW, dB, dTheta, dInvLs, sXc, sOut, sBlkBest, sBlkIdx, sRunV, sRunI;
+  // canonical features of a decoupled trajectory: scaled training inputs + per-trajectory weights v [nbc, N]
+  tb::DevBuf dXs, dV, sCanon;
+  int kernel = TB_MATERN52, nbc = 0;
+  int64_t N = 0;
 };
 
 extern "C" {
@@ -1240,7 +1260,7 @@ int tb_rff_destroy(tb_rff* r) {
   cudaSetDevice(r->device);
   cudaStreamSynchronize(r->stream);
   for (tb::DevBuf* b : {&r->dW, &r->dB, &r->dTheta, &r->dInvLs, &r->sXc, &r->sOut, &r->sBlkBest, &r->sBlkIdx,
-                        &r->sRunV, &r->sRunI})
+                        &r->sRunV, &r->sRunI, &r->dXs, &r->dV, &r->sCanon})
     b->release();
   cudaStreamDestroy(r->stream);
   delete r;
@@ -1274,6 +1294,8 @@ int tb_rff_set(tb_rff* r, const double* W, const double* b, int F, int D, const 
   r->variance = variance;
   r->mean_const = mean_const;
   r->nb = 0;
+  r->nbc = 0;
+  r->N = 0;
   return 0;
 }
 
@@ -1293,14 +1315,14 @@ int tb_rff_set_theta(tb_rff* r, const double* theta, int nb) {
 namespace tb {
 template <int DP>
 static int launch_rff(tb_rff* r, int nbt, int blocks, const double* xc, int b0, int64_t mc, int64_t idx0, double scale,
-                      double* out, double* bb, int64_t* bi) {
+                      const double* addend, double* out, double* bb, int64_t* bi) {
   const size_t smem = sizeof(double) * ((size_t)RFF_FCHUNK * DP + RFF_FCHUNK + (size_t)nbt * RFF_FCHUNK);
 #define TB_RFF(NBT)                                                                                              \
   {                                                                                                              \
     TB_CUDA(cudaFuncSetAttribute(rff_eval_kernel<DP, NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     rff_eval_kernel<DP, NBT><<<blocks, RFF_THREADS, smem, r->stream>>>(r->dW.as<double>(), r->dB.as<double>(),      \
         r->dTheta.as<double>(), xc, r->dInvLs.as<double>(), r->D, r->F, r->nb, b0, mc, idx0, scale, r->mean_const,  \
-        out, bb, bi);                                                                                             \
+        addend, out, bb, bi);                                                                                             \
   }
   switch (nbt) {
     case 1: TB_RFF(1); break;
@@ -1313,6 +1335,82 @@ static int launch_rff(tb_rff* r, int nbt, int blocks, const double* xc, int b0, 
   return 0;
 }
 }  // namespace tb
+
+namespace tb {
+template <int KIND, int DP>
+static void launch_kdot_nbt(tb_rff* r, const double* xc, int64_t mc, double* out) {
+  const int blocks = (int)((mc + 255) / 256);
+  for (int b0 = 0; b0 < r->nbc; b0 += 4) {
+    const int rem = r->nbc - b0;
+    if (rem >= 3)
+      kdot_kernel<KIND, DP, 4><<<blocks, 256, 0, r->stream>>>(r->dXs.as<double>(), r->dV.as<double>(), r->N, xc, r->dInvLs.as<double>(),
+                                                            (int)r->N, r->D, r->nbc, b0, mc, r->variance, out);
+    else if (rem == 2)
+      kdot_kernel<KIND, DP, 2><<<blocks, 256, 0, r->stream>>>(r->dXs.as<double>(), r->dV.as<double>(), r->N, xc, r->dInvLs.as<double>(),
+                                                            (int)r->N, r->D, r->nbc, b0, mc, r->variance, out);
+    else
+      kdot_kernel<KIND, DP, 1><<<blocks, 256, 0, r->stream>>>(r->dXs.as<double>(), r->dV.as<double>(), r->N, xc, r->dInvLs.as<double>(),
+                                                            (int)r->N, r->D, r->nbc, b0, mc, r->variance, out);
+    TB_LAUNCHED();
+  }
+}
+template <int KIND>
+static void launch_kdot_dp(tb_rff* r, const double* xc, int64_t mc, double* out) {
+  switch (r->DP) {
+    case 2: launch_kdot_nbt<KIND, 2>(r, xc, mc, out); break;
+    case 4: launch_kdot_nbt<KIND, 4>(r, xc, mc, out); break;
+    case 6: launch_kdot_nbt<KIND, 6>(r, xc, mc, out); break;
+    case 8: launch_kdot_nbt<KIND, 8>(r, xc, mc, out); break;
+    case 10: launch_kdot_nbt<KIND, 10>(r, xc, mc, out); break;
+    case 12: launch_kdot_nbt<KIND, 12>(r, xc, mc, out); break;
+    case 16: launch_kdot_nbt<KIND, 16>(r, xc, mc, out); break;
+    case 20: launch_kdot_nbt<KIND, 20>(r, xc, mc, out); break;
+    case 24: launch_kdot_nbt<KIND, 24>(r, xc, mc, out); break;
+    default: launch_kdot_nbt<KIND, 32>(r, xc, mc, out); break;
+  }
+}
+static int launch_kdot(tb_rff* r, const double* xc, int64_t mc, double* out) {
+  switch (r->kernel) {
+    case TB_RBF: launch_kdot_dp<TB_RBF>(r, xc, mc, out); break;
+    case TB_MATERN12: launch_kdot_dp<TB_MATERN12>(r, xc, mc, out); break;
+    case TB_MATERN32: launch_kdot_dp<TB_MATERN32>(r, xc, mc, out); break;
+    default: launch_kdot_dp<TB_MATERN52>(r, xc, mc, out); break;
+  }
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace tb
+
+extern "C" {
+
+int tb_rff_set_canonical(tb_rff* r, int kernel, const double* X, int64_t N, const double* v, int nb) {
+  TB_CHECK(r, "tb_rff_set_canonical: null handle");
+  TB_CHECK(r->F > 0, "tb_rff_set_canonical: call tb_rff_set first");
+  if (N == 0) {  // switch the canonical part off
+    r->N = 0;
+    r->nbc = 0;
+    return 0;
+  }
+  TB_CHECK(X && v, "tb_rff_set_canonical: null argument");
+  TB_CHECK(kernel >= TB_RBF && kernel <= TB_MATERN52, "tb_rff_set_canonical: unknown kernel kind");
+  TB_CHECK(N > 0 && nb >= 1, "tb_rff_set_canonical: need N >= 1 training points and nb >= 1 trajectories");
+  TB_CUDA(cudaSetDevice(r->device));
+  const int D = r->D, DP = r->DP;
+  std::vector<double> il(DP, 0.0), Xs((size_t)N * DP, 0.0);
+  TB_CUDA(cudaMemcpy(il.data(), r->dInvLs.p, sizeof(double) * DP, cudaMemcpyDeviceToHost));
+  for (int64_t k = 0; k < N; ++k)
+    for (int d = 0; d < D; ++d) Xs[(size_t)k * DP + d] = X[(size_t)k * D + d] * il[d];
+  TB_TRY(r->dXs.reserve(sizeof(double) * Xs.size()));
+  TB_TRY(r->dV.reserve(sizeof(double) * (size_t)nb * N));
+  TB_CUDA(cudaMemcpy(r->dXs.p, Xs.data(), sizeof(double) * Xs.size(), cudaMemcpyHostToDevice));
+  TB_CUDA(cudaMemcpy(r->dV.p, v, sizeof(double) * (size_t)nb * N, cudaMemcpyDefault));
+  r->kernel = kernel;
+  r->N = N;
+  r->nbc = nb;
+  return 0;
+}
+
+}  // extern "C"
 
 extern "C" {
 
@@ -1352,12 +1450,19 @@ int tb_rff_eval(tb_rff* r, const void* Xc, int64_t M, void* out, double* min_val
       xc = r->sXc.as<double>();
     }
     double* od = out ? (odev ? (double*)out + c0 * nb : r->sOut.as<double>()) : nullptr;
+    const double* addend = nullptr;
+    if (r->N > 0) {
+      TB_CHECK(r->nbc == nb, "tb_rff_eval: canonical weights and theta must have the same number of trajectories");
+      TB_TRY(r->sCanon.reserve(sizeof(double) * (size_t)chunk * nb));
+      TB_TRY(tb::launch_kdot(r, xc, mc, r->sCanon.as<double>()));
+      addend = r->sCanon.as<double>();
+    }
     for (int b0 = 0; b0 < nb; b0 += 4) {
       const int rem = nb - b0;
       const int nbt = rem >= 3 ? 4 : rem;  // kernel handles up to nbt trajectories per pass
       double* bb = want_min ? r->sBlkBest.as<double>() : nullptr;
       int64_t* bi = want_min ? r->sBlkIdx.as<int64_t>() : nullptr;
-#define TB_RFF_DP(DPV) TB_TRY((tb::launch_rff<DPV>(r, nbt, blocks, xc, b0, mc, c0, scale, od, bb, bi)))
+#define TB_RFF_DP(DPV) TB_TRY((tb::launch_rff<DPV>(r, nbt, blocks, xc, b0, mc, c0, scale, addend, od, bb, bi)))
       switch (r->DP) {
         case 2: TB_RFF_DP(2); break;
         case 4: TB_RFF_DP(4); break;

@@ -91,7 +91,7 @@ def _flatten_leading(x, keep: int):
 class GaussianProcessRegression:
     """B200-native exact GPR posterior.  Construct from a :class:`GPRSpec` (or ``build_gpr(...)``)."""
 
-    def __init__(self, model: GPRSpec, device: int = 0, num_rff_features: int = 1000, use_decoupled_sampler: bool = False):
+    def __init__(self, model: GPRSpec, device: int = 0, num_rff_features: int = 1000, use_decoupled_sampler: bool = True):
         _lib.require_gpu()
         if num_rff_features <= 0:
             raise ValueError(f"num_rff_features must be greater or equal to zero, got {num_rff_features}.")
@@ -99,8 +99,6 @@ class GaussianProcessRegression:
         self._device = device
         self._num_rff_features = num_rff_features
         self._use_decoupled_sampler = use_decoupled_sampler
-        if use_decoupled_sampler:
-            raise NotImplementedError("DecoupledTrajectorySampler is listed as 'next' (SURVEY.md §8f-2)")
         h = C.c_void_p()
         self._dtype = model.dtype
         _lib.check(_lib.lib().tb_gp_create(C.byref(h), device, _lib.TB_F32 if self._dtype == np.float32 else _lib.TB_F64))
@@ -274,9 +272,11 @@ class GaussianProcessRegression:
         return BatchReparametrizationSampler(num_samples, self)
 
     def trajectory_sampler(self):
-        """models.py:323-345 (RFF branch, ``use_decoupled_sampler=False``)."""
-        from .sampler import RandomFourierFeatureTrajectorySampler
+        """models.py:323-345: decoupled sampler by default, plain RFF with ``use_decoupled_sampler=False``."""
+        from .sampler import DecoupledTrajectorySampler, RandomFourierFeatureTrajectorySampler
 
+        if self._use_decoupled_sampler:
+            return DecoupledTrajectorySampler(self, self._num_rff_features)
         return RandomFourierFeatureTrajectorySampler(self, self._num_rff_features)
 
     # ---- helpers -----------------------------------------------------------------------------------

@@ -343,3 +343,95 @@ class RandomFourierFeatureTrajectorySampler:
         self._weight_sampler = self._prepare_weight_sampler()
         trajectory.update(self._weight_sampler)
         return trajectory
+
+
+# ---------------------------------------------------------------------------------------------------
+# Decoupled (pathwise) sampling (sampler.py:594-738, 809-855) — the reference's default for GPR
+# (models.py:342-345): f(x) = phi(x) w + sum_j v_j k(x, x_j) + m(x)
+# ---------------------------------------------------------------------------------------------------
+class decoupled_trajectory(feature_decomposition_trajectory):
+    """``feature_decomposition_trajectory`` over F RFF features + N canonical features ``k(., x_j)``; the weight
+    sampler returns ``(w [B, F], v [B, N])``."""
+
+    def resample(self) -> None:
+        w, v = self._weight_sampler(self._batch_size)
+        self._weights_sample = np.ascontiguousarray(w, dtype=np.float64)
+        self._canonical_weights = np.ascontiguousarray(v, dtype=np.float64)
+        self._push_theta()
+        data = self._model.get_internal_data()
+        X = np.ascontiguousarray(np.asarray(data.query_points, dtype=np.float64))
+        dp = C.POINTER(C.c_double)
+        _lib.check(
+            _lib.lib().tb_rff_set_canonical(
+                self._h, _lib.KERNEL_IDS[self._model.get_kernel().kind], X.ctypes.data_as(dp), X.shape[0],
+                self._canonical_weights.ctypes.data, self._canonical_weights.shape[0],
+            )
+        )
+
+
+class DecoupledTrajectorySampler:
+    """sampler.py:594-738 (exact-GP branch :668-677): prior part through RFF weights ``w ~ N(0, I)``, data
+    update through canonical weights ``v = (K + noise I)^-1 (y - m + sqrt(noise) eps - phi(X) w)`` — the solve
+    reuses the model's cached Cholesky factor on the GPU (``tb_gp_kinv_apply``)."""
+
+    def __init__(self, model: GaussianProcessRegression, num_features: int = 1000, seed: Optional[int] = None):
+        for name in ("get_kernel", "get_observation_noise", "get_internal_data"):
+            if not hasattr(model, name):
+                raise NotImplementedError(
+                    "DecoupledTrajectorySampler only works with models that either support get_kernel, "
+                    f"get_observation_noise and get_internal_data or support get_kernel and get_inducing_variables; but received {model!r}."
+                )
+        if num_features <= 0:
+            raise ValueError("num_features must be positive")
+        if len(model.get_internal_data()) == 0:
+            raise ValueError("Dataset must be populated.")
+        self._model = model
+        self._num_features = num_features
+        self._rng = np.random.default_rng(seed)
+        self._feature_functions = ResampleableRandomFourierFeatureFunctions(model, num_features, seed=None if seed is None else seed + 1)
+        self._weight_sampler = None
+
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}({self._model!r}, {self._num_features!r})"
+
+    def canonical_weights(self, prior_w: np.ndarray, eps: np.ndarray) -> np.ndarray:
+        """v [B, N] for given prior weights w [B, F] and noise draws eps [B, N]."""
+        import torch
+
+        data = self._model.get_internal_data()
+        dev = torch.device("cuda", self._model.device)
+        phi_Z = self._feature_functions(data.query_points)  # [N, F] on the GPU
+        resid = np.asarray(data.observations, dtype=np.float64) - self._model.get_mean_function()(data.query_points)  # [N, 1]
+        u = torch.as_tensor(resid[:, 0][None, :] + math.sqrt(self._model.get_observation_noise()) * np.asarray(eps), device=dev)
+        diff = (u - torch.as_tensor(np.asarray(prior_w), device=dev) @ phi_Z.T).contiguous()  # [B, N]
+        out = torch.empty_like(diff)
+        _lib.check(_lib.lib().tb_gp_kinv_apply(self._model.handle, diff.data_ptr(), diff.shape[0], out.data_ptr()))
+        return out.cpu().numpy()
+
+    def _prepare_weight_sampler(self):
+        n = len(self._model.get_internal_data())
+
+        def sample(b: int):
+            w = self._rng.standard_normal((b, self._num_features))
+            eps = self._rng.standard_normal((b, n))
+            return w, self.canonical_weights(w, eps)
+
+        return sample
+
+    def get_trajectory(self) -> decoupled_trajectory:
+        self._weight_sampler = self._prepare_weight_sampler()
+        return decoupled_trajectory(self._feature_functions, self._weight_sampler, self._model)
+
+    def resample_trajectory(self, trajectory: decoupled_trajectory) -> decoupled_trajectory:
+        if not isinstance(trajectory, decoupled_trajectory):
+            raise ValueError("trajectory must be a decoupled_trajectory")
+        trajectory.resample()
+        return trajectory
+
+    def update_trajectory(self, trajectory: decoupled_trajectory) -> decoupled_trajectory:
+        if not isinstance(trajectory, decoupled_trajectory):
+            raise ValueError("trajectory must be a decoupled_trajectory")
+        self._feature_functions.resample()
+        self._weight_sampler = self._prepare_weight_sampler()
+        trajectory.update(self._weight_sampler)
+        return trajectory
