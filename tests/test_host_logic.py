@@ -197,7 +197,26 @@ def _gloo_worker(rank, world, port, q):
                 return i, float(v[i])
 
         pt, bv, bi = sharded_argmax(Fn(), pts)
-        q.put((rank, bi, bv, pt.tolist()))
+
+        # Thompson argmin over sharded candidates with a fake 2-trajectory evaluator
+        from trieste_b200.parallel import sharded_multistart, sharded_thompson_argmin
+
+        tv = np.stack([(pts - 0.25).sum(-1) ** 2, -pts[:, 0]], axis=1)  # [M, 2]
+
+        class Traj:
+            _batch_size = 2
+
+            def argmin_over(self, p):
+                lo = int(np.where((pts == p[0]).all(1))[0][0])
+                v = tv[lo : lo + len(p)]
+                idx = np.argmin(v, axis=0)
+                return v[idx, np.arange(2)], idx
+
+        tp, tvals, tidx = sharded_thompson_argmin(Traj(), pts)
+
+        # multi-start sharding: each rank "optimises" its slice (identity) and reports its best
+        ms_pt, ms_v, ms_i = sharded_multistart(lambda st: (st, -((st - 0.3) ** 2).sum(-1)), pts)
+        q.put((rank, bi, bv, pt.tolist(), tidx.tolist(), tvals.tolist(), int(ms_i), float(ms_v)))
     finally:
         dist.destroy_process_group()
 
@@ -216,6 +235,11 @@ def test_sharded_argmax_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     pts = np.random.default_rng(0).uniform(size=(1001, 3))
-    for rank, bi, bv, pt in res:
+    tv = np.stack([(pts - 0.25).sum(-1) ** 2, -pts[:, 0]], axis=1)
+    ms = -((pts - 0.3) ** 2).sum(-1)
+    for rank, bi, bv, pt, tidx, tvals, ms_i, ms_v in res:
         assert bi == 10 and bv == 1.0
         np.testing.assert_allclose(pt[0], pts[10])
+        assert tidx == list(np.argmin(tv, axis=0))
+        np.testing.assert_allclose(tvals, tv.min(0))
+        assert ms_i == int(np.argmax(ms)) and ms_v == ms.max()

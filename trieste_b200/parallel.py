@@ -83,3 +83,53 @@ def sharded_argmax(fn, points: np.ndarray, group=None):
         gidx, val, pt = -1, float("-inf"), np.zeros(points.shape[1])
     bv, bi, bp = allgather_best(val, gidx, pt, group=group)
     return bp[None, :], bv, bi
+
+
+def sharded_thompson_argmin(trajectory, points: np.ndarray, group=None):
+    """BASELINE config 4: batch Thompson sampling over candidates sharded across the ranks.  Every rank holds the same
+    trajectory (same W, b, theta — broadcast or seeded identically) and evaluates its slice with the fused eval+argmin
+    kernel; one all-gather per trajectory of (-value, global index) picks the minimiser.  Returns (points [B, D],
+    values [B], global indices [B])."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    lo, hi = shard_bounds(points.shape[0], rank, world)
+    if hi > lo:
+        mv, mi = trajectory.argmin_over(points[lo:hi])
+    else:
+        mv, mi = None, None
+    B = len(mv) if mv is not None else int(getattr(trajectory, "_batch_size", 1) or 1)
+    out_p, out_v, out_i = [], [], []
+    for b in range(B):
+        if mv is not None:
+            val, gidx = -float(mv[b]), lo + int(mi[b])
+            pt = points[gidx]
+        else:
+            val, gidx, pt = float("-inf"), -1, np.zeros(points.shape[1])
+        bv, bi, bp = allgather_best(val, gidx, pt, group=group)
+        out_p.append(bp if bp is not None else pt)
+        out_v.append(-bv)
+        out_i.append(bi)
+    return np.stack(out_p), np.asarray(out_v), np.asarray(out_i)
+
+
+def sharded_multistart(optimize_starts, starts: np.ndarray, group=None):
+    """BASELINE config 5: the R multi-starts of ``generate_continuous_optimizer`` sharded across the ranks — each rank
+    runs its slice of starts to convergence with no communication (``optimize_starts(starts_slice) -> (x [r, D],
+    values [r])``), then one all-gather of (best value, global start index, x) picks the winner
+    (optimizer.py:556-559)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    lo, hi = shard_bounds(starts.shape[0], rank, world)
+    if hi > lo:
+        xs, vals = optimize_starts(starts[lo:hi])
+        vals = np.asarray(vals, dtype=np.float64).reshape(-1)
+        j = int(np.argmax(np.where(np.isfinite(vals), vals, -np.inf)))
+        val, gidx, pt = float(vals[j]), lo + j, np.asarray(xs)[j]
+    else:
+        val, gidx, pt = float("-inf"), -1, np.zeros(starts.shape[1])
+    bv, bi, bp = allgather_best(val, gidx, pt, group=group)
+    return (bp if bp is not None else pt)[None, :], bv, bi
