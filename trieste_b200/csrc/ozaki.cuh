@@ -349,8 +349,10 @@ enum { OZ_SUMSQ = 0, OZ_STORE = 1 };
 template <int EPI, int EW>
 __global__ void __launch_bounds__((EW + 2) * 32, EW == 4 ? 2 : 1)  // EW == 4: cap registers at 168 so that K* CTAs fit beside it
 trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, const double* __restrict__ rowscale,
-                  int NB, int nst, int G, int64_t McPad, double out_scale, double* __restrict__ partial,
+                  int NB, int nst, int G, int64_t McPad, double out_scale, int npass, double* __restrict__ partial,
                   double* __restrict__ Aplain, int64_t lda) {
+  // npass = 2: full fp64 accuracy (LO + HI passes, 21 digit products).  npass = 1: HI pass only (digits 1..4, 10 products,
+  // ~2^-28 of the operand scales) — used for fp32 models, whose tolerance it exceeds by orders of magnitude.
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES_LO * STAGE_BYTES_LO);
   uint64_t* full_hi = bars;            // [3]
@@ -392,8 +394,8 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
         if (I >= NB) break;
         const int nk = min(2 * (I + 1), nst);
         const int8_t* aRow = AS + a_stage_offset(I) * (int64_t)(S * TILE);
-        for (int j = 0; j < 2; ++j, ++n) {
-          const bool lo = pass_is_lo(i, j);
+        for (int j = 0; j < npass; ++j, ++n) {
+          const bool lo = npass == 2 && pass_is_lo(i, j);
           // the two pass types lay different stage geometries over the same bytes: on a type change wait until every MMA
           // of the previous pass has retired (completion #n of acc_full); same-type passes just keep streaming
           // (completions are consumed one by one: a parity wait cannot tell completion #k from #k+2)
@@ -431,8 +433,8 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
         const int I = serpentine_rowblock(i, g, G);
         if (I >= NB) break;
         const int nk = min(2 * (I + 1), nst);
-        for (int j = 0; j < 2; ++j, ++n) {
-          const bool lo = pass_is_lo(i, j);
+        for (int j = 0; j < npass; ++j, ++n) {
+          const bool lo = npass == 2 && pass_is_lo(i, j);
           if (n > 0) {  // accumulators must have been read out by the epilogue warps (completion #n of acc_empty)
             mbar_wait(acc_empty, (uint32_t)((n - 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -473,8 +475,8 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
       const int I = serpentine_rowblock(i, g, G);
       if (I >= NB) break;
       const double rs = rowscale[(int64_t)I * 128 + lq * 32 + lane] * out_scale;
-      for (int j = 0; j < 2; ++j, ++n) {
-        const bool lo = pass_is_lo(i, j);
+      for (int j = 0; j < npass; ++j, ++n) {
+        const bool lo = npass == 2 && pass_is_lo(i, j);
         mbar_wait(acc_full, (uint32_t)(n & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lo) {
@@ -511,14 +513,14 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty);  // accumulators are free again: the next pass starts now
-        if (j == 1 && EPI == OZ_STORE) {
+        if (j == npass - 1 && EPI == OZ_STORE) {
           // A[n,t] = rowscale * 2^f * v, stored candidate-major: the 32 lanes of a warp write 32 consecutive rows (256 B)
           const int64_t nrow = (int64_t)I * 128 + lq * 32 + lane;
           double* dstA = Aplain + ((int64_t)tile * 128 + ch * CW) * lda + nrow;
 #pragma unroll
           for (int c = 0; c < CW; ++c) dstA[(int64_t)c * lda] = vacc[c] * rs;
         }
-        if (j == 1 && EPI == OZ_SUMSQ) {
+        if (j == npass - 1 && EPI == OZ_SUMSQ) {
           // A[n,t] = rowscale * 2^f * v; column sums of A^2 over the warp's 32 rows by recursive halving
           // (16 + 8 + 4 + 2 + 2 shuffles per 16 columns instead of 160)
 #pragma unroll

@@ -482,6 +482,9 @@ static int gradient_chunk(tb_gp* gp, int acq, double param, const double* xc, in
   return 0;
 }
 
+// fp32 models (TB_F32 handles) run the HI pass only: 10 digit products, error ~1e-7 sigma_f^2 << the fp32 tolerance
+static inline int oz_npass(const tb_gp* gp) { return gp->dtype == TB_F32 ? 1 : 2; }
+
 // Ozaki engine state: digit tiles of Linv + row scales, built lazily after each cache refresh
 static int ensure_ozaki(tb_gp* gp) {
   if (gp->oz_valid) return 0;
@@ -675,11 +678,11 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
     if (gp->oz_epi_warps == 4)
       oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 4><<<dim3(G, tiles), 6 * 32, oz::SMEM_BYTES, sa>>>(
           gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
-          part[slot]->as<double>(), nullptr, 0);
+          oz_npass(gp), part[slot]->as<double>(), nullptr, 0);
     else
       oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8><<<dim3(G, tiles), 10 * 32, oz::SMEM_BYTES, sa>>>(
           gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
-          part[slot]->as<double>(), nullptr, 0);
+          oz_npass(gp), part[slot]->as<double>(), nullptr, 0);
     TB_LAUNCHED();
     if (gp->profile) {
       TB_CUDA(cudaEventRecord(e1, sa));
@@ -814,7 +817,7 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
     if (use_oz)
       oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8><<<dim3(G, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
           gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad,
-          gp->oz_out_scale, gp->sPartial.as<double>(), nullptr, 0);
+          gp->oz_out_scale, oz_npass(gp), gp->sPartial.as<double>(), nullptr, 0);
     else if (rq.out_grad)
       trigemm_kernel<false, EPI_SUMSQ_PACKED><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
           gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, gp->sPartial.as<double>(),
@@ -1089,7 +1092,7 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
       const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
       oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Goz, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
           gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, Goz, McPad,
-          gp->oz_out_scale, nullptr, gp->sV.as<double>(), lda);
+          gp->oz_out_scale, oz_npass(gp), nullptr, gp->sV.as<double>(), lda);
     } else {
       TB_TRY(launch_kstar(gp, xc_chunk, mc, tiles, gp->sKs.as<double>(), gp->sMean.as<double>()));
       trigemm_kernel<false, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
