@@ -93,7 +93,7 @@ def c5():
     R = 12_500  # one GPU's shard of the 1e5 multi-starts
     xs = torch.rand(R, 1, 20, dtype=torch.float32, device="cuda")
     tg = timed(lambda: fn.value_and_gradient(xs), reps=2)
-    return {"config": "C5 Synthetic-20D GPR N=8192 fp32 I/O log-EI (int8 engine, 10-product fp32 mode; gradients on the fp64 engine)", "engine": m.engine,
+    return {"config": "C5 Synthetic-20D GPR N=8192 fp32 I/O log-EI (int8 engine, 10-product fp32 mode; gradient V = K^-1 k* as a dense digit GEMM)", "engine": m.engine,
             "forward_cand_per_s": M / tf, "value_and_gradient_starts_per_s": R / tg, "ms_forward": tf * 1e3, "ms_grad": tg * 1e3}
 
 

@@ -82,6 +82,8 @@ struct tb_gp {
   // int8 (Ozaki) engine: digit tiles of Linv, per-row scales, K* scale
   int engine = 1;  // 0 = fp64 DMMA, 1 = int8 tensor cores (default; same stated tolerances, ~3x faster)
   tb::DevBuf dAS, dRowScale, dXn2;
+  tb::DevBuf dKinv, dKinvS, dKinvScale;  // gradient path of the int8 engine: digit tiles of K^-1 (full rows)
+  bool kinv_valid = false;
   int oz_epi_warps = 8;    // epilogue warps of the int8 GEMM (4 leaves register room for co-resident K* CTAs)
   bool kstar_mma = false;  // distances of the K* digit kernel on the DMMA pipe (expansion form)
   tb::DevBuf sKs2, sMean2, sPartial2;  // second scratch slot of the pipelined driver

@@ -174,6 +174,47 @@ __global__ void linv_digits_kernel(const double* __restrict__ Linv, int64_t N, c
   }
 }
 
+// K^-1 (gradient path): symmetric matrix given by its lower triangle (column-major, cusolver potri); full rows.
+__device__ __forceinline__ double sym_at(const double* __restrict__ A, int64_t N, int64_t n, int64_t k) {
+  return n >= k ? A[n + k * N] : A[k + n * N];
+}
+__global__ void sym_rowscale_kernel(const double* __restrict__ A, int64_t N, int64_t rows, double* __restrict__ rowscale) {
+  const int64_t n = blockIdx.x;
+  double mx = 0.0;
+  if (n < N)
+    for (int64_t k = threadIdx.x; k < N; k += blockDim.x) mx = fmax(mx, fabs(sym_at(A, N, n, k)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, sm[w]);
+    int e = 0;
+    if (mx > 0.0) {
+      frexp(mx, &e);
+      e += 2;
+    }
+    if (n < rows) rowscale[n] = ldexp(1.0, e);
+  }
+}
+__global__ void sym_digits_kernel(const double* __restrict__ A, int64_t N, int nst, const double* __restrict__ rowscale,
+                                  int8_t* __restrict__ AS) {
+  const int I = blockIdx.y, kc = blockIdx.x;
+  int8_t* dst = AS + ((int64_t)I * nst + kc) * (int64_t)(S * TILE);
+  for (int e = threadIdx.x; e < 128 * KST; e += blockDim.x) {
+    const int r = e % 128, kin = e / 128;
+    const int64_t n = (int64_t)I * 128 + r, k = (int64_t)kc * KST + kin;
+    long long v = 0;
+    if (n < N && k < N) v = __double2ll_rn(sym_at(A, N, n, k) / rowscale[n] * 281474976710656.0);
+    int d[S];
+    digits7(v, d);
+    const int off = (r >> 3) * SBO + (kin >> 4) * LBO + (r & 7) * 16 + (kin & 15);
+#pragma unroll
+    for (int p = 0; p < S; ++p) dst[p * TILE + off] = (int8_t)d[p];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K* digit tiles + posterior mean.  grid = candidate tiles x (512 / blockDim); warp w (0..15 within a tile) owns candidates
 // [8w, 8w+8); lane l <-> (candidate l % 8, 16-wide k chunk l / 8): every digit store of a warp is 512
@@ -349,8 +390,10 @@ enum { OZ_SUMSQ = 0, OZ_STORE = 1 };
 template <int EPI, int EW>
 __global__ void __launch_bounds__((EW + 2) * 32, EW == 4 ? 2 : 1)  // EW == 4: cap registers at 168 so that K* CTAs fit beside it
 trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, const double* __restrict__ rowscale,
-                  int NB, int nst, int G, int64_t McPad, double out_scale, int npass, double* __restrict__ partial,
-                  double* __restrict__ Aplain, int64_t lda) {
+                  int NB, int nst, int G, int64_t McPad, double out_scale, int npass, int full_rows,
+                  double* __restrict__ partial, double* __restrict__ Aplain, int64_t lda) {
+  // full_rows = 0: lower-triangular left factor (Linv): row-block I spans stages [0, 2(I+1)), packed triangularly.
+  // full_rows = 1: dense square left factor (K^-1, gradient path): every row-block spans all nst stages, offset I*nst.
   // npass = 2: full fp64 accuracy (LO + HI passes, 21 digit products).  npass = 1: HI pass only (digits 1..4, 10 products,
   // ~2^-28 of the operand scales) — used for fp32 models, whose tolerance it exceeds by orders of magnitude.
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -392,8 +435,8 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
       for (int i = 0;; ++i) {
         const int I = serpentine_rowblock(i, g, G);
         if (I >= NB) break;
-        const int nk = min(2 * (I + 1), nst);
-        const int8_t* aRow = AS + a_stage_offset(I) * (int64_t)(S * TILE);
+        const int nk = full_rows ? nst : min(2 * (I + 1), nst);
+        const int8_t* aRow = AS + (full_rows ? (int64_t)I * nst : a_stage_offset(I)) * (int64_t)(S * TILE);
         for (int j = 0; j < npass; ++j, ++n) {
           const bool lo = npass == 2 && pass_is_lo(i, j);
           // the two pass types lay different stage geometries over the same bytes: on a type change wait until every MMA
@@ -432,7 +475,7 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
       for (int i = 0;; ++i) {
         const int I = serpentine_rowblock(i, g, G);
         if (I >= NB) break;
-        const int nk = min(2 * (I + 1), nst);
+        const int nk = full_rows ? nst : min(2 * (I + 1), nst);
         for (int j = 0; j < npass; ++j, ++n) {
           const bool lo = npass == 2 && pass_is_lo(i, j);
           if (n > 0) {  // accumulators must have been read out by the epilogue warps (completion #n of acc_empty)

@@ -161,7 +161,7 @@ int tb_gp_destroy(tb_gp* gp) {
   cudaSetDevice(gp->device);
   cudaStreamSynchronize(gp->stream);
   for (tb::DevBuf* b : {&gp->dX, &gp->dy, &gp->dXs, &gp->dInvLs, &gp->dAlpha, &gp->dL, &gp->dLinv,
-                        &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->dXn2, &gp->sKs2, &gp->sMean2, &gp->sPartial2, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
+                        &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->dXn2, &gp->dKinv, &gp->dKinvS, &gp->dKinvScale, &gp->sKs2, &gp->sMean2, &gp->sPartial2, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
                         &gp->sVals, &gp->sVar, &gp->sXc, &gp->sBlkBest, &gp->sBlkIdx, &gp->sRun,
                         &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc})
     b->release();
@@ -311,6 +311,7 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
   gp->cache_valid = true;
   gp->upper_valid = false;
   gp->oz_valid = false;
+  gp->kinv_valid = false;
   return 0;
 }
 
@@ -513,6 +514,64 @@ static int ensure_ozaki(tb_gp* gp) {
   return 0;
 }
 
+// K^-1 digit tiles for the gradient path of the int8 engine: V = K^-1 k* as one dense digit GEMM (same K* digits as the
+// variance GEMM).  K^-1 from the cached factor with cuSOLVER potri (once per BO step, lazily).
+static int ensure_kinv_digits(tb_gp* gp) {
+  if (gp->kinv_valid) return 0;
+  TB_TRY(ensure_ozaki(gp));
+  cudaStream_t st = gp->stream;
+  const int64_t N = gp->N, rows = (int64_t)gp->NB * BM;
+  TB_TRY(gp->dKinv.reserve(sizeof(double) * N * N));
+  TB_CUDA(cudaMemcpyAsync(gp->dKinv.p, gp->dL.p, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, st));
+  int lwork = 0;
+  cusolverStatus_t cs = cusolverDnDpotri_bufferSize(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, &lwork);
+  TB_CHECK(cs == CUSOLVER_STATUS_SUCCESS, "cusolverDnDpotri_bufferSize failed");
+  TB_TRY(gp->dWork.reserve(sizeof(double) * (size_t)std::max(lwork, 1)));
+  cs = cusolverDnDpotri(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, gp->dWork.as<double>(), lwork,
+                        gp->dInfo.as<int>());
+  TB_CHECK(cs == CUSOLVER_STATUS_SUCCESS, "cusolverDnDpotri failed");
+  TB_TRY(gp->dKinvScale.reserve(sizeof(double) * rows));
+  oz::sym_rowscale_kernel<<<(unsigned)rows, 256, 0, st>>>(gp->dKinv.as<double>(), N, rows, gp->dKinvScale.as<double>());
+  TB_LAUNCHED();
+  const size_t bytes = (size_t)gp->NB * gp->nst * oz::S * oz::TILE;
+  TB_TRY(gp->dKinvS.reserve(bytes));
+  oz::sym_digits_kernel<<<dim3(gp->nst, gp->NB), 256, 0, st>>>(gp->dKinv.as<double>(), N, gp->nst, gp->dKinvScale.as<double>(),
+                                                              gp->dKinvS.as<int8_t>());
+  TB_LAUNCHED();
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
+  gp->dKinv.release();  // the dense copy is only needed to cut the digits
+  gp->kinv_valid = true;
+  return 0;
+}
+
+// int8 engine, gradient path: sum-of-squares is already in sPartial (variance GEMM); V = K^-1 k* on the tensor cores
+static int gradient_chunk_oz(tb_gp* gp, int acq, double param, const double* xc, int64_t mc, int tiles, int G, int64_t McPad,
+                             double* out_grad) {
+  cudaStream_t st = gp->stream;
+  double* cmu = gp->sMisc.as<double>();
+  acq_partials_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, st>>>(gp->sPartial.as<double>(), G, McPad, gp->sMean.as<double>(), mc,
+                                                                    gp->variance, acq, param, cmu, cmu + mc);
+  TB_LAUNCHED();
+  const int Gv = std::max(1, std::min(gp->NB, std::max((gp->NB + 7) / 8, (2 * 148 + tiles - 1) / tiles)));
+  oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Gv, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
+      gp->dKinvS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dKinvScale.as<double>(), gp->NB, gp->nst, Gv, McPad, gp->oz_out_scale,
+      oz_npass(gp), 1, nullptr, gp->sV.as<double>(), (int64_t)gp->NB * BM);
+  TB_LAUNCHED();
+  const bool gdev = is_device_ptr(out_grad);
+  double* gd = gdev ? out_grad : gp->sGrad.as<double>();
+  switch (gp->kernel) {
+    case TB_RBF: launch_grad_dp<TB_RBF>(gp, xc, mc, gd); break;
+    case TB_MATERN12: launch_grad_dp<TB_MATERN12>(gp, xc, mc, gd); break;
+    case TB_MATERN32: launch_grad_dp<TB_MATERN32>(gp, xc, mc, gd); break;
+    default: launch_grad_dp<TB_MATERN52>(gp, xc, mc, gd); break;
+  }
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  if (!gdev) TB_CUDA(cudaMemcpyAsync(out_grad, gd, sizeof(double) * mc * gp->D, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
 static int launch_kstar_digits(tb_gp* gp, const double* Xc_dev, int64_t mc, int tiles, int8_t* BS, double* mean) {
   const double* Xs = gp->dXs.as<double>();
   const double* al = gp->dAlpha.as<double>();
@@ -678,11 +737,11 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
     if (gp->oz_epi_warps == 4)
       oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 4><<<dim3(G, tiles), 6 * 32, oz::SMEM_BYTES, sa>>>(
           gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
-          oz_npass(gp), part[slot]->as<double>(), nullptr, 0);
+          oz_npass(gp), 0, part[slot]->as<double>(), nullptr, 0);
     else
       oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8><<<dim3(G, tiles), 10 * 32, oz::SMEM_BYTES, sa>>>(
           gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
-          oz_npass(gp), part[slot]->as<double>(), nullptr, 0);
+          oz_npass(gp), 0, part[slot]->as<double>(), nullptr, 0);
     TB_LAUNCHED();
     if (gp->profile) {
       TB_CUDA(cudaEventRecord(e1, sa));
@@ -762,10 +821,13 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
   const int64_t Mc_max = max_tiles * BT;
   const int64_t chunk_cap = std::min<int64_t>(Mc_max, ((rq.M + BT - 1) / BT) * BT);
   const int64_t tiles_cap = chunk_cap / BT;
-  const int Gmax = std::max(pick_groups(gp, (int)std::min<int64_t>(tiles_cap, 1 << 30)), (gp->NB + 1) / 2);
+  const int Gmax = gp->NB;  // upper bound of every group choice below
 
-  const bool ozaki = gp->engine == 1 && !rq.out_grad;
-  if (ozaki) TB_TRY(ensure_ozaki(gp));
+  const bool ozaki = gp->engine == 1 && gp->N <= 16384;  // here: only reached with a gradient request
+  if (ozaki) {
+    TB_TRY(ensure_ozaki(gp));
+    if (rq.out_grad) TB_TRY(ensure_kinv_digits(gp));
+  }
   TB_TRY(gp->sKs.reserve(std::max((size_t)tiles_cap * gp->nkc * PANEL * sizeof(double),
                                   (size_t)tiles_cap * gp->nst * oz::S * oz::TILE)));
   TB_TRY(gp->sPartial.reserve(sizeof(double) * (size_t)Gmax * chunk_cap));
@@ -775,8 +837,10 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
   if (rq.out_var && !var_dev) TB_TRY(gp->sVar.reserve(sizeof(double) * chunk_cap));
   if (rq.out_grad) {
     TB_CHECK(rq.acq >= 0, "gradients need an acquisition kind");
-    TB_TRY(ensure_upper_panels(gp));
-    TB_TRY(gp->sA.reserve((size_t)tiles_cap * gp->NB * (BM / BK) * PANEL * sizeof(double)));
+    if (!ozaki) {
+      TB_TRY(ensure_upper_panels(gp));
+      TB_TRY(gp->sA.reserve((size_t)tiles_cap * gp->NB * (BM / BK) * PANEL * sizeof(double)));
+    }
     TB_TRY(gp->sV.reserve((size_t)chunk_cap * gp->NB * BM * sizeof(double)));
     TB_TRY(gp->sMisc.reserve(sizeof(double) * 2 * chunk_cap));
     if (!is_device_ptr(rq.out_grad)) TB_TRY(gp->sGrad.reserve(sizeof(double) * chunk_cap * D));
@@ -793,7 +857,7 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
     const int64_t McPad = (int64_t)tiles * BT;
     // int8 engine: one serpentine PAIR of row-blocks per CTA, so the ~150 co-resident CTAs touch only ~9 candidate tiles
     // and their K* digit tiles are re-read from L2 instead of HBM (ncu: 28 GB -> ~1 GB of DRAM reads per launch)
-    const int G = (ozaki && !rq.out_grad) ? std::max(1, (gp->NB + 1) / 2) : pick_groups(gp, tiles);
+    const int G = ozaki ? std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles)) : pick_groups(gp, tiles);
 
     const double* xc_chunk;
     if (xc_dev) {
@@ -802,7 +866,7 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
       TB_CUDA(cudaMemcpyAsync(gp->sXc.p, rq.Xc + c0 * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, st));
       xc_chunk = gp->sXc.as<double>();
     }
-    const bool use_oz = ozaki && !rq.out_grad;
+    const bool use_oz = ozaki;
     if (use_oz)
       TB_TRY(launch_kstar_digits(gp, xc_chunk, mc, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
     else
@@ -817,7 +881,7 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
     if (use_oz)
       oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8><<<dim3(G, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
           gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad,
-          gp->oz_out_scale, oz_npass(gp), gp->sPartial.as<double>(), nullptr, 0);
+          gp->oz_out_scale, oz_npass(gp), 0, gp->sPartial.as<double>(), nullptr, 0);
     else if (rq.out_grad)
       trigemm_kernel<false, EPI_SUMSQ_PACKED><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
           gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, gp->sPartial.as<double>(),
@@ -834,7 +898,12 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
     }
     TB_CUDA(cudaGetLastError());
 
-    if (rq.out_grad) TB_TRY(gradient_chunk(gp, rq.acq, rq.param, xc_chunk, mc, tiles, G, McPad, rq.out_grad + c0 * D));
+    if (rq.out_grad) {
+      if (use_oz)
+        TB_TRY(gradient_chunk_oz(gp, rq.acq, rq.param, xc_chunk, mc, tiles, G, McPad, rq.out_grad + c0 * D));
+      else
+        TB_TRY(gradient_chunk(gp, rq.acq, rq.param, xc_chunk, mc, tiles, G, McPad, rq.out_grad + c0 * D));
+    }
 
     double* d_vals = rq.out_vals ? (vals_dev ? rq.out_vals + c0 : gp->sVals.as<double>()) : nullptr;
     double* d_mean = rq.out_mean ? (mean_dev ? rq.out_mean + c0 : nullptr) : nullptr;  // sMean already holds it
@@ -1092,7 +1161,7 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
       const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
       oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Goz, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
           gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, Goz, McPad,
-          gp->oz_out_scale, oz_npass(gp), nullptr, gp->sV.as<double>(), lda);
+          gp->oz_out_scale, oz_npass(gp), 0, nullptr, gp->sV.as<double>(), lda);
     } else {
       TB_TRY(launch_kstar(gp, xc_chunk, mc, tiles, gp->sKs.as<double>(), gp->sMean.as<double>()));
       trigemm_kernel<false, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
