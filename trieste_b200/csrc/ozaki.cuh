@@ -236,25 +236,47 @@ kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ al
 #pragma unroll
   for (int d = 0; d < DP; ++d) xc[d] = (valid && d < D) ? Xc[t * D + d] * inv_ls[d] : 0.0;
   int8_t* tile = BS + (int64_t)tile_id * nst * (S * TILE) + w * SBO + ch * LBO + cl * 16;
+  // the 64 training rows (+ alpha) of a stage are staged through shared memory with cp.async, double-buffered: ncu showed the
+  // kernel waiting on L1/L2 latency of these warp-broadcast loads (long_scoreboard was the top stall)
+  __shared__ __align__(16) double xs_s[2][KST * DP];
+  __shared__ __align__(16) double al_s[2][KST];
+  auto stage_load = [&](int kc, int buf) {
+    const double* src = Xs + (int64_t)kc * KST * DP;
+    for (int e = threadIdx.x; e < KST * DP / 2; e += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&xs_s[buf][2 * e])), "l"(src + 2 * e) : "memory");
+    for (int e = threadIdx.x; e < KST / 2; e += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&al_s[buf][2 * e])), "l"(alpha + (int64_t)kc * KST + 2 * e)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_load(0, 0);
   double macc = 0.0;
   for (int kc = 0; kc < nst; ++kc) {
+    const int buf = kc & 1;
+    if (kc + 1 < nst) {
+      stage_load(kc + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
     uint32_t pk[S][4];
 #pragma unroll
     for (int p = 0; p < S; ++p) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int k = kc * KST + ch * 16 + j;
-      const double* xr = Xs + (int64_t)k * DP;
+      const int kl = ch * 16 + j, k = kc * KST + kl;
+      const double* xr = &xs_s[buf][kl * DP];
       double r2 = 0.0;
 #pragma unroll
       for (int d = 0; d < DP; d += 2) {
-        double2 v = __ldg(reinterpret_cast<const double2*>(xr + d));
+        const double2 v = *reinterpret_cast<const double2*>(xr + d);
         double d0 = xc[d] - v.x, d1 = xc[d + 1] - v.y;
         r2 = fma(d0, d0, r2);
         r2 = fma(d1, d1, r2);
       }
       const double kval = (valid && k < N) ? kernel_from_r2<KIND>(r2, variance) : 0.0;
-      macc = fma(kval, __ldg(alpha + k), macc);
+      macc = fma(kval, al_s[buf][kl], macc);
       uint32_t wl, wh;
       digit_bytes6(__double2ll_rn(kval * inv_bscale_2p48), wl, wh);
       scatter_digits_rt(pk, j, wl, wh);
@@ -262,6 +284,7 @@ kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ al
 #pragma unroll
     for (int p = 0; p < S; ++p)
       *reinterpret_cast<uint4*>(tile + (int64_t)kc * (S * TILE) + p * TILE) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+    __syncthreads();  // everyone is done with xs_s[buf] before the next iteration's prefetch overwrites it
   }
   macc += __shfl_xor_sync(0xffffffffu, macc, 8);
   macc += __shfl_xor_sync(0xffffffffu, macc, 16);
