@@ -411,10 +411,10 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t stage_base, 
 enum { OZ_SUMSQ = 0, OZ_STORE = 1 };
 // EW = number of epilogue warps (8: 64 columns each; 4: 128 columns each, which leaves registers for co-resident K* CTAs)
 template <int EPI, int EW>
-__global__ void __launch_bounds__((EW + 2) * 32, EW == 4 ? 2 : 1)  // EW == 4: cap registers at 168 so that K* CTAs fit beside it
-trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, const double* __restrict__ rowscale,
-                  int NB, int nst, int G, int64_t McPad, double out_scale, int npass, int full_rows,
-                  double* __restrict__ partial, double* __restrict__ Aplain, int64_t lda) {
+__device__ __forceinline__ void trigemm_i8_body(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS,
+                                                const double* __restrict__ rowscale, int NB, int nst, int G, int64_t McPad,
+                                                double out_scale, int npass, int full_rows, double* __restrict__ partial,
+                                                double* __restrict__ Aplain, int64_t lda) {
   // full_rows = 0: lower-triangular left factor (Linv): row-block I spans stages [0, 2(I+1)), packed triangularly.
   // full_rows = 1: dense square left factor (K^-1, gradient path): every row-block spans all nst stages, offset I*nst.
   // npass = 2: full fp64 accuracy (LO + HI passes, 21 digit products).  npass = 1: HI pass only (digits 1..4, 10 products,
@@ -643,6 +643,23 @@ trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == EW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+template <int EPI, int EW>
+__global__ void __launch_bounds__((EW + 2) * 32, EW == 4 ? 2 : 1)  // EW == 4: cap registers at 168
+trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, const double* __restrict__ rowscale, int NB,
+                  int nst, int G, int64_t McPad, double out_scale, int npass, int full_rows, double* __restrict__ partial,
+                  double* __restrict__ Aplain, int64_t lda) {
+  trigemm_i8_body<EPI, EW>(AS, BS, rowscale, NB, nst, G, McPad, out_scale, npass, full_rows, partial, Aplain, lda);
+}
+// same kernel capped at 128 registers / thread (41 K registers per CTA): leaves room for three 128-thread K*-generation CTAs
+// on the same SM when the generation of the next chunk runs concurrently on the low-priority stream (TB_OZ_OVERLAP=1)
+template <int EPI, int EW>
+__global__ void __maxnreg__(128)
+trigemm_i8_lowreg_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, const double* __restrict__ rowscale, int NB,
+                         int nst, int G, int64_t McPad, double out_scale, int npass, int full_rows, double* __restrict__ partial,
+                         double* __restrict__ Aplain, int64_t lda) {
+  trigemm_i8_body<EPI, EW>(AS, BS, rowscale, NB, nst, G, McPad, out_scale, npass, full_rows, partial, Aplain, lda);
 }
 
 }  // namespace oz

@@ -403,6 +403,7 @@ static int pick_groups(const tb_gp* gp, int tiles) {
 
 int kernels_init() {
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
+  TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_lowreg_kernel<oz::OZ_SUMSQ, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_STORE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
@@ -734,7 +735,11 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
       TB_CUDA(cudaEventCreate(&e1));
       TB_CUDA(cudaEventRecord(e0, sa));
     }
-    if (gp->oz_epi_warps == 4)
+    if (sb != sa)  // overlapped K* generation: register-capped GEMM so that generation CTAs fit beside it
+      oz::trigemm_i8_lowreg_kernel<oz::OZ_SUMSQ, 8><<<dim3(G, tiles), 10 * 32, oz::SMEM_BYTES, sa>>>(
+          gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
+          oz_npass(gp), 0, part[slot]->as<double>(), nullptr, 0);
+    else if (gp->oz_epi_warps == 4)
       oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 4><<<dim3(G, tiles), 6 * 32, oz::SMEM_BYTES, sa>>>(
           gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
           oz_npass(gp), 0, part[slot]->as<double>(), nullptr, 0);
