@@ -65,8 +65,8 @@ int tb_gp_set_data(tb_gp* gp, const void* X, const void* y, int64_t N, int D);
 int tb_gp_set_hyper(tb_gp* gp, int kernel, double variance, const double* lengthscales, int n_ls,
                     double noise_variance, double mean_const);
 
-/* update_posterior_cache (interface.py:108-112): err = y − m(X), L = chol(K(X,X) + σ²I) (cuSOLVER,
- * once per BO step, off the per-candidate path), then Linv and alpha = K⁻¹err packed for the kernels. */
+/* update_posterior_cache (interface.py:108-112): err = y − m(X), L = chol(K(X,X) + σ²I) (hand-written blocked
+ * Cholesky on the DMMA pipe, once per BO step), then Linv and alpha = K⁻¹err packed for the kernels. */
 int tb_gp_update_posterior_cache(tb_gp* gp);
 
 /* copy out the cached Cholesky factor L [N,N] row-major lower (tests / diagnostics). */

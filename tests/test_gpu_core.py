@@ -186,3 +186,44 @@ def test_probability_of_improvement_and_feasibility():
     e[2] = h
     fd = (pof((Xq[:100] + e)[:, None, :]) - pof((Xq[:100] - e)[:, None, :])) / (2 * h)
     np.testing.assert_allclose(grad[:, 0, 2], fd[:, 0], rtol=2e-4, atol=1e-6 * np.abs(grad).max())
+
+
+@pytest.mark.parametrize("N,D,noise", [(5, 2, None), (128, 6, None), (129, 6, None), (300, 6, None), (1024, 6, None), (700, 2, 0.05)])
+def test_handwritten_factorisation_matches_cusolver_and_oracle(N, D, noise, monkeypatch):
+    # posterior-cache precompute (interface.py:89-112): hand-written blocked Cholesky / Linv / alpha (factor.cuh, default)
+    # against the cuSOLVER + cuBLAS cross-check path and the oracle's LAPACK factor
+    obj = o.branin if D == 2 else o.hartmann_6
+    om, nm = model_pair(obj, N, D, noise=noise)
+    monkeypatch.setenv("TB_FACTOR", "cusolver")
+    from tests.util import native_from_oracle
+
+    ref = native_from_oracle(om)
+    monkeypatch.delenv("TB_FACTOR")
+    L, Lr = nm.get_cholesky(), ref.get_cholesky()
+    scale = np.abs(om.L).max()
+    # ill-conditioned case (cond(K) ~ 4e7): the entries of L are only determined to ~cond * eps by ANY factorisation
+    ltol = 1e-9 if noise is None else 1e-5
+    np.testing.assert_allclose(L, om.L, rtol=ltol, atol=ltol * 1e-2 * scale)
+    np.testing.assert_allclose(L, Lr, rtol=ltol, atol=ltol * 1e-2 * scale)
+    Xq = candidates(400, D)
+    m1, v1 = nm.predict(Xq)
+    m2, v2 = ref.predict(Xq)
+    tol = 1e-9 if noise is None else 1e-7  # Branin: Var(y) ~ 2.5e3, so noise 0.05 means cond(K) ~ 4e7: both factorisations are only that accurate
+    np.testing.assert_allclose(m1, m2, rtol=tol, atol=tol * np.sqrt(om.variance))
+    np.testing.assert_allclose(v1, v2, rtol=0, atol=tol * om.variance)
+    # gradient path builds K^-1 from the hand-written Linv (kinv_kernel) vs cuSOLVER potri
+    from trieste_b200.acquisition import lower_confidence_bound
+
+    g1 = lower_confidence_bound(nm, 1.96).value_and_gradient(Xq[:64, None, :])[1]
+    g2 = lower_confidence_bound(ref, 1.96).value_and_gradient(Xq[:64, None, :])[1]
+    gtol = 1e-6 if noise is None else 1e-3  # K^-1 itself carries cond(K) * eps ~ 1e-8..1e-7 in the ill-conditioned case
+    np.testing.assert_allclose(g1, g2, rtol=gtol, atol=gtol * 1e-2 * np.abs(g2).max())
+
+
+def test_not_positive_definite_is_reported():
+    import trieste_b200 as tb
+
+    X = np.array([[0.1, 0.2], [0.1, 0.2], [0.7, 0.3]])  # duplicate point, (almost) no noise -> singular K
+    spec = tb.GPRSpec((X, np.zeros((3, 1))), tb.SquaredExponential(1.0, [0.3, 0.3]), tb.Constant(0.0), 1e-300)
+    with pytest.raises(ValueError, match="Cholesky decomposition was not successful"):
+        tb.GaussianProcessRegression(spec)

@@ -1,0 +1,234 @@
+// Hand-written posterior-cache precompute: blocked Cholesky of K + noise I, triangular
+// inverse Linv = L^-1, alpha = K^-1 err and K^-1 = Linv^T Linv, all on the fp64 DMMA pipe — no cuSOLVER / cuBLAS.
+// Column-major N x N matrices, block size 128.  Once per BO step (off the per-candidate path): written for clarity and
+// determinism, not tuned (single-buffered shared-memory tiles).
+#pragma once
+#include "common.cuh"
+
+namespace tb {
+namespace fac {
+
+constexpr int FB = 128;          // block size
+constexpr int KS = 32;           // k depth of one shared-memory step
+constexpr int LDS = KS + 4;      // padded row stride (doubles): conflict-free m8n8k4 fragment loads
+constexpr int THREADS = 256;     // 8 warps: 2 (rows) x 4 (cols), warp tile 64 x 32
+constexpr size_t GEMM_SMEM = 2 * FB * LDS * sizeof(double);  // 73,728 B
+
+// acc[8][4][2] += A(128 x [k0,k1)) * B([k0,k1) x 128); a_at(m, k), b_at(k, n) return the operand elements (0 outside)
+// A_KFAST / B_KFAST: the operand is contiguous in memory along k (else along its row / column index m, n): picks the
+// thread -> element mapping of the staging loads so that global reads coalesce
+template <bool A_KFAST, bool B_KFAST, class FA, class FB_>
+__device__ __forceinline__ void dmma_tile(FA a_at, FB_ b_at, int k0, int k1, double (&acc)[8][4][2], double* sm) {
+  double* As = sm;
+  double* Bs = sm + FB * LDS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp >> 2, wn = warp & 3;
+  for (int kb = k0; kb < k1; kb += KS) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < FB * KS; e += THREADS) {
+      const int ma = A_KFAST ? e / KS : e % FB, ka = A_KFAST ? e % KS : e / FB;
+      const int nb_ = B_KFAST ? e / KS : e % FB, kb_ = B_KFAST ? e % KS : e / FB;
+      As[ma * LDS + ka] = (kb + ka < k1) ? a_at(ma, kb + ka) : 0.0;
+      Bs[nb_ * LDS + kb_] = (kb + kb_ < k1) ? b_at(kb + kb_, nb_) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k4 = 0; k4 < KS / 4; ++k4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) af[i] = As[(wm * 64 + i * 8 + (lane >> 2)) * LDS + k4 * 4 + (lane & 3)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = Bs[(wn * 32 + j * 8 + (lane >> 2)) * LDS + k4 * 4 + (lane & 3)];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+}
+// visit the accumulator elements of this thread: f(row m in [0,128), col n in [0,128), value&)
+template <class F>
+__device__ __forceinline__ void for_each_acc(double (&acc)[8][4][2], F f) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) f(wm * 64 + i * 8 + (lane >> 2), wn * 32 + j * 8 + (lane & 3) * 2 + c, acc[i][j][c]);
+}
+__device__ __forceinline__ void zero_acc(double (&acc)[8][4][2]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+}
+
+// ---- Cholesky ---------------------------------------------------------------------------------
+// diagonal block j: unblocked Cholesky in shared memory + its inverse; one CTA.  info = first failing pivot (1-based)
+__global__ void __launch_bounds__(THREADS)
+chol_diag_kernel(double* __restrict__ A, int64_t N, int j0, double* __restrict__ Dinv, int* __restrict__ info) {
+  extern __shared__ __align__(16) double S[];  // [FB][FB + 1]
+  const int nb = (int)min((int64_t)FB, N - j0);
+  const int ld = FB + 1;
+  for (int e = threadIdx.x; e < FB * FB; e += THREADS) {
+    const int r = e % FB, c = e / FB;
+    S[r * ld + c] = (r < nb && c < nb && r >= c) ? A[(j0 + r) + (int64_t)(j0 + c) * N] : 0.0;
+  }
+  __syncthreads();
+  for (int k = 0; k < nb; ++k) {
+    const double piv = S[k * ld + k];
+    if (!(piv > 0.0)) {  // uniform across the CTA
+      if (threadIdx.x == 0) atomicCAS(info, 0, j0 + k + 1);
+      return;
+    }
+    const double d = sqrt(piv);
+    __syncthreads();
+    for (int r = k + threadIdx.x; r < nb; r += THREADS) S[r * ld + k] = (r == k) ? d : S[r * ld + k] / d;
+    __syncthreads();
+    // trailing update of the lower triangle: S[r][c] -= S[r][k] S[c][k], k < c <= r
+    const int m = nb - k - 1;
+    for (int e = threadIdx.x; e < m * m; e += THREADS) {
+      const int r = k + 1 + e % m, c = k + 1 + e / m;
+      if (r >= c) S[r * ld + c] = fma(-S[r * ld + k], S[c * ld + k], S[r * ld + c]);
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < nb * nb; e += THREADS) {
+    const int r = e % nb, c = e / nb;
+    A[(j0 + r) + (int64_t)(j0 + c) * N] = (r >= c) ? S[r * ld + c] : 0.0;
+  }
+  // inverse of the lower-triangular block by forward substitution, one column per thread.  X[r][c] (r > c) lives in the
+  // unused strict upper triangle of S (at S[c][r]), the diagonal in xd: every operand of the dependent FMA chain is in smem
+  __shared__ double xd[FB];
+  __syncthreads();
+  for (int c = threadIdx.x; c < nb; c += THREADS) {
+    xd[c] = 1.0 / S[c * ld + c];
+    for (int r = c + 1; r < nb; ++r) {
+      double s = -S[r * ld + c] * xd[c];
+      for (int k = c + 1; k < r; ++k) s = fma(-S[r * ld + k], S[c * ld + k], s);
+      S[c * ld + r] = s / S[r * ld + r];
+    }
+  }
+  __syncthreads();
+  double* X = Dinv + (int64_t)(j0 / FB) * FB * FB;  // column-major [FB][FB]
+  for (int e = threadIdx.x; e < FB * FB; e += THREADS) {
+    const int r = e % FB, c = e / FB;
+    double v = 0.0;
+    if (r < nb && c < nb) v = (r == c) ? xd[c] : (r > c ? S[c * ld + r] : 0.0);
+    X[r + (int64_t)c * FB] = v;
+  }
+}
+
+// panel below diagonal block j: L21 = A21 * invL11^T (in place); grid.x = 128-row tiles below the block
+__global__ void __launch_bounds__(THREADS)
+chol_panel_kernel(double* __restrict__ A, int64_t N, int j0, const double* __restrict__ Dinv) {
+  extern __shared__ __align__(16) double sm[];
+  const int64_t r0 = (int64_t)j0 + FB + (int64_t)blockIdx.x * FB;
+  const double* X = Dinv + (int64_t)(j0 / FB) * FB * FB;
+  double acc[8][4][2];
+  zero_acc(acc);
+  // out[m][n] = sum_k A21[m][k] * invL11[n][k]
+  dmma_tile<false, false>([&](int m, int k) { return (r0 + m < N) ? A[(r0 + m) + (int64_t)(j0 + k) * N] : 0.0; },
+                          [&](int k, int n) { return X[n + (int64_t)k * FB]; }, 0, FB, acc, sm);
+  __syncthreads();
+  for_each_acc(acc, [&](int m, int n, double& v) {
+    if (r0 + m < N && j0 + n < N) A[(r0 + m) + (int64_t)(j0 + n) * N] = v;
+  });
+}
+
+// trailing update after panel j: A22[I][J] -= L21[I] L21[J]^T for the lower tiles I >= J
+__global__ void __launch_bounds__(THREADS)
+chol_syrk_kernel(double* __restrict__ A, int64_t N, int j0) {
+  extern __shared__ __align__(16) double sm[];
+  const int tj = blockIdx.x, ti = blockIdx.y;
+  if (ti < tj) return;
+  const int64_t r0 = (int64_t)j0 + FB + (int64_t)ti * FB, c0 = (int64_t)j0 + FB + (int64_t)tj * FB;
+  if (r0 >= N || c0 >= N) return;
+  double acc[8][4][2];
+  zero_acc(acc);
+  dmma_tile<false, false>([&](int m, int k) { return (r0 + m < N) ? A[(r0 + m) + (int64_t)(j0 + k) * N] : 0.0; },
+                          [&](int k, int n) { return (c0 + n < N) ? A[(c0 + n) + (int64_t)(j0 + k) * N] : 0.0; }, 0, FB, acc, sm);
+  for_each_acc(acc, [&](int m, int n, double& v) {
+    if (r0 + m < N && c0 + n < N && r0 + m >= c0 + n) A[(r0 + m) + (int64_t)(c0 + n) * N] -= v;
+  });
+}
+
+// ---- Linv = L^-1 (lower), block row i:  Linv[i][j] = -invLii * sum_{k=j}^{i-1} L[i][k] Linv[k][j],  Linv[i][i] = invLii ----
+__global__ void __launch_bounds__(THREADS)
+trinv_w_kernel(const double* __restrict__ L, double* __restrict__ Linv, int64_t N, int i) {  // grid.x = j in [0, i)
+  extern __shared__ __align__(16) double sm[];
+  const int j = blockIdx.x;
+  const int64_t r0 = (int64_t)i * FB, c0 = (int64_t)j * FB;
+  double acc[8][4][2];
+  zero_acc(acc);
+  dmma_tile<false, true>([&](int m, int k) { return (r0 + m < N) ? L[(r0 + m) + (int64_t)k * N] : 0.0; },
+                         [&](int k, int n) { return (k >= c0 + n) ? Linv[k + (int64_t)(c0 + n) * N] : 0.0; }, (int)c0, (int)r0, acc, sm);
+  for_each_acc(acc, [&](int m, int n, double& v) {
+    if (r0 + m < N) Linv[(r0 + m) + (int64_t)(c0 + n) * N] = v;  // W, overwritten by trinv_mul_kernel
+  });
+}
+__global__ void __launch_bounds__(THREADS)
+trinv_mul_kernel(double* __restrict__ Linv, int64_t N, int i, const double* __restrict__ Dinv) {  // grid.x = j in [0, i]
+  extern __shared__ __align__(16) double sm[];
+  const int j = blockIdx.x;
+  const int64_t r0 = (int64_t)i * FB, c0 = (int64_t)j * FB;
+  const double* X = Dinv + (int64_t)i * FB * FB;
+  if (j == i) {  // diagonal block: copy invLii (and zero the strictly upper part of the block)
+    for (int e = threadIdx.x; e < FB * FB; e += THREADS) {
+      const int m = e % FB, n = e / FB;
+      if (r0 + m < N && c0 + n < N) Linv[(r0 + m) + (int64_t)(c0 + n) * N] = X[m + (int64_t)n * FB];
+    }
+    return;
+  }
+  double acc[8][4][2];
+  zero_acc(acc);
+  dmma_tile<false, true>([&](int m, int k) { return X[m + (int64_t)k * FB]; },
+                         [&](int k, int n) { return (r0 + k < N) ? Linv[(r0 + k) + (int64_t)(c0 + n) * N] : 0.0; }, 0, FB, acc, sm);
+  __syncthreads();  // every thread has read W before anyone overwrites it
+  for_each_acc(acc, [&](int m, int n, double& v) {
+    if (r0 + m < N) Linv[(r0 + m) + (int64_t)(c0 + n) * N] = -v;
+  });
+}
+
+// ---- K^-1 = Linv^T Linv, lower tiles (I >= J): sum over k >= I*128 of Linv[k][I-cols] * Linv[k][J-cols] ----
+__global__ void __launch_bounds__(THREADS)
+kinv_kernel(const double* __restrict__ Linv, double* __restrict__ Kinv, int64_t N) {
+  extern __shared__ __align__(16) double sm[];
+  const int tj = blockIdx.x, ti = blockIdx.y;
+  if (ti < tj) return;
+  const int64_t r0 = (int64_t)ti * FB, c0 = (int64_t)tj * FB;
+  double acc[8][4][2];
+  zero_acc(acc);
+  dmma_tile<true, true>([&](int m, int k) { return (r0 + m < N && k >= r0 + m) ? Linv[k + (int64_t)(r0 + m) * N] : 0.0; },
+                        [&](int k, int n) { return (c0 + n < N && k >= c0 + n) ? Linv[k + (int64_t)(c0 + n) * N] : 0.0; }, (int)r0, (int)N, acc, sm);
+  for_each_acc(acc, [&](int m, int n, double& v) {
+    if (r0 + m < N && c0 + n < N) Kinv[(r0 + m) + (int64_t)(c0 + n) * N] = v;
+  });
+}
+
+// ---- alpha = Linv^T (Linv r): two triangular mat-vecs, one warp per output element ----
+__global__ void trmv_lower_kernel(const double* __restrict__ Linv, int64_t N, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  double s = 0.0;
+  for (int64_t k = lane; k <= n; k += 32) s = fma(Linv[n + k * N], x[k], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) y[n] = s;
+}
+__global__ void trmv_lower_t_kernel(const double* __restrict__ Linv, int64_t N, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= N) return;
+  double s = 0.0;
+  for (int64_t n = k + lane; n < N; n += 32) s = fma(Linv[n + k * N], x[n], s);  // column k: contiguous
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) y[k] = s;
+}
+
+}  // namespace fac
+}  // namespace tb

@@ -95,7 +95,9 @@ struct tb_gp {
   bool oz_valid = false;
   int nst = 0, oz_bscale_exp = 0;
   double oz_out_scale = 1.0;
-  tb::DevBuf dWork, dInfo;      // cusolver workspace
+  tb::DevBuf dWork, dInfo;      // cusolver workspace / info flag
+  tb::DevBuf dDinv;             // inverses of the diagonal blocks of L (hand-written factorisation)
+  bool factor_own = true;       // false (TB_FACTOR=cusolver): cuSOLVER / cuBLAS cross-check path
 
   // per-call scratch
   tb::DevBuf sKs, sPartial, sMean, sVals, sVar, sXc, sBlkBest, sBlkIdx, sRun;

@@ -3,6 +3,7 @@
 #include "gp_handle.cuh"
 #include "kernels_extra.cuh"
 #include "ozaki.cuh"
+#include "factor.cuh"
 
 using namespace tb;
 namespace tb {
@@ -132,6 +133,7 @@ int tb_gp_create(tb_gp** out, int device, int dtype) {
   tb_gp* gp = new tb_gp();
   gp->device = device;
   gp->dtype = dtype;
+  if (const char* e = std::getenv("TB_FACTOR")) gp->factor_own = std::string(e) != "cusolver";
   if (const char* e = std::getenv("TB_ENGINE")) gp->engine = (std::string(e) == "fp64") ? 0 : 1;
   if (const char* e = std::getenv("TB_OZ_EW")) gp->oz_epi_warps = std::atoi(e) == 4 ? 4 : 8;
   if (const char* e = std::getenv("TB_KSTAR_MMA")) gp->kstar_mma = std::atoi(e) != 0;
@@ -161,7 +163,7 @@ int tb_gp_destroy(tb_gp* gp) {
   cudaSetDevice(gp->device);
   cudaStreamSynchronize(gp->stream);
   for (tb::DevBuf* b : {&gp->dX, &gp->dy, &gp->dXs, &gp->dInvLs, &gp->dAlpha, &gp->dL, &gp->dLinv,
-                        &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->dXn2, &gp->dKinv, &gp->dKinvS, &gp->dKinvScale, &gp->sKs2, &gp->sMean2, &gp->sPartial2, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
+                        &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->dXn2, &gp->dKinv, &gp->dKinvS, &gp->dKinvScale, &gp->dDinv, &gp->sKs2, &gp->sMean2, &gp->sPartial2, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
                         &gp->sVals, &gp->sVar, &gp->sXc, &gp->sBlkBest, &gp->sBlkIdx, &gp->sRun,
                         &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc})
     b->release();
@@ -263,39 +265,87 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
     }
     TB_LAUNCHED();
   }
-  // L = chol(K + noise I): library call on the once-per-step path (cuSOLVER), SURVEY.md §8 a3 / §8f-1
-  int lwork = 0;
-  TB_CUSOLVER(cusolverDnDpotrf_bufferSize(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dL.as<double>(),
-                                          (int)N, &lwork));
-  TB_TRY(gp->dWork.reserve(sizeof(double) * (size_t)std::max(lwork, 1)));
   TB_TRY(gp->dInfo.reserve(sizeof(int)));
-  TB_CUSOLVER(cusolverDnDpotrf(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dL.as<double>(), (int)N,
-                               gp->dWork.as<double>(), lwork, gp->dInfo.as<int>()));
-  int info = 0;
-  TB_CUDA(cudaMemcpyAsync(&info, gp->dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  TB_CUDA(cudaStreamSynchronize(st));
-  TB_CHECK(info == 0, "tb_gp_update_posterior_cache: Cholesky decomposition was not successful "
-                      "(K + noise*I not positive definite at leading minor " + std::to_string(info) + ")");
-  {
-    dim3 grid((unsigned)((N + 127) / 128), (unsigned)N);
-    zero_upper_kernel<<<grid, 128, 0, st>>>(N, gp->dL.as<double>());
-    TB_LAUNCHED();
-  }
-  // alpha = K^-1 err
   TB_TRY(gp->dAlpha.reserve(sizeof(double) * rows));
-  residual_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(gp->dy.as<double>(), N, rows, gp->mean_const,
-                                                                  gp->dAlpha.as<double>());
-  TB_LAUNCHED();
-  TB_CUSOLVER(cusolverDnDpotrs(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, 1, gp->dL.as<double>(), (int)N,
-                               gp->dAlpha.as<double>(), (int)N, gp->dInfo.as<int>()));
-  // Linv = L^-1 (triangular solve against the identity)
-  {
+  if (gp->factor_own) {
+    // ---- hand-written path (factor.cuh): blocked Cholesky, Linv, alpha on the DMMA pipe; no library call ----
+    const int nbk = (int)((N + fac::FB - 1) / fac::FB);
+    TB_TRY(gp->dDinv.reserve(sizeof(double) * (size_t)nbk * fac::FB * fac::FB));
+    TB_CUDA(cudaMemsetAsync(gp->dInfo.p, 0, sizeof(int), st));
+    double* A = gp->dL.as<double>();
+    const size_t diag_smem = sizeof(double) * fac::FB * (fac::FB + 1);
+    for (int jb = 0; jb < nbk; ++jb) {
+      const int j0 = jb * fac::FB;
+      fac::chol_diag_kernel<<<1, fac::THREADS, diag_smem, st>>>(A, N, j0, gp->dDinv.as<double>(), gp->dInfo.as<int>());
+      TB_LAUNCHED();
+      const int64_t below = N - (int64_t)(j0 + fac::FB);
+      if (below > 0) {
+        const unsigned t = (unsigned)((below + fac::FB - 1) / fac::FB);
+        fac::chol_panel_kernel<<<t, fac::THREADS, fac::GEMM_SMEM, st>>>(A, N, j0, gp->dDinv.as<double>());
+        TB_LAUNCHED();
+        fac::chol_syrk_kernel<<<dim3(t, t), fac::THREADS, fac::GEMM_SMEM, st>>>(A, N, j0);
+        TB_LAUNCHED();
+      }
+    }
+    int info = 0;
+    TB_CUDA(cudaMemcpyAsync(&info, gp->dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    TB_CUDA(cudaGetLastError());
+    TB_CHECK(info == 0, "tb_gp_update_posterior_cache: Cholesky decomposition was not successful "
+                        "(K + noise*I not positive definite at leading minor " + std::to_string(info) + ")");
+    {
+      dim3 grid((unsigned)((N + 127) / 128), (unsigned)N);
+      zero_upper_kernel<<<grid, 128, 0, st>>>(N, A);
+      TB_LAUNCHED();
+    }
+    TB_CUDA(cudaMemsetAsync(gp->dLinv.p, 0, sizeof(double) * N * N, st));
+    for (int ib = 0; ib < nbk; ++ib) {
+      if (ib > 0) {
+        fac::trinv_w_kernel<<<ib, fac::THREADS, fac::GEMM_SMEM, st>>>(A, gp->dLinv.as<double>(), N, ib);
+        TB_LAUNCHED();
+      }
+      fac::trinv_mul_kernel<<<ib + 1, fac::THREADS, fac::GEMM_SMEM, st>>>(gp->dLinv.as<double>(), N, ib, gp->dDinv.as<double>());
+      TB_LAUNCHED();
+    }
+    // alpha = Linv^T (Linv err)
+    TB_TRY(gp->sMisc.reserve(sizeof(double) * 2 * rows));
+    double* err = gp->sMisc.as<double>();
+    double* tmp = err + rows;
+    residual_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(gp->dy.as<double>(), N, rows, gp->mean_const, err);
+    TB_LAUNCHED();
+    TB_CUDA(cudaMemsetAsync(gp->dAlpha.p, 0, sizeof(double) * rows, st));
+    fac::trmv_lower_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(gp->dLinv.as<double>(), N, err, tmp);
+    TB_LAUNCHED();
+    fac::trmv_lower_t_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(gp->dLinv.as<double>(), N, tmp, gp->dAlpha.as<double>());
+    TB_LAUNCHED();
+  } else {
+    // ---- library path (TB_FACTOR=cusolver): cuSOLVER potrf / potrs + cuBLAS trsm; kept as a cross-check ----
+    int lwork = 0;
+    TB_CUSOLVER(cusolverDnDpotrf_bufferSize(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dL.as<double>(), (int)N, &lwork));
+    TB_TRY(gp->dWork.reserve(sizeof(double) * (size_t)std::max(lwork, 1)));
+    TB_CUSOLVER(cusolverDnDpotrf(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dL.as<double>(), (int)N,
+                                 gp->dWork.as<double>(), lwork, gp->dInfo.as<int>()));
+    int info = 0;
+    TB_CUDA(cudaMemcpyAsync(&info, gp->dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    TB_CHECK(info == 0, "tb_gp_update_posterior_cache: Cholesky decomposition was not successful "
+                        "(K + noise*I not positive definite at leading minor " + std::to_string(info) + ")");
+    {
+      dim3 grid((unsigned)((N + 127) / 128), (unsigned)N);
+      zero_upper_kernel<<<grid, 128, 0, st>>>(N, gp->dL.as<double>());
+      TB_LAUNCHED();
+    }
+    residual_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(gp->dy.as<double>(), N, rows, gp->mean_const,
+                                                                    gp->dAlpha.as<double>());
+    TB_LAUNCHED();
+    TB_CUSOLVER(cusolverDnDpotrs(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, 1, gp->dL.as<double>(), (int)N,
+                                 gp->dAlpha.as<double>(), (int)N, gp->dInfo.as<int>()));
     int64_t tot = N * N;
     identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(N, gp->dLinv.as<double>());
     TB_LAUNCHED();
     const double one = 1.0;
-    TB_CUBLAS(cublasDtrsm(gp->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
-                          (int)N, (int)N, &one, gp->dL.as<double>(), (int)N, gp->dLinv.as<double>(), (int)N));
+    TB_CUBLAS(cublasDtrsm(gp->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)N,
+                          (int)N, &one, gp->dL.as<double>(), (int)N, gp->dLinv.as<double>(), (int)N));
   }
   // pack the lower triangle of Linv into DMMA-fragment-ordered panels
   {
@@ -402,6 +452,12 @@ static int pick_groups(const tb_gp* gp, int tiles) {
 }
 
 int kernels_init() {
+  TB_CUDA(cudaFuncSetAttribute(fac::chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * fac::FB * (fac::FB + 1))));
+  TB_CUDA(cudaFuncSetAttribute(fac::chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
+  TB_CUDA(cudaFuncSetAttribute(fac::chol_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
+  TB_CUDA(cudaFuncSetAttribute(fac::trinv_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
+  TB_CUDA(cudaFuncSetAttribute(fac::trinv_mul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
+  TB_CUDA(cudaFuncSetAttribute(fac::kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_lowreg_kernel<oz::OZ_SUMSQ, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
@@ -523,6 +579,11 @@ static int ensure_kinv_digits(tb_gp* gp) {
   cudaStream_t st = gp->stream;
   const int64_t N = gp->N, rows = (int64_t)gp->NB * BM;
   TB_TRY(gp->dKinv.reserve(sizeof(double) * N * N));
+  if (gp->factor_own) {
+    const unsigned t = (unsigned)((N + fac::FB - 1) / fac::FB);
+    fac::kinv_kernel<<<dim3(t, t), fac::THREADS, fac::GEMM_SMEM, st>>>(gp->dLinv.as<double>(), gp->dKinv.as<double>(), N);
+    TB_LAUNCHED();
+  } else {
   TB_CUDA(cudaMemcpyAsync(gp->dKinv.p, gp->dL.p, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, st));
   int lwork = 0;
   cusolverStatus_t cs = cusolverDnDpotri_bufferSize(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, &lwork);
@@ -531,6 +592,7 @@ static int ensure_kinv_digits(tb_gp* gp) {
   cs = cusolverDnDpotri(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, gp->dWork.as<double>(), lwork,
                         gp->dInfo.as<int>());
   TB_CHECK(cs == CUSOLVER_STATUS_SUCCESS, "cusolverDnDpotri failed");
+  }
   TB_TRY(gp->dKinvScale.reserve(sizeof(double) * rows));
   oz::sym_rowscale_kernel<<<(unsigned)rows, 256, 0, st>>>(gp->dKinv.as<double>(), N, rows, gp->dKinvScale.as<double>());
   TB_LAUNCHED();
