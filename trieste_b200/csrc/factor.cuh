@@ -155,41 +155,44 @@ chol_syrk_kernel(double* __restrict__ A, int64_t N, int j0) {
   });
 }
 
-// ---- Linv = L^-1 (lower), block row i:  Linv[i][j] = -invLii * sum_{k=j}^{i-1} L[i][k] Linv[k][j],  Linv[i][i] = invLii ----
+// ---- Linv by recursive doubling (fully parallel GEMMs): with L = [[A, 0], [B, C]] and A^-1, C^-1 known (size n),
+//      Linv[B-block] = -C^-1 (B A^-1).  One level = two launches over all pairs; log2(N/128) levels.
+//      STEP 1: T = B A^-1 into a scratch matrix (same coordinates);  STEP 2: Linv[B-block] = -C^-1 T.
+template <int STEP>
 __global__ void __launch_bounds__(THREADS)
-trinv_w_kernel(const double* __restrict__ L, double* __restrict__ Linv, int64_t N, int i) {  // grid.x = j in [0, i)
+trinv_level_kernel(const double* __restrict__ L, double* __restrict__ Linv, double* __restrict__ T, int64_t N, int n) {
   extern __shared__ __align__(16) double sm[];
-  const int j = blockIdx.x;
-  const int64_t r0 = (int64_t)i * FB, c0 = (int64_t)j * FB;
+  const int64_t c0 = (int64_t)blockIdx.z * 2 * n, r0 = c0 + n;  // A at (c0, c0), B at (r0, c0), C at (r0, r0)
+  const int64_t m0 = r0 + (int64_t)blockIdx.y * FB, n0 = c0 + (int64_t)blockIdx.x * FB;
+  if (m0 >= N) return;
   double acc[8][4][2];
   zero_acc(acc);
-  dmma_tile<false, true>([&](int m, int k) { return (r0 + m < N) ? L[(r0 + m) + (int64_t)k * N] : 0.0; },
-                         [&](int k, int n) { return (k >= c0 + n) ? Linv[k + (int64_t)(c0 + n) * N] : 0.0; }, (int)c0, (int)r0, acc, sm);
-  for_each_acc(acc, [&](int m, int n, double& v) {
-    if (r0 + m < N) Linv[(r0 + m) + (int64_t)(c0 + n) * N] = v;  // W, overwritten by trinv_mul_kernel
-  });
-}
-__global__ void __launch_bounds__(THREADS)
-trinv_mul_kernel(double* __restrict__ Linv, int64_t N, int i, const double* __restrict__ Dinv) {  // grid.x = j in [0, i]
-  extern __shared__ __align__(16) double sm[];
-  const int j = blockIdx.x;
-  const int64_t r0 = (int64_t)i * FB, c0 = (int64_t)j * FB;
-  const double* X = Dinv + (int64_t)i * FB * FB;
-  if (j == i) {  // diagonal block: copy invLii (and zero the strictly upper part of the block)
-    for (int e = threadIdx.x; e < FB * FB; e += THREADS) {
-      const int m = e % FB, n = e / FB;
-      if (r0 + m < N && c0 + n < N) Linv[(r0 + m) + (int64_t)(c0 + n) * N] = X[m + (int64_t)n * FB];
-    }
-    return;
+  if (STEP == 1) {
+    // T[m][nn] = sum_{k >= nn} L[m][c0 + k] * Linv[c0 + k][nn]
+    dmma_tile<false, true>([&](int m, int k) { return (m0 + m < N) ? L[(m0 + m) + (c0 + k) * N] : 0.0; },
+                           [&](int k, int nn) { return (c0 + k >= n0 + nn) ? Linv[(c0 + k) + (n0 + nn) * N] : 0.0; },
+                           (int)(n0 - c0), n, acc, sm);
+    for_each_acc(acc, [&](int m, int nn, double& v) {
+      if (m0 + m < N) T[(m0 + m) + (n0 + nn) * N] = v;
+    });
+  } else {
+    // Linv[m][nn] = - sum_{k <= m} Linv[m][r0 + k] * T[r0 + k][nn]
+    const int kend = (int)min((int64_t)n, m0 - r0 + FB);
+    dmma_tile<false, true>([&](int m, int k) { return (m0 + m < N && r0 + k <= m0 + m) ? Linv[(m0 + m) + (r0 + k) * N] : 0.0; },
+                           [&](int k, int nn) { return (r0 + k < N) ? T[(r0 + k) + (n0 + nn) * N] : 0.0; }, 0, kend, acc, sm);
+    for_each_acc(acc, [&](int m, int nn, double& v) {
+      if (m0 + m < N) Linv[(m0 + m) + (n0 + nn) * N] = -v;
+    });
   }
-  double acc[8][4][2];
-  zero_acc(acc);
-  dmma_tile<false, true>([&](int m, int k) { return X[m + (int64_t)k * FB]; },
-                         [&](int k, int n) { return (r0 + k < N) ? Linv[(r0 + k) + (int64_t)(c0 + n) * N] : 0.0; }, 0, FB, acc, sm);
-  __syncthreads();  // every thread has read W before anyone overwrites it
-  for_each_acc(acc, [&](int m, int n, double& v) {
-    if (r0 + m < N) Linv[(r0 + m) + (int64_t)(c0 + n) * N] = -v;
-  });
+}
+// diagonal blocks of Linv = inverses of the diagonal blocks of L
+__global__ void trinv_diag_kernel(double* __restrict__ Linv, int64_t N, const double* __restrict__ Dinv) {
+  const int64_t b0 = (int64_t)blockIdx.x * FB;
+  const double* X = Dinv + (int64_t)blockIdx.x * FB * FB;
+  for (int e = threadIdx.x; e < FB * FB; e += blockDim.x) {
+    const int m = e % FB, nn = e / FB;
+    if (b0 + m < N && b0 + nn < N) Linv[(b0 + m) + (b0 + nn) * N] = X[m + (int64_t)nn * FB];
+  }
 }
 
 // ---- K^-1 = Linv^T Linv, lower tiles (I >= J): sum over k >= I*128 of Linv[k][I-cols] * Linv[k][J-cols] ----

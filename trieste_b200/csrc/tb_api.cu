@@ -299,13 +299,20 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
       TB_LAUNCHED();
     }
     TB_CUDA(cudaMemsetAsync(gp->dLinv.p, 0, sizeof(double) * N * N, st));
-    for (int ib = 0; ib < nbk; ++ib) {
-      if (ib > 0) {
-        fac::trinv_w_kernel<<<ib, fac::THREADS, fac::GEMM_SMEM, st>>>(A, gp->dLinv.as<double>(), N, ib);
+    // Linv by recursive doubling: diagonal 128-blocks first, then block sizes 128, 256, ... (two GEMM launches per level)
+    fac::trinv_diag_kernel<<<nbk, 256, 0, st>>>(gp->dLinv.as<double>(), N, gp->dDinv.as<double>());
+    TB_LAUNCHED();
+    if (nbk > 1) {
+      TB_TRY(gp->dKinv.reserve(sizeof(double) * N * N));  // scratch T (the buffer is reused later for K^-1)
+      for (int64_t n = fac::FB; n < (int64_t)nbk * fac::FB; n *= 2) {
+        const unsigned tiles = (unsigned)(n / fac::FB), pairs = (unsigned)((N + 2 * n - 1) / (2 * n));
+        fac::trinv_level_kernel<1><<<dim3(tiles, tiles, pairs), fac::THREADS, fac::GEMM_SMEM, st>>>(A, gp->dLinv.as<double>(),
+                                                                                                   gp->dKinv.as<double>(), N, (int)n);
+        TB_LAUNCHED();
+        fac::trinv_level_kernel<2><<<dim3(tiles, tiles, pairs), fac::THREADS, fac::GEMM_SMEM, st>>>(A, gp->dLinv.as<double>(),
+                                                                                                   gp->dKinv.as<double>(), N, (int)n);
         TB_LAUNCHED();
       }
-      fac::trinv_mul_kernel<<<ib + 1, fac::THREADS, fac::GEMM_SMEM, st>>>(gp->dLinv.as<double>(), N, ib, gp->dDinv.as<double>());
-      TB_LAUNCHED();
     }
     // alpha = Linv^T (Linv err)
     TB_TRY(gp->sMisc.reserve(sizeof(double) * 2 * rows));
@@ -455,8 +462,8 @@ int kernels_init() {
   TB_CUDA(cudaFuncSetAttribute(fac::chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * fac::FB * (fac::FB + 1))));
   TB_CUDA(cudaFuncSetAttribute(fac::chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
   TB_CUDA(cudaFuncSetAttribute(fac::chol_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
-  TB_CUDA(cudaFuncSetAttribute(fac::trinv_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
-  TB_CUDA(cudaFuncSetAttribute(fac::trinv_mul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
+  TB_CUDA(cudaFuncSetAttribute(fac::trinv_level_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
+  TB_CUDA(cudaFuncSetAttribute(fac::trinv_level_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
   TB_CUDA(cudaFuncSetAttribute(fac::kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_lowreg_kernel<oz::OZ_SUMSQ, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
