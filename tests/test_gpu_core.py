@@ -227,3 +227,41 @@ def test_not_positive_definite_is_reported():
     spec = tb.GPRSpec((X, np.zeros((3, 1))), tb.SquaredExponential(1.0, [0.3, 0.3]), tb.Constant(0.0), 1e-300)
     with pytest.raises(ValueError, match="Cholesky decomposition was not successful"):
         tb.GaussianProcessRegression(spec)
+
+
+@pytest.mark.parametrize("engine", ["int8", "fp64"])
+@pytest.mark.parametrize("D", [1, 7, 19, 32])
+def test_input_dimension_extremes(D, engine):
+    # every padded-dimension instantiation (DP = 2 .. 32), odd D included
+    om, nm = model_pair(o.ackley, 200, D, engine=engine)
+    Xq = candidates(513, D)
+    _check_predict(om, nm, Xq)
+    with pytest.raises(ValueError):
+        import trieste_b200 as tb
+
+        tb.GaussianProcessRegression(tb.GPRSpec((np.zeros((4, 33)), np.zeros((4, 1))), tb.Matern52(1.0, np.ones(33)), tb.Constant(0.0), 0.1))
+
+
+def test_single_candidate_and_single_training_point():
+    from trieste_b200.acquisition import expected_improvement
+
+    om, nm = model_pair(o.branin, 1, 2)
+    _check_predict(om, nm, candidates(3, 2))
+    om, nm = model_pair(o.hartmann_6, 50, 6)
+    x1 = candidates(1, 6)
+    mean, var = nm.predict(x1)
+    omean, ovar = o.predict(om, x1)
+    np.testing.assert_allclose(mean, omean, rtol=1e-9, atol=1e-9)
+    idx, best = expected_improvement(nm, o.ei_eta(om)).fused_argmax(x1)
+    assert idx == 0 and best == o.expected_improvement(omean, ovar, o.ei_eta(om))[0, 0] or abs(best - o.expected_improvement(omean, ovar, o.ei_eta(om))[0, 0]) < 1e-12
+
+
+def test_large_model_falls_back_to_fp64_engine():
+    # the int8 engine's int32 accumulators are exact up to N = 16384; beyond that the native fp64 engine takes over
+    om, nm = model_pair(o.hartmann_6, 16500, 6)
+    assert nm.engine == "int8"  # requested engine; the library falls back transparently
+    Xq = candidates(256, 6)
+    mean, var = nm.predict(Xq)
+    omean, ovar = o.predict(om, Xq)
+    np.testing.assert_allclose(mean, omean, rtol=1e-8, atol=1e-8 * np.sqrt(om.variance))
+    np.testing.assert_allclose(var, ovar, rtol=0, atol=1e-8 * om.variance)

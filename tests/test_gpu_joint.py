@@ -110,3 +110,17 @@ def test_builder_argument_checks():
         BatchMonteCarloExpectedImprovement(0)
     with pytest.raises(ValueError):
         BatchMonteCarloExpectedImprovement(10, jitter=-1.0)
+
+
+def test_predict_joint_max_batch_size_and_argument_checks():
+    om, nm = model_pair(o.hartmann_6, 150, 6)
+    X = candidates(5 * 32, 6).reshape(5, 32, 6)
+    mean, cov = nm.predict_joint(X)
+    omean, ocov = o.predict_joint(om, X)
+    np.testing.assert_allclose(cov, ocov, rtol=0, atol=1e-9 * om.variance)
+    with pytest.raises(ValueError):
+        nm.predict_joint(candidates(33 * 2, 6).reshape(2, 33, 6))  # q > 32 is not supported
+    with pytest.raises(ValueError):
+        nm.predict_joint(candidates(6, 6)[0])  # rank < 2
+    m0, c0 = nm.predict_joint(np.zeros((0, 4, 6)))
+    assert m0.shape == (0, 4, 1) and c0.shape == (0, 1, 4, 4)
