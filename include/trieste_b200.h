@@ -41,8 +41,10 @@ enum tb_acq {
   TB_ACQ_LOG_EI = 1,  /* log of the above; ABSENT in the reference */
   TB_ACQ_NEG_LCB = 2, /* NegativeLowerConfidenceBound, function.py:358-359 (−lower_confidence_bound :415-416) */
   TB_ACQ_LCB = 3,     /* lower_confidence_bound, function.py:389-418 */
-  TB_ACQ_PBT = 4      /* probability_below_threshold.__call__, function.py:501-509 (ProbabilityOfImprovement :47-93,
+  TB_ACQ_PBT = 4,     /* probability_below_threshold.__call__, function.py:501-509 (ProbabilityOfImprovement :47-93,
                          ProbabilityOfFeasibility :421-478): Normal(mean, sqrt(var)).cdf(param) */
+  TB_ACQ_AEI = 5      /* augmented_expected_improvement.__call__, function.py:311-325: EI(param = eta) times
+                         1 − sqrt(noise)/sqrt(noise + var), noise = the handle's likelihood variance */
 };
 
 /* ---- errors / build info ------------------------------------------------------------------ */
@@ -68,6 +70,12 @@ int tb_gp_set_hyper(tb_gp* gp, int kernel, double variance, const double* length
 /* update_posterior_cache (interface.py:108-112): err = y − m(X), L = chol(K(X,X) + σ²I) (hand-written blocked
  * Cholesky on the DMMA pipe, once per BO step), then Linv and alpha = K⁻¹err packed for the kernels. */
 int tb_gp_update_posterior_cache(tb_gp* gp);
+
+/* Append m (1..64) observations to the data AND extend the cached L, Linv and alpha in O(m N²) — the incremental form of
+ * update_encoded (models.py:171-186) followed by update_posterior_cache (interface.py:108-112), which in the reference
+ * refactorise from scratch every BO step.  Requires a valid cache and unchanged hyper-parameters;
+ * same error behaviour as tb_gp_update_posterior_cache (on failure the cache is left invalid).  Xnew [m,D], ynew [m]. */
+int tb_gp_append_data(tb_gp* gp, const void* Xnew, const void* ynew, int64_t m);
 
 /* copy out the cached Cholesky factor L [N,N] row-major lower (tests / diagnostics). */
 int tb_gp_get_cholesky(tb_gp* gp, void* L_out);

@@ -210,6 +210,21 @@ def expected_improvement(mean, var, eta):
     return (eta - mean) * cdf + var * np.exp(log_prob)
 
 
+def augmented_expected_improvement(mean, var, eta, noise):
+    """function.py:318-325: EI times the augmentation ``1 - sqrt(noise) / sqrt(noise + variance)``."""
+    return expected_improvement(mean, var, eta) * (1.0 - math.sqrt(noise) / np.sqrt(noise + var))
+
+
+def aei_gradient(m: GPRModel, Xq: np.ndarray, eta: float):
+    """Value and d AEI / d x* by the product rule on :func:`ei_gradient` and the augmentation factor."""
+    mean, var = predict(m, Xq)
+    _, dvar = posterior_gradients(m, Xq)
+    ei, gei = ei_gradient(m, Xq, eta)
+    aug = 1.0 - math.sqrt(m.noise) / np.sqrt(m.noise + var)
+    daug = np.where(var <= VAR_CLIP, 0.0, 0.5 * math.sqrt(m.noise) * (m.noise + var) ** -1.5)
+    return ei * aug, gei * aug + ei * daug * dvar
+
+
 def expected_improvement_at(m: GPRModel, Xq: np.ndarray, eta: float, chunk: int = 16384):
     mean, var = predict_batched(m, Xq, chunk)
     return expected_improvement(mean, var, eta)

@@ -265,3 +265,33 @@ def test_large_model_falls_back_to_fp64_engine():
     omean, ovar = o.predict(om, Xq)
     np.testing.assert_allclose(mean, omean, rtol=1e-8, atol=1e-8 * np.sqrt(om.variance))
     np.testing.assert_allclose(var, ovar, rtol=0, atol=1e-8 * om.variance)
+
+
+@pytest.mark.parametrize("engine", ["int8", "fp64"])
+@pytest.mark.parametrize("noise", [None, 1e-4, 0.5])
+def test_augmented_expected_improvement_matches_oracle(noise, engine):
+    # function.py:283-325; the builder's eta is the EI builder's (function.py:256-257)
+    import trieste_b200 as tb
+    from trieste_b200.acquisition import AugmentedExpectedImprovement, augmented_expected_improvement
+
+    om, nm = model_pair(o.hartmann_6, 300, 6, noise=noise, engine=engine)
+    Xq = candidates(2000, 6)
+    builder = AugmentedExpectedImprovement()
+    fn = builder.prepare_acquisition_function(nm, tb.Dataset(om.X, om.y))
+    assert isinstance(fn, augmented_expected_improvement)
+    eta = o.ei_eta(om)
+    np.testing.assert_allclose(fn.eta, eta, rtol=1e-9)
+    omean, ovar = o.predict(om, Xq)
+    ref = o.augmented_expected_improvement(omean, ovar, eta, om.noise)
+    got = fn(Xq[:, None, :])
+    np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-15)
+    idx, best = fn.fused_argmax(Xq)
+    assert idx == int(np.argmax(ref[:, 0])) or abs(best - ref.max()) <= 1e-6 * abs(ref.max())
+    assert builder.update_acquisition_function(fn, nm, tb.Dataset(om.X, om.y)) is fn
+    with pytest.raises(ValueError):
+        fn(candidates(6, 6).reshape(3, 2, 6))  # batch size must be one (function.py:313-316)
+    # gradient of the augmented tail
+    val, grad = fn.value_and_gradient(Xq[:200, None, :])
+    oval, ograd = o.aei_gradient(om, Xq[:200], eta)
+    np.testing.assert_allclose(val, oval, rtol=1e-6, atol=1e-15)
+    np.testing.assert_allclose(grad[:, 0, :], ograd, rtol=1e-6, atol=1e-9 * np.abs(ograd).max())

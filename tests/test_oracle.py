@@ -165,3 +165,26 @@ def test_decoupled_sampler_moments():
     mean, var = o.predict(om, Xq)
     np.testing.assert_allclose(f.mean(1), mean[:, 0], atol=0.15 * math.sqrt(om.variance))
     np.testing.assert_allclose(f.var(1), var[:, 0], rtol=0.5, atol=0.02 * om.variance)
+
+
+def test_augmented_ei_bounds_and_gradient():
+    # function.py:318-325: AEI = EI * (1 - tau / sqrt(tau^2 + s^2)) in (0, EI), -> EI as the noise vanishes
+    m = o.synthetic_model(o.hartmann_6, 40, 6)
+    Xq = np.random.default_rng(1).uniform(size=(30, 6))
+    mean, var = o.predict(m, Xq)
+    eta = o.ei_eta(m)
+    ei = o.expected_improvement(mean, var, eta)
+    aei = o.augmented_expected_improvement(mean, var, eta, m.noise)
+    assert np.all(aei < ei) and np.all(aei >= 0)
+    np.testing.assert_allclose(o.augmented_expected_improvement(mean, var, eta, 1e-30), ei, rtol=1e-12)
+    val, grad = o.aei_gradient(m, Xq, eta)
+    np.testing.assert_allclose(val, aei, rtol=1e-12)
+    h = 1e-6
+    for d in range(6):
+        e = np.zeros(6)
+        e[d] = h
+        fd = []
+        for sgn in (1, -1):
+            mu, v = o.predict(m, Xq + sgn * e)
+            fd.append(o.augmented_expected_improvement(mu, v, eta, m.noise))
+        np.testing.assert_allclose(grad[:, d], ((fd[0] - fd[1]) / (2 * h))[:, 0], rtol=1e-4, atol=1e-8 * np.abs(grad).max())

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libtrieste_b200.so")
 
 TB_F64, TB_F32 = 0, 1
 KERNEL_IDS = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3}
-ACQ_EI, ACQ_LOG_EI, ACQ_NEG_LCB, ACQ_LCB, ACQ_PBT = 0, 1, 2, 3, 4
+ACQ_EI, ACQ_LOG_EI, ACQ_NEG_LCB, ACQ_LCB, ACQ_PBT, ACQ_AEI = 0, 1, 2, 3, 4, 5
 
 _lib: Optional[C.CDLL] = None
 
@@ -32,6 +32,7 @@ SIGNATURES = {
     "tb_gp_set_data": (_i32, [_vp, _vp, _vp, _i64, _i32]),
     "tb_gp_set_hyper": (_i32, [_vp, _i32, _f64, C.POINTER(_f64), _i32, _f64, _f64]),
     "tb_gp_update_posterior_cache": (_i32, [_vp]),
+    "tb_gp_append_data": (_i32, [_vp, _vp, _vp, _i64]),
     "tb_gp_get_cholesky": (_i32, [_vp, _vp]),
     "tb_gp_predict": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "tb_gp_predict_joint": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),

@@ -1,4 +1,6 @@
 from .function import (  # noqa: F401
+    AugmentedExpectedImprovement,
+    augmented_expected_improvement,
     BatchMonteCarloExpectedImprovement,
     ExpectedImprovement,
     LogExpectedImprovement,

@@ -111,6 +111,14 @@ class log_expected_improvement(expected_improvement):
     _acq = _lib.ACQ_LOG_EI
 
 
+class augmented_expected_improvement(expected_improvement):
+    """function.py:283-325: EI times ``1 - sqrt(noise) / sqrt(noise + variance)`` (Huang et al. 2006); the noise
+    variance is the model's likelihood variance, read from the native handle on every call (the reference re-assigns it
+    in ``update``, :306-309)."""
+
+    _acq = _lib.ACQ_AEI
+
+
 class _lcb(_FusedSingleQuery):
     def __init__(self, model, beta: float, negate: bool):
         if beta < 0:
@@ -209,6 +217,18 @@ class ExpectedImprovement(SingleModelAcquisitionBuilder):
 
 class LogExpectedImprovement(ExpectedImprovement):
     _fn_class = log_expected_improvement
+
+
+class AugmentedExpectedImprovement(ExpectedImprovement):
+    """function.py:225-280: eta = min posterior mean at the data, as for EI."""
+
+    _fn_class = augmented_expected_improvement
+
+    def __init__(self):
+        super().__init__(None)
+
+    def __repr__(self) -> str:
+        return "AugmentedExpectedImprovement()"
 
 
 class NegativeLowerConfidenceBound(SingleModelAcquisitionBuilder):

@@ -307,15 +307,18 @@ __device__ __forceinline__ double ndtr_tfp(double x) {  // tfp special_math._ndt
   double y = (z < hs2) ? 1.0 + erf(w) : ((w > 0.0) ? 2.0 - erfc(z) : erfc(z));
   return 0.5 * y;
 }
-__device__ __forceinline__ double acq_value(int acq, double param, double mean, double var) {
+// aux: second parameter of the tail (the likelihood noise variance for AEI; unused otherwise)
+__device__ __forceinline__ double acq_value(int acq, double param, double aux, double mean, double var) {
   const double sigma = sqrt(var);
   if (acq == TB_ACQ_LCB) return mean - param * sigma;
   if (acq == TB_ACQ_NEG_LCB) return -(mean - param * sigma);
   const double z = (param - mean) / sigma;
   if (acq == TB_ACQ_PBT) return ndtr_tfp(z);
-  if (acq == TB_ACQ_EI) {
+  if (acq == TB_ACQ_EI || acq == TB_ACQ_AEI) {
     const double pdf_term = sigma * exp(-0.5 * z * z) * 0.3989422804014327;  // variance * N(eta; mean, sigma)
-    return (param - mean) * ndtr_tfp(z) + pdf_term;
+    const double ei = (param - mean) * ndtr_tfp(z) + pdf_term;
+    if (acq == TB_ACQ_EI) return ei;
+    return ei * (1.0 - sqrt(aux) / sqrt(aux + var));  // function.py:318-325
   }
   // log-EI: log(sigma) + log(phi(z) + z Phi(z))
   double lh;
@@ -335,7 +338,7 @@ __device__ __forceinline__ double acq_value(int acq, double param, double mean, 
 }
 
 // d acq / d mean and d acq / d var (for the gradient path); clipped variance has zero gradient
-__device__ __forceinline__ void acq_partials(int acq, double param, double mean, double var,
+__device__ __forceinline__ void acq_partials(int acq, double param, double aux, double mean, double var,
                                              bool clipped, double& dmu, double& dvar) {
   const double sigma = sqrt(var);
   if (acq == TB_ACQ_LCB || acq == TB_ACQ_NEG_LCB) {
@@ -355,6 +358,14 @@ __device__ __forceinline__ void acq_partials(int acq, double param, double mean,
   if (acq == TB_ACQ_EI) {
     dmu = -cdf;
     dvar = clipped ? 0.0 : pdf / (2.0 * sigma);
+    return;
+  }
+  if (acq == TB_ACQ_AEI) {
+    const double ei = (param - mean) * cdf + sigma * pdf;
+    const double tv = aux + var;
+    const double aug = 1.0 - sqrt(aux) / sqrt(tv);
+    dmu = -cdf * aug;
+    dvar = clipped ? 0.0 : pdf / (2.0 * sigma) * aug + ei * 0.5 * sqrt(aux) / (tv * sqrt(tv));
     return;
   }
   // log-EI: d/dmu = -Phi/(sigma h), d/dvar = phi/(2 sigma^2 h)... with h = phi + z Phi; use the
@@ -390,7 +401,7 @@ __device__ __forceinline__ void best_merge(double& v, int64_t& i, double v2, int
 // one thread per candidate of the chunk; block-level first-max argmax
 __global__ void __launch_bounds__(256)
 tail_kernel(const double* __restrict__ partial, int G, int64_t McPad, const double* __restrict__ mean,
-            int64_t Mc, int64_t idx0, double variance, int acq, double param,
+            int64_t Mc, int64_t idx0, double variance, int acq, double param, double aux,
             double* __restrict__ out_vals, double* __restrict__ out_mean, double* __restrict__ out_var,
             double* __restrict__ blk_best, int64_t* __restrict__ blk_idx) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -404,7 +415,7 @@ tail_kernel(const double* __restrict__ partial, int G, int64_t McPad, const doub
     if (out_mean) out_mean[t] = mu;
     if (out_var) out_var[t] = var;
     if (acq >= 0) {
-      double v = acq_value(acq, param, mu, var);
+      double v = acq_value(acq, param, aux, mu, var);
       if (out_vals) out_vals[t] = v;
       if (v == v) { bv = v; bi = idx0 + t; }
     }

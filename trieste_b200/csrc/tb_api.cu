@@ -42,6 +42,138 @@ __global__ void gram_kernel(const double* __restrict__ Xs, int64_t N, int DP, do
   K[i + j * N] = v;
 }
 
+// ---- rank-m append of training points to an existing cache (tb_gp_append_data) ----
+// W[:, j] (column-major [N, m]) = k(x_i, xnew_j) for every row i of the grown data set; the diagonal entry of the new
+// block carries the likelihood noise
+template <int KIND>
+__global__ void append_cross_kernel(const double* __restrict__ Xs, int DP, int64_t N0, int64_t N, double variance,
+                                    double noise, double* __restrict__ W) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i >= N) return;
+  double r2 = 0.0;
+  for (int d = 0; d < DP; ++d) {
+    const double df = Xs[i * DP + d] - Xs[(N0 + j) * DP + d];
+    r2 = fma(df, df, r2);
+  }
+  double v = kernel_from_r2<KIND>(r2, variance);
+  if (i == N0 + j) v = variance + noise;
+  W[i + j * N] = v;
+}
+
+// Y[:, j] = T[0:n, 0:n] X[:, j] for a column-major lower-triangular T with leading dimension ld (one thread per row:
+// coalesced along the rows of a column)
+__global__ void trmv_lower_cols_kernel(const double* __restrict__ T, int64_t n, int64_t ld, const double* __restrict__ X,
+                                       int64_t ldx, double* __restrict__ Y, int64_t ldy) {
+  __shared__ double xs[128];
+  const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  const int64_t kend = min(n, ((int64_t)blockIdx.x + 1) * 128);
+  double s = 0.0;
+  for (int64_t k0 = 0; k0 < kend; k0 += 128) {
+    __syncthreads();
+    xs[threadIdx.x] = (k0 + threadIdx.x < n) ? X[k0 + threadIdx.x + j * ldx] : 0.0;
+    __syncthreads();
+    if (r < n) {
+      const int64_t kk_end = min((int64_t)128, r - k0 + 1);
+      for (int64_t kk = 0; kk < kk_end; ++kk) s = fma(T[r + (k0 + kk) * ld], xs[kk], s);
+    }
+  }
+  if (r < n) Y[r + j * ldy] = s;
+}
+
+// U[:, j] = T[0:n, 0:n]^T X[:, j] (one warp per column of T)
+__global__ void trmv_lower_t_cols_kernel(const double* __restrict__ T, int64_t n, int64_t ld, const double* __restrict__ X,
+                                         int64_t ldx, double* __restrict__ U, int64_t ldu) {
+  const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int64_t j = blockIdx.y;
+  if (k >= n) return;
+  double s = 0.0;
+  for (int64_t r = k + lane; r < n; r += 32) s = fma(T[r + k * ld], X[r + j * ldx], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) U[k + j * ldu] = s;
+}
+
+// S[i + j*m] = C[i][j] - l_i . l_j (Schur complement of the new block; l_i = Y[:, i], C = W[N0:, :])
+__global__ void append_schur_kernel(const double* __restrict__ Y, const double* __restrict__ W, int64_t N0, int64_t N, int m,
+                                    double* __restrict__ S) {
+  __shared__ double red[8];
+  const int i = blockIdx.x, j = blockIdx.y;
+  double s = 0.0;
+  for (int64_t k = threadIdx.x; k < N0; k += blockDim.x) s = fma(Y[k + (int64_t)i * N], Y[k + (int64_t)j * N], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    S[i + j * m] = W[N0 + i + (int64_t)j * N] - t;
+  }
+}
+
+constexpr int APPEND_MAX = 64;  // larger appends refactorise from scratch
+
+// one CTA of APPEND_MAX threads: L22 = chol(S) in shared memory, R = L22^-1; writes both into the new corner of L / Linv
+// and R (row-major [m, m]) to Rout; info = failing leading minor (global index) if S is not positive definite
+__global__ void append_chol_kernel(const double* __restrict__ S, int m, int64_t N0, int64_t N, double* __restrict__ L,
+                                   double* __restrict__ Linv, double* __restrict__ Rout, int* __restrict__ info) {
+  __shared__ double A[APPEND_MAX][APPEND_MAX + 1];
+  __shared__ int bad;
+  const int t = threadIdx.x;
+  if (t == 0) bad = 0;
+  for (int j = 0; j < m; ++j)
+    if (t < m) A[t][j] = S[t + j * m];
+  __syncthreads();
+  for (int j = 0; j < m; ++j) {
+    if (t == j) {
+      const double d = A[j][j];
+      if (!(d > 0.0)) {
+        if (!bad) bad = (int)(N0 + j + 1);
+        A[j][j] = 1.0;
+      } else {
+        A[j][j] = sqrt(d);
+      }
+    }
+    __syncthreads();
+    if (t > j && t < m) A[t][j] /= A[j][j];
+    __syncthreads();
+    if (t > j && t < m)
+      for (int k = j + 1; k <= t; ++k) A[t][k] -= A[t][j] * A[k][j];
+    __syncthreads();
+  }
+  // column t of R: forward substitution of L22 r = e_t
+  if (t < m) {
+    for (int i = 0; i < m; ++i) {
+      double s = (i == t) ? 1.0 : 0.0;
+      for (int k = t; k < i; ++k) s -= A[i][k] * Rout[k * m + t];
+      Rout[i * m + t] = (i < t) ? 0.0 : s / A[i][i];  // column t is private to this thread
+    }
+  }
+  __syncthreads();
+  if (t == 0 && bad) *info = bad;
+  if (t < m)
+    for (int j = 0; j < m; ++j) {
+      L[(N0 + t) + (N0 + j) * N] = (j <= t) ? A[t][j] : 0.0;
+      Linv[(N0 + t) + (N0 + j) * N] = (j <= t) ? Rout[t * m + j] : 0.0;
+    }
+}
+
+// new rows left of the corner: L[N0+i, k] = Y[k, i] (Y = Linv0 B, so L21 = Y^T) and Linv[N0+i, k] = -(R U^T)[i, k] with
+// U = Linv0^T Y (Linv21 = -L22^-1 L21 Linv0)
+__global__ void append_rows_kernel(const double* __restrict__ Y, const double* __restrict__ U, const double* __restrict__ R,
+                                   int m, int64_t N0, int64_t N, double* __restrict__ L, double* __restrict__ Linv) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (k >= N0) return;
+  double b = 0.0;
+  for (int j = 0; j <= i; ++j) b = fma(R[i * m + j], U[k + (int64_t)j * N], b);
+  L[(N0 + i) + k * N] = Y[k + (int64_t)i * N];
+  Linv[(N0 + i) + k * N] = -b;
+}
+
 __global__ void identity_kernel(int64_t N, double* __restrict__ A) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * N) return;
@@ -230,6 +362,57 @@ int tb_gp_set_hyper(tb_gp* gp, int kernel, double variance, const double* length
   return 0;
 }
 
+static int scale_inputs(tb_gp* gp) {
+  const int D = gp->D, DP = gp->DP;
+  const int64_t rows = (int64_t)gp->NB * BM;
+  std::vector<double> inv_ls(DP, 0.0);
+  for (int d = 0; d < D; ++d) inv_ls[d] = 1.0 / gp->ls[d];
+  TB_TRY(gp->dInvLs.reserve(sizeof(double) * DP));
+  TB_CUDA(cudaMemcpyAsync(gp->dInvLs.p, inv_ls.data(), sizeof(double) * DP, cudaMemcpyHostToDevice, gp->stream));
+  TB_TRY(gp->dXs.reserve(sizeof(double) * rows * DP));
+  int64_t tot = rows * DP;
+  scale_inputs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, gp->stream>>>(gp->dX.as<double>(), gp->dInvLs.as<double>(), gp->N, D,
+                                                                            DP, rows, gp->dXs.as<double>());
+  TB_LAUNCHED();
+  return 0;
+}
+
+// alpha = Linv^T (Linv (y - m)) by two triangular mat-vecs on the current Linv
+static int alpha_from_linv(tb_gp* gp) {
+  const int64_t N = gp->N, rows = (int64_t)gp->NB * BM;
+  cudaStream_t st = gp->stream;
+  TB_TRY(gp->sMisc.reserve(sizeof(double) * 2 * rows));
+  double* err = gp->sMisc.as<double>();
+  double* tmp = err + rows;
+  residual_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(gp->dy.as<double>(), N, rows, gp->mean_const, err);
+  TB_LAUNCHED();
+  TB_CUDA(cudaMemsetAsync(gp->dAlpha.p, 0, sizeof(double) * rows, st));
+  fac::trmv_lower_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(gp->dLinv.as<double>(), N, err, tmp);
+  TB_LAUNCHED();
+  fac::trmv_lower_t_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(gp->dLinv.as<double>(), N, tmp, gp->dAlpha.as<double>());
+  TB_LAUNCHED();
+  return 0;
+}
+
+// pack the lower triangle of Linv into DMMA-fragment-ordered panels and mark the derived operand sets stale
+static int finish_cache(tb_gp* gp) {
+  const int64_t N = gp->N;
+  cudaStream_t st = gp->stream;
+  int64_t npanels = rowblock_panel_offset(gp->NB);
+  TB_TRY(gp->dLinvP.reserve(sizeof(double) * npanels * PANEL));
+  TB_CUDA(cudaMemsetAsync(gp->dLinvP.p, 0, sizeof(double) * npanels * PANEL, st));
+  dim3 grid((unsigned)std::min<int64_t>(gp->nkc, (int64_t)gp->NB * (BM / BK)), (unsigned)gp->NB);
+  pack_lower_panels_kernel<<<grid, 256, 0, st>>>(gp->dLinv.as<double>(), N, gp->nkc, gp->dLinvP.as<double>());
+  TB_LAUNCHED();
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
+  gp->cache_valid = true;
+  gp->upper_valid = false;
+  gp->oz_valid = false;
+  gp->kinv_valid = false;
+  return 0;
+}
+
 int tb_gp_update_posterior_cache(tb_gp* gp) {
   TB_CHECK(gp, "tb_gp_update_posterior_cache: null handle");
   TB_CHECK(gp->have_data && gp->have_hyper, "tb_gp_update_posterior_cache: set data and hyper-parameters first");
@@ -240,17 +423,7 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
   const int64_t rows = (int64_t)gp->NB * BM;  // >= nkc*16 and >= nst*64
   cudaStream_t st = gp->stream;
 
-  std::vector<double> inv_ls(DP, 0.0);
-  for (int d = 0; d < D; ++d) inv_ls[d] = 1.0 / gp->ls[d];
-  TB_TRY(gp->dInvLs.reserve(sizeof(double) * DP));
-  TB_CUDA(cudaMemcpyAsync(gp->dInvLs.p, inv_ls.data(), sizeof(double) * DP, cudaMemcpyHostToDevice, st));
-  TB_TRY(gp->dXs.reserve(sizeof(double) * rows * DP));
-  {
-    int64_t tot = rows * DP;
-    scale_inputs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
-        gp->dX.as<double>(), gp->dInvLs.as<double>(), N, D, DP, rows, gp->dXs.as<double>());
-    TB_LAUNCHED();
-  }
+  TB_TRY(scale_inputs(gp));
   TB_TRY(gp->dL.reserve(sizeof(double) * N * N));
   TB_TRY(gp->dLinv.reserve(sizeof(double) * N * N));
   {
@@ -314,17 +487,7 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
         TB_LAUNCHED();
       }
     }
-    // alpha = Linv^T (Linv err)
-    TB_TRY(gp->sMisc.reserve(sizeof(double) * 2 * rows));
-    double* err = gp->sMisc.as<double>();
-    double* tmp = err + rows;
-    residual_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(gp->dy.as<double>(), N, rows, gp->mean_const, err);
-    TB_LAUNCHED();
-    TB_CUDA(cudaMemsetAsync(gp->dAlpha.p, 0, sizeof(double) * rows, st));
-    fac::trmv_lower_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(gp->dLinv.as<double>(), N, err, tmp);
-    TB_LAUNCHED();
-    fac::trmv_lower_t_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(gp->dLinv.as<double>(), N, tmp, gp->dAlpha.as<double>());
-    TB_LAUNCHED();
+    TB_TRY(alpha_from_linv(gp));
   } else {
     // ---- library path (TB_FACTOR=cusolver): cuSOLVER potrf / potrs + cuBLAS trsm; kept as a cross-check ----
     int lwork = 0;
@@ -354,22 +517,90 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
     TB_CUBLAS(cublasDtrsm(gp->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)N,
                           (int)N, &one, gp->dL.as<double>(), (int)N, gp->dLinv.as<double>(), (int)N));
   }
-  // pack the lower triangle of Linv into DMMA-fragment-ordered panels
+  return finish_cache(gp);
+}
+
+// Rank-m append: the reference refactorises from scratch whenever the data change
+// (models.py:171-186 -> interface.py:108-112); one BO step only appends rows, so L, Linv and alpha are extended in
+// O(m N^2) instead of O(N^3).  The hyper-parameters must be unchanged since the cache was built.
+static int tb_gp_append_data_f64(tb_gp* gp, const double* Xnew, const double* ynew, int64_t m) {
+  TB_CHECK(gp && Xnew && ynew, "tb_gp_append_data: null argument");
+  TB_CHECK(gp->cache_valid, "tb_gp_append_data: posterior cache is not built: call tb_gp_update_posterior_cache first");
+  TB_CHECK(m > 0 && m <= APPEND_MAX, "tb_gp_append_data: between 1 and " + std::to_string(APPEND_MAX) + " new points per call");
+  const int64_t N0 = gp->N, N = N0 + m;
+  TB_CHECK(N <= 65536, "tb_gp_append_data: N > 65536 is not supported");
+  TB_CUDA(cudaSetDevice(gp->device));
+  cudaStream_t st = gp->stream;
+  const int D = gp->D, DP = gp->DP;
+  // grow the raw data and the two triangular factors (leading dimension N0 -> N)
+  tb::DevBuf nX, ny, nL, nLinv;
+  TB_TRY(nX.reserve(sizeof(double) * N * D));
+  TB_TRY(ny.reserve(sizeof(double) * N));
+  TB_TRY(nL.reserve(sizeof(double) * N * N));
+  TB_TRY(nLinv.reserve(sizeof(double) * N * N));
+  TB_CUDA(cudaMemcpyAsync(nX.p, gp->dX.p, sizeof(double) * N0 * D, cudaMemcpyDeviceToDevice, st));
+  TB_CUDA(cudaMemcpyAsync(nX.as<double>() + N0 * D, Xnew, sizeof(double) * m * D, cudaMemcpyDefault, st));
+  TB_CUDA(cudaMemcpyAsync(ny.p, gp->dy.p, sizeof(double) * N0, cudaMemcpyDeviceToDevice, st));
+  TB_CUDA(cudaMemcpyAsync(ny.as<double>() + N0, ynew, sizeof(double) * m, cudaMemcpyDefault, st));
+  TB_CUDA(cudaMemsetAsync(nL.p, 0, sizeof(double) * N * N, st));
+  TB_CUDA(cudaMemsetAsync(nLinv.p, 0, sizeof(double) * N * N, st));
+  TB_CUDA(cudaMemcpy2DAsync(nL.p, sizeof(double) * N, gp->dL.p, sizeof(double) * N0, sizeof(double) * N0, N0,
+                            cudaMemcpyDeviceToDevice, st));
+  TB_CUDA(cudaMemcpy2DAsync(nLinv.p, sizeof(double) * N, gp->dLinv.p, sizeof(double) * N0, sizeof(double) * N0, N0,
+                            cudaMemcpyDeviceToDevice, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  std::swap(gp->dX, nX);
+  std::swap(gp->dy, ny);
+  std::swap(gp->dL, nL);
+  std::swap(gp->dLinv, nLinv);
+  nX.release(); ny.release(); nL.release(); nLinv.release();
+  gp->N = N;
+  gp->nkc = (int)((N + BK - 1) / BK);
+  gp->NB = (int)((N + BM - 1) / BM);
+  gp->cache_valid = false;  // until the append completes
+  const int64_t rows = (int64_t)gp->NB * BM;
+  TB_TRY(scale_inputs(gp));
+  TB_TRY(gp->dAlpha.reserve(sizeof(double) * rows));
+  // scratch: W (cross kernel block), Y = Linv0 B, U = Linv0^T Y as [N, m] column-major; S, R as [m, m]
+  TB_TRY(gp->sA.reserve(sizeof(double) * (3 * N * m + 2 * m * m)));
+  double* W = gp->sA.as<double>();
+  double* Y = W + N * m;
+  double* U = Y + N * m;
+  double* S = U + N * m;
+  double* R = S + m * m;
+  TB_TRY(gp->dInfo.reserve(sizeof(int)));
+  TB_CUDA(cudaMemsetAsync(gp->dInfo.p, 0, sizeof(int), st));
   {
-    int64_t npanels = rowblock_panel_offset(gp->NB);
-    TB_TRY(gp->dLinvP.reserve(sizeof(double) * npanels * PANEL));
-    TB_CUDA(cudaMemsetAsync(gp->dLinvP.p, 0, sizeof(double) * npanels * PANEL, st));
-    dim3 grid((unsigned)std::min<int64_t>(gp->nkc, (int64_t)gp->NB * (BM / BK)), (unsigned)gp->NB);
-    pack_lower_panels_kernel<<<grid, 256, 0, st>>>(gp->dLinv.as<double>(), N, gp->nkc, gp->dLinvP.as<double>());
+    dim3 grid((unsigned)((N + 127) / 128), (unsigned)m);
+    const double* Xs = gp->dXs.as<double>();
+    switch (gp->kernel) {
+      case TB_RBF: append_cross_kernel<TB_RBF><<<grid, 128, 0, st>>>(Xs, DP, N0, N, gp->variance, gp->noise, W); break;
+      case TB_MATERN12: append_cross_kernel<TB_MATERN12><<<grid, 128, 0, st>>>(Xs, DP, N0, N, gp->variance, gp->noise, W); break;
+      case TB_MATERN32: append_cross_kernel<TB_MATERN32><<<grid, 128, 0, st>>>(Xs, DP, N0, N, gp->variance, gp->noise, W); break;
+      default: append_cross_kernel<TB_MATERN52><<<grid, 128, 0, st>>>(Xs, DP, N0, N, gp->variance, gp->noise, W); break;
+    }
     TB_LAUNCHED();
   }
+  double* L = gp->dL.as<double>();
+  double* Linv = gp->dLinv.as<double>();
+  trmv_lower_cols_kernel<<<dim3((unsigned)((N0 + 127) / 128), (unsigned)m), 128, 0, st>>>(Linv, N0, N, W, N, Y, N);
+  TB_LAUNCHED();
+  append_schur_kernel<<<dim3((unsigned)m, (unsigned)m), 256, 0, st>>>(Y, W, N0, N, (int)m, S);
+  TB_LAUNCHED();
+  append_chol_kernel<<<1, APPEND_MAX, 0, st>>>(S, (int)m, N0, N, L, Linv, R, gp->dInfo.as<int>());
+  TB_LAUNCHED();
+  trmv_lower_t_cols_kernel<<<dim3((unsigned)((N0 + 7) / 8), (unsigned)m), 256, 0, st>>>(Linv, N0, N, Y, N, U, N);
+  TB_LAUNCHED();
+  append_rows_kernel<<<dim3((unsigned)((N0 + 127) / 128), (unsigned)m), 128, 0, st>>>(Y, U, R, (int)m, N0, N, L, Linv);
+  TB_LAUNCHED();
+  int info = 0;
+  TB_CUDA(cudaMemcpyAsync(&info, gp->dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
   TB_CUDA(cudaGetLastError());
-  gp->cache_valid = true;
-  gp->upper_valid = false;
-  gp->oz_valid = false;
-  gp->kinv_valid = false;
-  return 0;
+  TB_CHECK(info == 0, "tb_gp_append_data: Cholesky decomposition was not successful "
+                      "(K + noise*I not positive definite at leading minor " + std::to_string(info) + ")");
+  TB_TRY(alpha_from_linv(gp));
+  return finish_cache(gp);
 }
 
 static int tb_gp_get_cholesky_f64(tb_gp* gp, void* L_out) {
@@ -526,7 +757,7 @@ static int gradient_chunk(tb_gp* gp, int acq, double param, const double* xc, in
   double* cmu = gp->sMisc.as<double>();
   acq_partials_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, st>>>(gp->sPartial.as<double>(), G, McPad,
                                                                     gp->sMean.as<double>(), mc, gp->variance, acq,
-                                                                    param, cmu, cmu + mc);
+                                                                    param, gp->noise, cmu, cmu + mc);
   TB_LAUNCHED();
   const int nkB = gp->NB * (BM / BK);
   trigemm_kernel<true, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
@@ -621,7 +852,7 @@ static int gradient_chunk_oz(tb_gp* gp, int acq, double param, const double* xc,
   cudaStream_t st = gp->stream;
   double* cmu = gp->sMisc.as<double>();
   acq_partials_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, st>>>(gp->sPartial.as<double>(), G, McPad, gp->sMean.as<double>(), mc,
-                                                                    gp->variance, acq, param, cmu, cmu + mc);
+                                                                    gp->variance, acq, param, gp->noise, cmu, cmu + mc);
   TB_LAUNCHED();
   const int Gv = std::max(1, std::min(gp->NB, std::max((gp->NB + 7) / 8, (2 * 148 + tiles - 1) / tiles)));
   oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Gv, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
@@ -828,7 +1059,7 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
     double* d_var = rq.out_var ? (var_dev ? rq.out_var + c0 : gp->sVar.as<double>()) : nullptr;
     const int tb_blocks = (int)((mc + 255) / 256);
     tail_kernel<<<tb_blocks, 256, 0, sa>>>(part[slot]->as<double>(), G, McPad, mean[slot]->as<double>(), mc, c0, gp->variance,
-                                           rq.acq, rq.param, d_vals, d_mean, d_var,
+                                           rq.acq, rq.param, gp->noise, d_vals, d_mean, d_var,
                                            rq.want_argmax ? gp->sBlkBest.as<double>() : nullptr,
                                            rq.want_argmax ? gp->sBlkIdx.as<int64_t>() : nullptr);
     TB_LAUNCHED();
@@ -984,7 +1215,7 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
     double* d_var = rq.out_var ? (var_dev ? rq.out_var + c0 : gp->sVar.as<double>()) : nullptr;
     const int tb_blocks = (int)((mc + 255) / 256);
     tail_kernel<<<tb_blocks, 256, 0, st>>>(gp->sPartial.as<double>(), G, McPad, gp->sMean.as<double>(), mc, c0,
-                                           gp->variance, rq.acq, rq.param, d_vals, d_mean, d_var,
+                                           gp->variance, rq.acq, rq.param, gp->noise, d_vals, d_mean, d_var,
                                            rq.want_argmax ? gp->sBlkBest.as<double>() : nullptr,
                                            rq.want_argmax ? gp->sBlkIdx.as<int64_t>() : nullptr);
     TB_LAUNCHED();
@@ -1042,7 +1273,7 @@ static int tb_gp_predict_f64(tb_gp* gp, const void* Xc, int64_t M, void* mean, v
 
 static int tb_acq_eval_f64(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* grad) {
   TB_CHECK(gp && (M == 0 || (Xc && out)), "tb_acq_eval: null argument");
-  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_PBT, "tb_acq_eval: unknown acquisition kind");
+  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_AEI, "tb_acq_eval: unknown acquisition kind");
   if (acq == TB_ACQ_LCB || acq == TB_ACQ_NEG_LCB)
     TB_CHECK(param >= 0.0, "Standard deviation scaling parameter beta must not be negative");
   tb::EvalRequest rq;
@@ -1058,7 +1289,7 @@ static int tb_acq_eval_f64(tb_gp* gp, int acq, double param, const void* Xc, int
 static int tb_acq_argmax_f64(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* best_value,
                   int64_t* best_index) {
   TB_CHECK(gp && Xc && best_value && best_index, "tb_acq_argmax: null argument");
-  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_PBT, "tb_acq_argmax: unknown acquisition kind");
+  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_AEI, "tb_acq_argmax: unknown acquisition kind");
   if (acq == TB_ACQ_LCB || acq == TB_ACQ_NEG_LCB)
     TB_CHECK(param >= 0.0, "Standard deviation scaling parameter beta must not be negative");
   tb::EvalRequest rq;
@@ -1736,6 +1967,18 @@ int tb_gp_set_data(tb_gp* gp, const void* X, const void* y, int64_t N, int D) {
   TB_TRY(br.in(X, N * D, &Xd));
   TB_TRY(br.in(y, N, &yd));
   return tb_gp_set_data_f64(gp, Xd, yd, N, D);
+}
+
+int tb_gp_append_data(tb_gp* gp, const void* Xnew, const void* ynew, int64_t m) {
+  TB_CHECK(gp && Xnew && ynew, "tb_gp_append_data: null argument");
+  if (gp->dtype == TB_F64) return tb_gp_append_data_f64(gp, (const double*)Xnew, (const double*)ynew, m);
+  TB_CHECK(m > 0 && gp->have_data, "tb_gp_append_data: set the data first and append at least one point");
+  TB_CUDA(cudaSetDevice(gp->device));
+  tb::F32Bridge br(gp);
+  const double *Xd, *yd;
+  TB_TRY(br.in(Xnew, m * gp->D, &Xd));
+  TB_TRY(br.in(ynew, m, &yd));
+  return tb_gp_append_data_f64(gp, Xd, yd, m);
 }
 
 int tb_gp_get_cholesky(tb_gp* gp, void* L_out) {

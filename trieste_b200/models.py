@@ -136,11 +136,13 @@ class GaussianProcessRegression:
         if X.shape[0] == 0:
             raise ValueError("Dataset must be populated.")
         y = np.ascontiguousarray(Y[:, 0])
+        self._cache_current = False
         _lib.check(_lib.lib().tb_gp_set_data(self._h, X.ctypes.data, y.ctypes.data, X.shape[0], X.shape[1]))
 
     def _push_hyper(self) -> None:
         k = self._spec.kernel
         ls = np.ascontiguousarray(k.lengthscales, dtype=np.float64)
+        self._cache_current = False
         _lib.check(
             _lib.lib().tb_gp_set_hyper(
                 self._h,
@@ -167,7 +169,9 @@ class GaussianProcessRegression:
 
     def update_posterior_cache(self) -> None:
         """interface.py:108-112 — must follow any change of data or hyper-parameters."""
+        self._cache_current = False
         _lib.check(_lib.lib().tb_gp_update_posterior_cache(self._h))
+        self._cache_current = True
 
     # ---- ProbabilisticModel ------------------------------------------------------------------
     def predict(self, query_points) -> Tuple[np.ndarray, np.ndarray]:
@@ -217,13 +221,33 @@ class GaussianProcessRegression:
         """TensorBoard summaries in the reference (models/utils.py:33-107): observability only."""
 
     # ---- TrainableProbabilisticModel -----------------------------------------------------------
+    APPEND_MAX = 64  # tb_gp_append_data handles up to this many new rows per call
+
     def update(self, dataset: Dataset) -> None:
-        """models.py:171-186: swap the data, refresh the posterior cache."""
+        """models.py:171-186: swap the data, refresh the posterior cache.  When the new data set is the old one plus a
+        few appended rows (the BO loop's case, bayesian_optimizer.py:786-800) the cached factors are extended in
+        O(m N^2) by ``tb_gp_append_data`` instead of being rebuilt in O(N^3)."""
         X = np.ascontiguousarray(np.asarray(dataset.query_points, dtype=self._dtype))
         Y = np.ascontiguousarray(np.asarray(dataset.observations, dtype=self._dtype))
         if X.ndim != 2 or X.shape[-1] != self._spec.X.shape[-1]:
             raise ValueError(f"new query points must be [N, {self._spec.X.shape[-1]}], got {X.shape}")
+        n0 = self._spec.X.shape[0]
+        m = X.shape[0] - n0
+        appended = (
+            getattr(self, "_cache_current", False) and 0 < m <= self.APPEND_MAX and Y.shape[0] == X.shape[0]
+            and np.array_equal(X[:n0], self._spec.X) and np.array_equal(Y[:n0], self._spec.Y)
+        )
         self._spec.X, self._spec.Y = X, Y
+        self.last_update_appended = bool(appended)
+        if appended:
+            xn = np.ascontiguousarray(X[n0:])
+            yn = np.ascontiguousarray(Y[n0:].reshape(-1))
+            try:
+                _lib.check(_lib.lib().tb_gp_append_data(self._h, xn.ctypes.data, yn.ctypes.data, m))
+                return
+            except Exception:
+                self._cache_current = False
+                raise
         self._push_data()
         self.update_posterior_cache()
 
