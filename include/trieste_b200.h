@@ -43,8 +43,10 @@ enum tb_acq {
   TB_ACQ_LCB = 3,     /* lower_confidence_bound, function.py:389-418 */
   TB_ACQ_PBT = 4,     /* probability_below_threshold.__call__, function.py:501-509 (ProbabilityOfImprovement :47-93,
                          ProbabilityOfFeasibility :421-478): Normal(mean, sqrt(var)).cdf(param) */
-  TB_ACQ_AEI = 5      /* augmented_expected_improvement.__call__, function.py:311-325: EI(param = eta) times
+  TB_ACQ_AEI = 5,     /* augmented_expected_improvement.__call__, function.py:311-325: EI(param = eta) times
                          1 − sqrt(noise)/sqrt(noise + var), noise = the handle's likelihood variance */
+  TB_ACQ_MES = 6      /* min_value_entropy_search.__call__, entropy.py:193-213: mean over the min-value samples set by
+                         tb_acq_set_min_value_samples of −γ·φ(γ)/(2Φ(−γ)) − log Φ(−γ), γ = (y* − mean)/sd; param unused */
 };
 
 /* ---- errors / build info ------------------------------------------------------------------ */
@@ -98,6 +100,11 @@ int tb_acq_eval(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, voi
  * best_index (host).  out may be NULL (values are then never written to HBM). */
 int tb_acq_argmax(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out,
                   void* best_value, int64_t* best_index);
+
+/* min_value_entropy_search.update / __init__ (entropy.py:166-191): the samples of the objective minimum y* are a
+ * tf.Variable assigned in place; here they are a device array owned by the handle.  samples [S] (the reference holds them
+ * as [S,1]), always double, S ≥ 1.  Required before any TB_ACQ_MES evaluation. */
+int tb_acq_set_min_value_samples(tb_gp* gp, const double* samples, int S);
 
 /* batch_monte_carlo_expected_improvement.__call__ (function.py:1181-1186) on top of
  * BatchReparametrizationSampler.sample (models/gpflow/sampler.py:208-287):

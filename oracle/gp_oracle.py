@@ -225,6 +225,47 @@ def aei_gradient(m: GPRModel, Xq: np.ndarray, eta: float):
     return ei * aug, gei * aug + ei * daug * dvar
 
 
+MES_CLAMP_LB = 1e-8  # entropy.py:47
+
+
+def min_value_entropy_search(mean, var, samples):
+    """entropy.py:193-213.  mean, var [M,1]; samples [S,1] -> [M,1]:
+    gamma = (y* - mean) / clip(sd, 1e-8); mean_S( -gamma * exp(logpdf(gamma) - logcdf(-gamma)) / 2 - logcdf(-gamma) )."""
+    from scipy.special import log_ndtr
+
+    sd = np.maximum(np.sqrt(var), MES_CLAMP_LB)
+    gamma = (np.asarray(samples).reshape(1, -1) - mean) / sd  # [M, S]
+    log_minus_cdf = log_ndtr(-gamma)
+    log_prob = -0.5 * gamma * gamma - 0.5 * math.log(2.0 * math.pi)
+    ratio = np.exp(log_prob - log_minus_cdf)
+    return (-gamma * ratio / 2.0 - log_minus_cdf).mean(axis=1, keepdims=True)
+
+
+def gumbel_fit(fmean, fsd):
+    """acquisition/sampler.py:186-204: Gumbel (a, b) matching the quartiles of Pr(y* < y) = 1 - prod Phi(-(y - mu)/sd),
+    found by bisection on [min(mu - 5 sd), max(mu + 5 sd)]."""
+    from scipy.optimize import bisect
+    from scipy.special import log_ndtr
+
+    fmean = np.asarray(fmean, dtype=np.float64).reshape(-1)
+    fsd = np.asarray(fsd, dtype=np.float64).reshape(-1)
+
+    def probf(y):
+        return 1.0 - math.exp(float(np.sum(log_ndtr(-(y - fmean) / fsd))))
+
+    left, right = float(np.min(fmean - 5 * fsd)), float(np.max(fmean + 5 * fsd))
+    q1 = bisect(lambda y: probf(y) - 0.25, left, right, maxiter=10000)
+    q2 = bisect(lambda y: probf(y) - 0.75, left, right, maxiter=10000)
+    l1, l2 = math.log(math.log(4.0 / 3.0)), math.log(math.log(4.0))
+    return (q2 * l1 - q1 * l2) / (l1 - l2), (q1 - q2) / (l1 - l2)
+
+
+def gumbel_samples(a, b, uniform):
+    """acquisition/sampler.py:206-211: inverse probability integral transform of uniform draws -> [S, 1]."""
+    u = np.asarray(uniform, dtype=np.float64)
+    return (np.log(-np.log(1.0 - u)) * b + a)[:, None]
+
+
 def expected_improvement_at(m: GPRModel, Xq: np.ndarray, eta: float, chunk: int = 16384):
     mean, var = predict_batched(m, Xq, chunk)
     return expected_improvement(mean, var, eta)

@@ -124,3 +124,34 @@ def test_predict_joint_max_batch_size_and_argument_checks():
         nm.predict_joint(candidates(6, 6)[0])  # rank < 2
     m0, c0 = nm.predict_joint(np.zeros((0, 4, 6)))
     assert m0.shape == (0, 4, 1) and c0.shape == (0, 1, 4, 4)
+
+
+def test_monte_carlo_expected_improvement_single_point():
+    # function.py:782-920 (reference test: MC-EI close to EI, test_function.py:651-672)
+    from trieste_b200 import Dataset
+    from trieste_b200.acquisition import ExpectedImprovement, MonteCarloExpectedImprovement, monte_carlo_expected_improvement
+
+    om, nm = model_pair(o.branin, 20, 2)
+    ds = Dataset(om.X, om.y)
+    S = 20000
+    builder = MonteCarloExpectedImprovement(S)
+    fn = builder.prepare_acquisition_function(nm, ds)
+    assert isinstance(fn, monte_carlo_expected_improvement)
+    eps = fn._sampler._get_eps(1).copy()  # [1, S], fixed until reset
+    # eta = min over the data of the sample mean (function.py:838-846), reproduced from the oracle's joint q = 1 samples
+    m1, c1 = o.predict_joint(om, om.X[:, None, :])
+    samples = o.batch_reparam_sample(m1, c1, eps[None], 1e-6)  # [N, S, 1, 1]
+    eta_ref = samples.mean(axis=-3).min()
+    np.testing.assert_allclose(fn._eta, eta_ref, rtol=1e-8)
+    X = candidates(300, 2)
+    ref = o.batch_monte_carlo_expected_improvement(om, X[:, None, :], eps[None], fn._eta, 1e-6)
+    np.testing.assert_allclose(fn(X[:, None, :]), ref, rtol=1e-6, atol=1e-12)
+    ei = ExpectedImprovement().prepare_acquisition_function(nm, ds)(X[:, None, :])
+    big = ei[:, 0] > 0.2 * ei.max()
+    np.testing.assert_allclose(fn(X[:, None, :])[big], ei[big], rtol=0.1)
+    with pytest.raises(ValueError):
+        fn(candidates(8, 2).reshape(2, 2, 2))  # batch size one only (function.py:911-914)
+    assert builder.update_acquisition_function(fn, nm, ds) is fn
+    assert not np.array_equal(fn._sampler._get_eps(1), eps)  # update resets the sampler (function.py:866)
+    with pytest.raises(ValueError):
+        MonteCarloExpectedImprovement(0)

@@ -243,3 +243,22 @@ def test_sharded_argmax_gloo_world2():
         assert tidx == list(np.argmin(tv, axis=0))
         np.testing.assert_allclose(tvals, tv.min(0))
         assert ms_i == int(np.argmax(ms)) and ms_v == ms.max()
+
+
+def test_gumbel_fit_and_sampler_argument_checks():
+    # acquisition/sampler.py:140-152,186-204 (host logic only: no model call)
+    from oracle import gp_oracle as o
+    from trieste_b200.acquisition.sampler import GumbelSampler, ThompsonSampler, ThompsonSamplerFromTrajectory
+
+    rng = np.random.default_rng(0)
+    mu, sd = rng.normal(size=40), rng.uniform(0.1, 2.0, size=40)
+    np.testing.assert_allclose(GumbelSampler.fit(mu, sd), o.gumbel_fit(mu, sd), rtol=1e-12)
+    with pytest.raises(ValueError):
+        GumbelSampler()  # can only sample the minimum value
+    assert ThompsonSamplerFromTrajectory().sample_min_value is False
+    assert ThompsonSamplerFromTrajectory(True).sample_min_value is True
+    assert "True" in repr(ThompsonSampler(True))
+    with pytest.raises(ValueError):
+        ThompsonSamplerFromTrajectory().sample(object(), 1, np.zeros((3, 2)))  # no trajectory_sampler
+    with pytest.raises(ValueError):
+        ThompsonSamplerFromTrajectory().sample(object(), 1, np.zeros(3))  # at must be [N, D]

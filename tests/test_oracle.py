@@ -188,3 +188,36 @@ def test_augmented_ei_bounds_and_gradient():
             mu, v = o.predict(m, Xq + sgn * e)
             fd.append(o.augmented_expected_improvement(mu, v, eta, m.noise))
         np.testing.assert_allclose(grad[:, d], ((fd[0] - fd[1]) / (2 * h))[:, 0], rtol=1e-4, atol=1e-8 * np.abs(grad).max())
+
+
+def test_min_value_entropy_search_restatement():
+    # entropy.py:193-213 against the closed form for gamma >> 0 / gamma << 0 and direct quadrature-free identities
+    from scipy.stats import norm
+
+    mean = np.array([[0.0], [1.0], [-2.0]])
+    var = np.array([[1.0], [0.25], [4.0]])
+    samples = np.array([[-1.5], [-0.3], [-4.0]])
+    got = o.min_value_entropy_search(mean, var, samples)
+    gam = (samples.reshape(1, -1) - mean) / np.sqrt(var)
+    ref = (-gam * norm.pdf(gam) / (2 * norm.cdf(-gam)) - np.log(norm.cdf(-gam))).mean(1, keepdims=True)
+    np.testing.assert_allclose(got, ref, rtol=1e-12)
+    assert np.all(got >= 0)  # information gain
+    # far tail: finite where the naive form underflows (cdf(-40) == 0)
+    far = o.min_value_entropy_search(np.array([[0.0]]), np.array([[1.0]]), np.array([[40.0]]))
+    assert np.isfinite(far).all() and far[0, 0] > 0
+    # entropy.py:47,201-204: sd clipped from below
+    tiny = o.min_value_entropy_search(np.array([[0.0]]), np.array([[1e-30]]), np.array([[-1e-9]]))
+    np.testing.assert_allclose(tiny, o.min_value_entropy_search(np.array([[0.0]]), np.array([[1e-16]]), np.array([[-1e-9]])))
+
+
+def test_gumbel_sampler_restatement_matches_empirical_minimum_quartiles():
+    # acquisition/sampler.py:186-204: the fitted Gumbel reproduces the quartiles of the min over independent normals
+    rng = np.random.default_rng(0)
+    mu = rng.normal(size=50)
+    sd = rng.uniform(0.2, 1.0, size=50)
+    a, b = o.gumbel_fit(mu, sd)
+    draws = (mu + sd * rng.standard_normal((200_000, 50))).min(axis=1)
+    q1, q2 = np.quantile(draws, [0.25, 0.75])
+    g = o.gumbel_samples(a, b, np.array([0.25, 0.75]))[:, 0]
+    np.testing.assert_allclose(g, [q1, q2], atol=0.01)
+    assert b > 0

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libtrieste_b200.so")
 
 TB_F64, TB_F32 = 0, 1
 KERNEL_IDS = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3}
-ACQ_EI, ACQ_LOG_EI, ACQ_NEG_LCB, ACQ_LCB, ACQ_PBT, ACQ_AEI = 0, 1, 2, 3, 4, 5
+ACQ_EI, ACQ_LOG_EI, ACQ_NEG_LCB, ACQ_LCB, ACQ_PBT, ACQ_AEI, ACQ_MES = 0, 1, 2, 3, 4, 5, 6
 
 _lib: Optional[C.CDLL] = None
 
@@ -38,6 +38,7 @@ SIGNATURES = {
     "tb_gp_predict_joint": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "tb_acq_eval": (_i32, [_vp, _i32, _f64, _vp, _i64, _vp, _vp]),
     "tb_acq_argmax": (_i32, [_vp, _i32, _f64, _vp, _i64, _vp, _vp, C.POINTER(_i64)]),
+    "tb_acq_set_min_value_samples": (_i32, [_vp, C.POINTER(_f64), _i32]),
     "tb_acq_batch_mc_ei": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _f64, _f64, _vp]),
     "tb_gp_reparam_sample": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp]),
     "tb_topk": (_i32, [_i32, _i32, _vp, _i64, _i32, _vp, C.POINTER(_i64)]),

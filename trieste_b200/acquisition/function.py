@@ -45,7 +45,11 @@ class _FusedSingleQuery(AcquisitionFunctionClass):
         self._model = _require_native(model)
         self._param = float(param)
 
+    def _before_call(self) -> None:
+        """state that lives in the native handle and must be current before a launch (none by default)"""
+
     def _squeeze(self, x):
+        self._before_call()
         x, _ = _lib.as_contiguous(x, self._model.dtype)
         if x.ndim < 2 or x.shape[-2] != 1:
             raise ValueError(
@@ -74,6 +78,7 @@ class _FusedSingleQuery(AcquisitionFunctionClass):
     def fused_argmax(self, points):
         """points [M, D] -> (first-max index, value) without writing the M values to HBM
         (generate_random_search_optimizer / _get_max_discrete_points, optimizer.py:124-150)."""
+        self._before_call()
         pts, _ = _lib.as_contiguous(points, self._model.dtype)
         if pts.ndim != 2:
             raise ValueError(f"points must be [M, D], got {tuple(pts.shape)}")
@@ -117,6 +122,37 @@ class augmented_expected_improvement(expected_improvement):
     in ``update``, :306-309)."""
 
     _acq = _lib.ACQ_AEI
+
+
+class min_value_entropy_search(_FusedSingleQuery):
+    """entropy.py:166-213: information gain about the objective minimum y* from evaluating at x, averaged over samples
+    of y* (Wang & Jegelka 2017, adapted for minimisation).  The samples are pushed to the native handle before every
+    launch (two functions may share one model)."""
+
+    _acq = _lib.ACQ_MES
+
+    def __init__(self, model, samples):
+        super().__init__(model, 0.0)
+        self.update(samples)
+
+    def update(self, samples) -> None:
+        s = np.asarray(samples, dtype=np.float64)
+        if s.ndim != 2:
+            raise ValueError(f"samples must have rank two, got shape {s.shape}")
+        if s.shape[0] == 0:
+            raise ValueError("samples must not be empty")
+        self._samples = np.ascontiguousarray(s.reshape(-1))
+
+    @property
+    def samples(self) -> np.ndarray:
+        return self._samples[:, None]
+
+    def _before_call(self) -> None:
+        _lib.check(
+            _lib.lib().tb_acq_set_min_value_samples(
+                self._model.handle, self._samples.ctypes.data_as(C.POINTER(C.c_double)), int(self._samples.size)
+            )
+        )
 
 
 class _lcb(_FusedSingleQuery):
@@ -219,6 +255,54 @@ class LogExpectedImprovement(ExpectedImprovement):
     _fn_class = log_expected_improvement
 
 
+class MinValueEntropySearch(SingleModelAcquisitionBuilder):
+    """entropy.py:52-164.  The min-value samples come from ``min_value_sampler`` evaluated on the data plus
+    ``grid_size`` random points of the search space (:134-137).  The reference's default sampler is
+    ``ExactThompsonSampler`` — joint samples over all N + grid_size points, an (N + grid)^3 Cholesky outside this
+    engine's q <= 32 joint path; the default here is the :class:`GumbelSampler` the reference also offers (and the one
+    Wang & Jegelka recommend), or any sampler with ``sample_min_value=True`` (e.g. ``ThompsonSamplerFromTrajectory``)."""
+
+    def __init__(self, search_space, num_samples: int = 5, grid_size: int = 1000, min_value_sampler=None, seed=None):
+        if num_samples <= 0:
+            raise ValueError(f"num_samples must be positive, got {num_samples}")
+        if grid_size <= 0:
+            raise ValueError(f"grid_size must be positive, got {grid_size}")
+        if min_value_sampler is not None:
+            if not min_value_sampler.sample_min_value:
+                raise ValueError(
+                    "Minvalue Entropy Search requires a min_value_sampler that samples minimum values, "
+                    "however the passed sampler has sample_min_value=False."
+                )
+        else:
+            from .sampler import GumbelSampler
+
+            min_value_sampler = GumbelSampler(sample_min_value=True, seed=seed)
+        self._min_value_sampler = min_value_sampler
+        self._search_space = search_space
+        self._num_samples = num_samples
+        self._grid_size = grid_size
+
+    def __repr__(self) -> str:
+        return (f"MinValueEntropySearch({self._search_space!r}, {self._num_samples!r}, {self._grid_size!r}, "
+                f"{self._min_value_sampler!r})")
+
+    def _draw(self, model, dataset: Dataset) -> np.ndarray:
+        grid = np.asarray(self._search_space.sample(self._grid_size))
+        query_points = np.concatenate([np.asarray(dataset.query_points, dtype=grid.dtype), grid], axis=0)
+        return self._min_value_sampler.sample(model, self._num_samples, query_points)
+
+    def prepare_acquisition_function(self, model, dataset: Optional[Dataset] = None):
+        dataset = _check_populated(dataset)
+        return min_value_entropy_search(model, self._draw(model, dataset))
+
+    def update_acquisition_function(self, function, model, dataset: Optional[Dataset] = None):
+        dataset = _check_populated(dataset)
+        if not isinstance(function, min_value_entropy_search):
+            raise ValueError(f"expected a min_value_entropy_search function, got {function!r}")
+        function.update(self._draw(model, dataset))
+        return function
+
+
 class AugmentedExpectedImprovement(ExpectedImprovement):
     """function.py:225-280: eta = min posterior mean at the data, as for EI."""
 
@@ -284,6 +368,58 @@ class batch_monte_carlo_expected_improvement(AcquisitionFunctionClass):
             )
         )
         return out.reshape(lead + (1,))
+
+
+class monte_carlo_expected_improvement(batch_monte_carlo_expected_improvement):
+    """function.py:883-920: ``mean_S max(eta - f_s(x), 0)`` over reparametrised samples, batch size one.  For a GPR the
+    reference's ``model.reparam_sampler`` is the batch sampler (models.py:325-331), so this is the q = 1 case of the
+    batch kernel chain."""
+
+    def __call__(self, x):
+        x_arr = x if hasattr(x, "shape") else np.asarray(x)
+        if len(x_arr.shape) < 2 or x_arr.shape[-2] != 1:
+            raise ValueError(
+                f"This acquisition function only supports batch sizes of one; got input of shape {tuple(x_arr.shape)}"
+            )
+        return super().__call__(x)
+
+
+class MonteCarloExpectedImprovement(SingleModelAcquisitionBuilder):
+    """function.py:782-880: eta = min over the data of the sample mean at each training input."""
+
+    def __init__(self, sample_size: int, *, jitter: float = JITTER):
+        if sample_size <= 0:
+            raise ValueError(f"sample_size must be positive, got {sample_size}")
+        if jitter < 0:
+            raise ValueError(f"jitter must be non-negative, got {jitter}")
+        self._sample_size = sample_size
+        self._jitter = jitter
+
+    def __repr__(self) -> str:
+        return f"MonteCarloExpectedImprovement({self._sample_size!r}, jitter={self._jitter!r})"
+
+    def _eta(self, sampler, dataset: Dataset):
+        x = np.asarray(dataset.query_points)
+        samples = sampler.sample(x[..., None, :], jitter=self._jitter)  # [N, S, 1, 1]
+        return np.min(np.mean(samples, axis=-3), axis=0)
+
+    def prepare_acquisition_function(self, model, dataset: Optional[Dataset] = None):
+        if not hasattr(model, "reparam_sampler"):
+            raise ValueError(
+                f"MonteCarloExpectedImprovement only supports models with a reparam_sampler method; received {model!r}"
+            )
+        dataset = _check_populated(dataset)
+        fn = monte_carlo_expected_improvement(self._sample_size, model, 0.0, self._jitter)
+        fn._eta = float(np.asarray(self._eta(fn._sampler, dataset)).reshape(-1)[0])
+        return fn
+
+    def update_acquisition_function(self, function, model, dataset: Optional[Dataset] = None):
+        dataset = _check_populated(dataset)
+        if not isinstance(function, monte_carlo_expected_improvement):
+            raise ValueError(f"expected a monte_carlo_expected_improvement, got {function!r}")
+        function._sampler.reset_sampler()
+        function._eta = float(np.asarray(self._eta(function._sampler, dataset)).reshape(-1)[0])
+        return function
 
 
 class BatchMonteCarloExpectedImprovement(SingleModelAcquisitionBuilder):

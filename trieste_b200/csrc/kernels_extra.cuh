@@ -209,7 +209,8 @@ grad_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha, con
 // per-candidate partial derivatives of the acquisition w.r.t. (mean, var) from the tail inputs
 __global__ void __launch_bounds__(256)
 acq_partials_kernel(const double* __restrict__ partial, int G, int64_t McPad, const double* __restrict__ mean,
-                    int64_t Mc, double variance, int acq, double param, double aux, double* __restrict__ cmu,
+                    int64_t Mc, double variance, int acq, double param, double aux, const double* __restrict__ samp, int nsamp,
+                    double* __restrict__ cmu,
                     double* __restrict__ cvar) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= Mc) return;
@@ -218,7 +219,8 @@ acq_partials_kernel(const double* __restrict__ partial, int G, int64_t McPad, co
   const double raw = variance - ss;
   const bool clipped = raw < 1e-12;
   double dm, dv;
-  acq_partials(acq, param, aux, mean[t], fmax(raw, 1e-12), clipped, dm, dv);
+  if (acq == TB_ACQ_MES) mes_partials(samp, nsamp, mean[t], fmax(raw, 1e-12), clipped, dm, dv);
+  else acq_partials(acq, param, aux, mean[t], fmax(raw, 1e-12), clipped, dm, dv);
   cmu[t] = dm;
   cvar[t] = dv;
 }

@@ -398,11 +398,56 @@ __device__ __forceinline__ void best_merge(double& v, int64_t& i, double v2, int
   }
 }
 
+// ---- min-value entropy search (entropy.py:193-213): mean over the S min-value samples of
+//   -gamma r / 2 - log Phi(-gamma),  gamma = (y*_s - mean) / sd,  r = phi(gamma) / Phi(-gamma)
+// log Phi(x) and r are evaluated through erfcx for x < -1 (no cancellation, no underflow)
+__device__ __forceinline__ void mes_terms(double gamma, double& log_cdf_neg, double& ratio) {
+  const double x = -gamma;
+  if (x > -1.0) {
+    const double c = ndtr_tfp(x);
+    log_cdf_neg = (x > 8.0) ? -ndtr_tfp(-x) : log(c);
+    ratio = exp(-0.5 * x * x) * 0.3989422804014327 / c;
+  } else {
+    const double e = 0.5 * erfcx(-x * 0.7071067811865476);  // Phi(x) = e * exp(-x^2/2)
+    log_cdf_neg = log(e) - 0.5 * x * x;
+    ratio = 0.3989422804014327 / e;
+  }
+}
+constexpr double MES_CLAMP_LB = 1e-8;  // entropy.py:47
+__device__ __forceinline__ double mes_value(const double* __restrict__ samp, int ns, double mean, double var) {
+  const double sd = fmax(sqrt(var), MES_CLAMP_LB);
+  double acc = 0.0;
+  for (int s = 0; s < ns; ++s) {
+    const double gamma = (samp[s] - mean) / sd;
+    double lc, r;
+    mes_terms(gamma, lc, r);
+    acc += -0.5 * gamma * r - lc;
+  }
+  return acc / (double)ns;
+}
+// d/dmean and d/dvar of the above: df/dgamma = r/2 - gamma r (r - gamma) / 2, dgamma/dmean = -1/sd,
+// dgamma/dvar = -gamma / (2 var)
+__device__ __forceinline__ void mes_partials(const double* __restrict__ samp, int ns, double mean, double var, bool clipped,
+                                             double& dmu, double& dvar) {
+  const double sd = fmax(sqrt(var), MES_CLAMP_LB);
+  double am = 0.0, av = 0.0;
+  for (int s = 0; s < ns; ++s) {
+    const double gamma = (samp[s] - mean) / sd;
+    double lc, r;
+    mes_terms(gamma, lc, r);
+    const double dg = 0.5 * r - 0.5 * gamma * r * (r - gamma);
+    am += dg;
+    av += dg * gamma;
+  }
+  dmu = -am / (sd * (double)ns);
+  dvar = clipped ? 0.0 : -av / (2.0 * var * (double)ns);
+}
+
 // one thread per candidate of the chunk; block-level first-max argmax
 __global__ void __launch_bounds__(256)
 tail_kernel(const double* __restrict__ partial, int G, int64_t McPad, const double* __restrict__ mean,
             int64_t Mc, int64_t idx0, double variance, int acq, double param, double aux,
-            double* __restrict__ out_vals, double* __restrict__ out_mean, double* __restrict__ out_var,
+            const double* __restrict__ samp, int nsamp, double* __restrict__ out_vals, double* __restrict__ out_mean, double* __restrict__ out_var,
             double* __restrict__ blk_best, int64_t* __restrict__ blk_idx) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double bv = -DBL_MAX;
@@ -415,7 +460,7 @@ tail_kernel(const double* __restrict__ partial, int G, int64_t McPad, const doub
     if (out_mean) out_mean[t] = mu;
     if (out_var) out_var[t] = var;
     if (acq >= 0) {
-      double v = acq_value(acq, param, aux, mu, var);
+      double v = (acq == TB_ACQ_MES) ? mes_value(samp, nsamp, mu, var) : acq_value(acq, param, aux, mu, var);
       if (out_vals) out_vals[t] = v;
       if (v == v) { bv = v; bi = idx0 + t; }
     }

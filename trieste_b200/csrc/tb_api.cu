@@ -297,7 +297,7 @@ int tb_gp_destroy(tb_gp* gp) {
   for (tb::DevBuf* b : {&gp->dX, &gp->dy, &gp->dXs, &gp->dInvLs, &gp->dAlpha, &gp->dL, &gp->dLinv,
                         &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->dXn2, &gp->dKinv, &gp->dKinvS, &gp->dKinvScale, &gp->dDinv, &gp->sKs2, &gp->sMean2, &gp->sPartial2, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
                         &gp->sVals, &gp->sVar, &gp->sXc, &gp->sBlkBest, &gp->sBlkIdx, &gp->sRun,
-                        &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc})
+                        &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc, &gp->dMes})
     b->release();
   for (auto& ev : gp->prof_events) {
     cudaEventDestroy(ev.first);
@@ -757,7 +757,7 @@ static int gradient_chunk(tb_gp* gp, int acq, double param, const double* xc, in
   double* cmu = gp->sMisc.as<double>();
   acq_partials_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, st>>>(gp->sPartial.as<double>(), G, McPad,
                                                                     gp->sMean.as<double>(), mc, gp->variance, acq,
-                                                                    param, gp->noise, cmu, cmu + mc);
+                                                                    param, gp->noise, gp->dMes.as<double>(), gp->mesS, cmu, cmu + mc);
   TB_LAUNCHED();
   const int nkB = gp->NB * (BM / BK);
   trigemm_kernel<true, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
@@ -852,7 +852,7 @@ static int gradient_chunk_oz(tb_gp* gp, int acq, double param, const double* xc,
   cudaStream_t st = gp->stream;
   double* cmu = gp->sMisc.as<double>();
   acq_partials_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, st>>>(gp->sPartial.as<double>(), G, McPad, gp->sMean.as<double>(), mc,
-                                                                    gp->variance, acq, param, gp->noise, cmu, cmu + mc);
+                                                                    gp->variance, acq, param, gp->noise, gp->dMes.as<double>(), gp->mesS, cmu, cmu + mc);
   TB_LAUNCHED();
   const int Gv = std::max(1, std::min(gp->NB, std::max((gp->NB + 7) / 8, (2 * 148 + tiles - 1) / tiles)));
   oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Gv, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
@@ -1059,7 +1059,7 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
     double* d_var = rq.out_var ? (var_dev ? rq.out_var + c0 : gp->sVar.as<double>()) : nullptr;
     const int tb_blocks = (int)((mc + 255) / 256);
     tail_kernel<<<tb_blocks, 256, 0, sa>>>(part[slot]->as<double>(), G, McPad, mean[slot]->as<double>(), mc, c0, gp->variance,
-                                           rq.acq, rq.param, gp->noise, d_vals, d_mean, d_var,
+                                           rq.acq, rq.param, gp->noise, gp->dMes.as<double>(), gp->mesS, d_vals, d_mean, d_var,
                                            rq.want_argmax ? gp->sBlkBest.as<double>() : nullptr,
                                            rq.want_argmax ? gp->sBlkIdx.as<int64_t>() : nullptr);
     TB_LAUNCHED();
@@ -1215,7 +1215,7 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
     double* d_var = rq.out_var ? (var_dev ? rq.out_var + c0 : gp->sVar.as<double>()) : nullptr;
     const int tb_blocks = (int)((mc + 255) / 256);
     tail_kernel<<<tb_blocks, 256, 0, st>>>(gp->sPartial.as<double>(), G, McPad, gp->sMean.as<double>(), mc, c0,
-                                           gp->variance, rq.acq, rq.param, gp->noise, d_vals, d_mean, d_var,
+                                           gp->variance, rq.acq, rq.param, gp->noise, gp->dMes.as<double>(), gp->mesS, d_vals, d_mean, d_var,
                                            rq.want_argmax ? gp->sBlkBest.as<double>() : nullptr,
                                            rq.want_argmax ? gp->sBlkIdx.as<int64_t>() : nullptr);
     TB_LAUNCHED();
@@ -1273,9 +1273,10 @@ static int tb_gp_predict_f64(tb_gp* gp, const void* Xc, int64_t M, void* mean, v
 
 static int tb_acq_eval_f64(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* grad) {
   TB_CHECK(gp && (M == 0 || (Xc && out)), "tb_acq_eval: null argument");
-  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_AEI, "tb_acq_eval: unknown acquisition kind");
+  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_MES, "tb_acq_eval: unknown acquisition kind");
   if (acq == TB_ACQ_LCB || acq == TB_ACQ_NEG_LCB)
     TB_CHECK(param >= 0.0, "Standard deviation scaling parameter beta must not be negative");
+  if (acq == TB_ACQ_MES) TB_CHECK(gp->mesS > 0, "min-value entropy search: set the min-value samples first (tb_acq_set_min_value_samples)");
   tb::EvalRequest rq;
   rq.acq = acq;
   rq.param = param;
@@ -1289,9 +1290,10 @@ static int tb_acq_eval_f64(tb_gp* gp, int acq, double param, const void* Xc, int
 static int tb_acq_argmax_f64(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, void* out, void* best_value,
                   int64_t* best_index) {
   TB_CHECK(gp && Xc && best_value && best_index, "tb_acq_argmax: null argument");
-  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_AEI, "tb_acq_argmax: unknown acquisition kind");
+  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_MES, "tb_acq_argmax: unknown acquisition kind");
   if (acq == TB_ACQ_LCB || acq == TB_ACQ_NEG_LCB)
     TB_CHECK(param >= 0.0, "Standard deviation scaling parameter beta must not be negative");
+  if (acq == TB_ACQ_MES) TB_CHECK(gp->mesS > 0, "min-value entropy search: set the min-value samples first (tb_acq_set_min_value_samples)");
   tb::EvalRequest rq;
   rq.acq = acq;
   rq.param = param;
@@ -1302,6 +1304,17 @@ static int tb_acq_argmax_f64(tb_gp* gp, int acq, double param, const void* Xc, i
   TB_TRY(tb::run_eval(gp, rq));
   *(double*)best_value = rq.best_value;
   *best_index = rq.best_index;
+  return 0;
+}
+
+int tb_acq_set_min_value_samples(tb_gp* gp, const double* samples, int S) {
+  TB_CHECK(gp && samples, "tb_acq_set_min_value_samples: null argument");
+  TB_CHECK(S > 0, "tb_acq_set_min_value_samples: need at least one sample");
+  TB_CUDA(cudaSetDevice(gp->device));
+  TB_TRY(gp->dMes.reserve(sizeof(double) * (size_t)S));
+  TB_CUDA(cudaMemcpyAsync(gp->dMes.p, samples, sizeof(double) * (size_t)S, cudaMemcpyDefault, gp->stream));
+  TB_CUDA(cudaStreamSynchronize(gp->stream));
+  gp->mesS = S;
   return 0;
 }
 
