@@ -81,15 +81,10 @@ struct tb_gp {
   bool upper_valid = false;
   // int8 (Ozaki) engine: digit tiles of Linv, per-row scales, K* scale
   int engine = 1;  // 0 = fp64 DMMA, 1 = int8 tensor cores (default; same stated tolerances, ~3x faster)
-  tb::DevBuf dAS, dRowScale, dXn2;
+  tb::DevBuf dAS, dRowScale;
   tb::DevBuf dKinv, dKinvS, dKinvScale;  // gradient path of the int8 engine: digit tiles of K^-1 (full rows)
   bool kinv_valid = false;
-  int oz_epi_warps = 8;    // epilogue warps of the int8 GEMM (4 leaves register room for co-resident K* CTAs)
-  bool kstar_mma = false;  // distances of the K* digit kernel on the DMMA pipe (expansion form)
   tb::DevBuf sKs2, sMean2, sPartial2;  // second scratch slot of the pipelined driver
-  // dynamic smem requested by the K* digit CTAs only to bound how many of them share an SM with a GEMM CTA (2 by default)
-  size_t kstar_smem = 0;
-  int kstar_threads = 512;
   cudaStream_t stream2 = nullptr;      // K* digit generation stream (overlaps the digit GEMM)
   cudaEvent_t evK[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr};
   bool oz_valid = false;

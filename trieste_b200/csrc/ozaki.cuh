@@ -291,85 +291,6 @@ kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ al
   if (ch == 0) mean_out[(int64_t)tile_id * 128 + t_local] = macc + mean_const;
 }
 
-// ------------------------------------------------------------------------------------------------
-// K* digit tiles, distances on the DMMA pipe.  Same output as kstar_digits_kernel, but the D-dimensional dot
-// products x~* . x~_k of a warp's 8 candidates x 64 training points run as 8 x ceil(D/4) m8n8k4 DMMAs per stage
-// (GPflow's own expansion r^2 = |a|^2 + |b|^2 - 2 a.b), instead of 2 D scalar fp64 ops per pair.  The training
-// point fed into column c of n-tile j is k = 16 (c >> 1) + 2 j + (c & 1), so that lane (cand = l / 4, m = l % 4)
-// receives exactly the 16 consecutive k of its 16-byte digit row.
-// ------------------------------------------------------------------------------------------------
-template <int KIND, int DP4>
-__global__ void __launch_bounds__(512, 2)
-kstar_digits_mma_kernel(const double* __restrict__ Xs, int DP, const double* __restrict__ xn2, const double* __restrict__ alpha,
-                        const double* __restrict__ Xc, const double* __restrict__ inv_ls, int N, int nst, int D, int64_t M,
-                        double variance, double inv_bscale_2p48, double mean_const, int8_t* __restrict__ BS,
-                        double* __restrict__ mean_out) {
-  const int lane = threadIdx.x & 31;
-  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), w = wg & 15, tile_id = wg >> 4;
-  const int cl = lane >> 2, m = lane & 3;
-  const int t_local = w * 8 + cl;
-  const int64_t t = (int64_t)tile_id * 128 + t_local;
-  const bool valid = t < M;
-  double afr[DP4];
-  double cn2 = 0.0;
-#pragma unroll
-  for (int s = 0; s < DP4; ++s) {
-    const int d = 4 * s + m;
-    afr[s] = (valid && d < D) ? Xc[t * D + d] * inv_ls[d] : 0.0;
-    cn2 = fma(afr[s], afr[s], cn2);
-  }
-  cn2 += __shfl_xor_sync(0xffffffffu, cn2, 1);
-  cn2 += __shfl_xor_sync(0xffffffffu, cn2, 2);
-  int8_t* tile = BS + (int64_t)tile_id * nst * (S * TILE) + w * SBO + m * LBO + cl * 16;
-  // B-fragment source row of this lane for n-tile j: k = kc*64 + 16 (cl >> 1) + 2 j + (cl & 1)
-  const int kb = 16 * (cl >> 1) + (cl & 1);
-  double macc = 0.0;
-  for (int kc = 0; kc < nst; ++kc) {
-    const int k0 = kc * KST + 16 * m;  // this lane's 16 output columns: k0 .. k0+15
-    uint32_t pk[S][4];
-#pragma unroll
-    for (int p = 0; p < S; ++p) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      double c0 = 0.0, c1 = 0.0;
-      const double* xr = Xs + (int64_t)(kc * KST + kb + 2 * j) * DP;
-#pragma unroll
-      for (int s = 0; s < DP4; ++s) {
-        const int d = 4 * s + m;
-        const double bfr = d < DP ? __ldg(xr + d) : 0.0;
-        dmma_m8n8k4(c0, c1, afr[s], bfr);
-      }
-      const double2 xn = __ldg(reinterpret_cast<const double2*>(xn2 + k0 + 2 * j));
-      const double2 al = __ldg(reinterpret_cast<const double2*>(alpha + k0 + 2 * j));
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int k = k0 + 2 * j + e;
-        const double r2 = fmax(fma(-2.0, e ? c1 : c0, cn2 + (e ? xn.y : xn.x)), 0.0);
-        const double kval = (valid && k < N) ? kernel_from_r2<KIND>(r2, variance) : 0.0;
-        macc = fma(kval, e ? al.y : al.x, macc);
-        uint32_t wl, wh;
-        digit_bytes6(__double2ll_rn(kval * inv_bscale_2p48), wl, wh);
-        scatter_digits_rt(pk, 2 * j + e, wl, wh);
-      }
-    }
-#pragma unroll
-    for (int p = 0; p < S; ++p)
-      *reinterpret_cast<uint4*>(tile + (int64_t)kc * (S * TILE) + p * TILE) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
-  }
-  macc += __shfl_xor_sync(0xffffffffu, macc, 1);
-  macc += __shfl_xor_sync(0xffffffffu, macc, 2);
-  if (m == 0) mean_out[(int64_t)tile_id * 128 + t_local] = macc + mean_const;
-}
-
-// |x~_k|^2 of the scaled training inputs (zero rows beyond N)
-__global__ void rownorm2_kernel(const double* __restrict__ Xs, int DP, int64_t rows, double* __restrict__ xn2) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= rows) return;
-  double s = 0.0;
-  for (int d = 0; d < DP; ++d) s = fma(Xs[k * DP + d], Xs[k * DP + d], s);
-  xn2[k] = s;
-}
-
 // all MMAs of one pipeline stage, fully unrolled at compile time: per MMA two 32-bit adds on precomputed descriptors
 // (the issuing thread shares its scheduler with co-resident K*-generation warps, so its instruction count matters)
 __device__ __forceinline__ void umma_i8_desc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t acc) {
@@ -409,7 +330,7 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t stage_base, 
 // ------------------------------------------------------------------------------------------------
 // OZ_SUMSQ: partial column sums of A^2 (variance path).  OZ_STORE: A itself, fp64, candidate-major [t][lda] (joint path)
 enum { OZ_SUMSQ = 0, OZ_STORE = 1 };
-// EW = number of epilogue warps (8: 64 columns each; 4: 128 columns each, which leaves registers for co-resident K* CTAs)
+// EW = number of epilogue warps (8: 64 accumulator columns each; 4 = 128 columns each was measured slower and is not instantiated)
 template <int EPI, int EW>
 __device__ __forceinline__ void trigemm_i8_body(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS,
                                                 const double* __restrict__ rowscale, int NB, int nst, int G, int64_t McPad,
@@ -646,7 +567,7 @@ __device__ __forceinline__ void trigemm_i8_body(const int8_t* __restrict__ AS, c
 }
 
 template <int EPI, int EW>
-__global__ void __launch_bounds__((EW + 2) * 32, EW == 4 ? 2 : 1)  // EW == 4: cap registers at 168
+__global__ void __launch_bounds__((EW + 2) * 32, 1)
 trigemm_i8_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, const double* __restrict__ rowscale, int NB,
                   int nst, int G, int64_t McPad, double out_scale, int npass, int full_rows, double* __restrict__ partial,
                   double* __restrict__ Aplain, int64_t lda) {

@@ -267,13 +267,6 @@ int tb_gp_create(tb_gp** out, int device, int dtype) {
   gp->dtype = dtype;
   if (const char* e = std::getenv("TB_FACTOR")) gp->factor_own = std::string(e) != "cusolver";
   if (const char* e = std::getenv("TB_ENGINE")) gp->engine = (std::string(e) == "fp64") ? 0 : 1;
-  if (const char* e = std::getenv("TB_OZ_EW")) gp->oz_epi_warps = std::atoi(e) == 4 ? 4 : 8;
-  if (const char* e = std::getenv("TB_KSTAR_MMA")) gp->kstar_mma = std::atoi(e) != 0;
-  if (const char* e = std::getenv("TB_KSTAR_SMEM")) gp->kstar_smem = (size_t)std::atol(e);
-  if (const char* e = std::getenv("TB_KSTAR_THREADS")) {
-    int t = std::atoi(e);
-    if (t == 128 || t == 256 || t == 512) gp->kstar_threads = t;
-  }
   {
     // main stream at the highest priority: when the K*-generation stream (lowest) runs concurrently, GEMM CTAs are placed
     // first and the generation CTAs only fill the register / thread slots a GEMM CTA leaves free
@@ -295,7 +288,7 @@ int tb_gp_destroy(tb_gp* gp) {
   cudaSetDevice(gp->device);
   cudaStreamSynchronize(gp->stream);
   for (tb::DevBuf* b : {&gp->dX, &gp->dy, &gp->dXs, &gp->dInvLs, &gp->dAlpha, &gp->dL, &gp->dLinv,
-                        &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->dXn2, &gp->dKinv, &gp->dKinvS, &gp->dKinvScale, &gp->dDinv, &gp->sKs2, &gp->sMean2, &gp->sPartial2, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
+                        &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->dKinv, &gp->dKinvS, &gp->dKinvScale, &gp->dDinv, &gp->sKs2, &gp->sMean2, &gp->sPartial2, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
                         &gp->sVals, &gp->sVar, &gp->sXc, &gp->sBlkBest, &gp->sBlkIdx, &gp->sRun,
                         &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc, &gp->dMes})
     b->release();
@@ -698,7 +691,6 @@ int kernels_init() {
   TB_CUDA(cudaFuncSetAttribute(fac::kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_lowreg_kernel<oz::OZ_SUMSQ, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
-  TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_STORE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
@@ -791,8 +783,6 @@ static int ensure_ozaki(tb_gp* gp) {
   TB_TRY(gp->dRowScale.reserve(sizeof(double) * rows));
   oz::linv_rowscale_kernel<<<(unsigned)rows, 256, 0, st>>>(gp->dLinv.as<double>(), gp->N, rows, gp->dRowScale.as<double>());
   TB_LAUNCHED();
-  TB_TRY(gp->dXn2.reserve(sizeof(double) * rows));
-  oz::rownorm2_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(gp->dXs.as<double>(), gp->DP, rows, gp->dXn2.as<double>());
   TB_LAUNCHED();
   const int64_t nstages = oz::a_stage_offset(gp->NB);
   TB_TRY(gp->dAS.reserve((size_t)nstages * oz::S * oz::TILE));
@@ -881,37 +871,8 @@ static int launch_kstar_digits(tb_gp* gp, const double* Xc_dev, int64_t mc, int 
   const double var = gp->variance, mc0 = gp->mean_const;
   const double inv_b = std::ldexp(1.0, 48 - gp->oz_bscale_exp);
   cudaStream_t st = gp->stream;
-  if (gp->kstar_mma) {
-    const int dp4 = (D + 3) / 4;
-    const double* xn2 = gp->dXn2.as<double>();
-#define TB_KM(KIND, Q)                                                                                                      \
-  oz::kstar_digits_mma_kernel<KIND, Q><<<tiles * (512 / gp->kstar_threads), gp->kstar_threads, gp->kstar_smem, st>>>(        \
-      Xs, gp->DP, xn2, al, Xc_dev, il, N, nst, D, mc, var, inv_b, mc0, BS, mean)
-#define TB_KM_Q(KIND)              \
-  switch (dp4) {                   \
-    case 1: TB_KM(KIND, 1); break; \
-    case 2: TB_KM(KIND, 2); break; \
-    case 3: TB_KM(KIND, 3); break; \
-    case 4: TB_KM(KIND, 4); break; \
-    case 5: TB_KM(KIND, 5); break; \
-    case 6: TB_KM(KIND, 6); break; \
-    case 7: TB_KM(KIND, 7); break; \
-    default: TB_KM(KIND, 8); break; \
-  }
-    switch (gp->kernel) {
-      case TB_RBF: TB_KM_Q(TB_RBF); break;
-      case TB_MATERN12: TB_KM_Q(TB_MATERN12); break;
-      case TB_MATERN32: TB_KM_Q(TB_MATERN32); break;
-      default: TB_KM_Q(TB_MATERN52); break;
-    }
-#undef TB_KM_Q
-#undef TB_KM
-    TB_LAUNCHED();
-    TB_CUDA(cudaGetLastError());
-    return 0;
-  }
 #define TB_KD(KIND, DPV) \
-  oz::kstar_digits_kernel<KIND, DPV><<<tiles * (512 / gp->kstar_threads), gp->kstar_threads, gp->kstar_smem, st>>>(Xs, al, Xc_dev, il, N, nst, D, mc, var, inv_b, mc0, BS, mean)
+  oz::kstar_digits_kernel<KIND, DPV><<<tiles, 512, 0, st>>>(Xs, al, Xc_dev, il, N, nst, D, mc, var, inv_b, mc0, BS, mean)
 #define TB_KD_DP(KIND)                                   \
   switch (gp->DP) {                                      \
     case 2: TB_KD(KIND, 2); break;                       \
@@ -1037,10 +998,6 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
     }
     if (sb != sa)  // overlapped K* generation: register-capped GEMM so that generation CTAs fit beside it
       oz::trigemm_i8_lowreg_kernel<oz::OZ_SUMSQ, 8><<<dim3(G, tiles), 10 * 32, oz::SMEM_BYTES, sa>>>(
-          gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
-          oz_npass(gp), 0, part[slot]->as<double>(), nullptr, 0);
-    else if (gp->oz_epi_warps == 4)
-      oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 4><<<dim3(G, tiles), 6 * 32, oz::SMEM_BYTES, sa>>>(
           gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
           oz_npass(gp), 0, part[slot]->as<double>(), nullptr, 0);
     else
