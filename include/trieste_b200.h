@@ -106,6 +106,17 @@ int tb_acq_argmax(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, v
  * as [S,1]), always double, S ≥ 1.  Required before any TB_ACQ_MES evaluation. */
 int tb_acq_set_min_value_samples(tb_gp* gp, const double* samples, int S);
 
+/* _perform_parallel_continuous_optimization (acquisition/optimizer.py:566-697) with one ScipyOptimizerGreenlet per start
+ * (:700-745, L-BFGS-B): here P independent projected L-BFGS runs advance together ON THE DEVICE — one batched fused
+ * value+gradient evaluation of all active trial points per round, then one warp per run updates its curvature history,
+ * line search and convergence tests (SciPy's option names: maxcor ≤ 16, maxiter, maxls, gtol on the projected gradient,
+ * ftol on the relative decrease).  Maximises the acquisition `acq` inside the box.  lower, upper [D]; starts [P,D];
+ * x_out [P,D], f_out [P] (maximised values), success [P] (1 = converged), nfev [P].  All arrays double / as declared
+ * (the reference's SciPy side is fp64 whatever the model dtype, optimizer.py:635-639), host or device pointers. */
+int tb_acq_maximize(tb_gp* gp, int acq, double param, const double* lower, const double* upper, const double* starts,
+                    int64_t P, int maxcor, int maxiter, int maxls, double gtol, double ftol, double* x_out, double* f_out,
+                    int32_t* success, int64_t* nfev);
+
 /* batch_monte_carlo_expected_improvement.__call__ (function.py:1181-1186) on top of
  * BatchReparametrizationSampler.sample (models/gpflow/sampler.py:208-287):
  * Xc [B,q,D], eps [q,S] (the sampler's fixed base samples, injected) → out [B]. */

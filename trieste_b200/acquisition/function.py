@@ -28,6 +28,10 @@ def _check_populated(dataset: Optional[Dataset]) -> Dataset:
     return dataset
 
 
+def _to_host(x) -> np.ndarray:
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
+
+
 def _require_native(model) -> GaussianProcessRegression:
     if not isinstance(model, GaussianProcessRegression):
         raise ValueError(
@@ -74,6 +78,33 @@ class _FusedSingleQuery(AcquisitionFunctionClass):
         grad, pg = _lib.empty_like_kind(flat, (M, D), self._model.dtype)
         _lib.check(_lib.lib().tb_acq_eval(self._model.handle, self._acq, self._param, _ptr(flat), M, po, pg))
         return out.reshape(lead + (1,)), grad.reshape(lead + (1, D))
+
+    def maximize_from(self, starts, lower, upper, *, maxcor: int = 10, maxiter: int = 15000, maxls: int = 20,
+                      gtol: float = 1e-5, ftol: float = 2.220446049250313e-09):
+        """Device-side multi-start projected L-BFGS (``tb_acq_maximize``): every row of ``starts`` [P, D] is an
+        independent local maximisation inside the box — the work of ``_perform_parallel_continuous_optimization`` and its
+        SciPy greenlets (optimizer.py:566-745) without leaving the GPU between iterations.
+        Returns (success [P] bool, values [P], x [P, D], nfev [P]); fp64 like the reference's SciPy side."""
+        self._before_call()
+        x0 = np.ascontiguousarray(_to_host(starts), dtype=np.float64)
+        if x0.ndim != 2:
+            raise ValueError(f"starts must be [P, D], got {x0.shape}")
+        self._model._check_dim(x0)
+        P, D = x0.shape
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lower, dtype=np.float64), (D,)))
+        up = np.ascontiguousarray(np.broadcast_to(np.asarray(upper, dtype=np.float64), (D,)))
+        x = np.empty((P, D))
+        f = np.empty(P)
+        ok = np.zeros(P, dtype=np.int32)
+        nfev = np.zeros(P, dtype=np.int64)
+        _lib.check(
+            _lib.lib().tb_acq_maximize(
+                self._model.handle, self._acq, self._param, lo.ctypes.data, up.ctypes.data, x0.ctypes.data, P,
+                int(maxcor), int(maxiter), int(maxls), float(gtol), float(ftol),
+                x.ctypes.data, f.ctypes.data, ok.ctypes.data, nfev.ctypes.data,
+            )
+        )
+        return ok.astype(bool), f, x, nfev
 
     def fused_argmax(self, points):
         """points [M, D] -> (first-max index, value) without writing the M values to HBM

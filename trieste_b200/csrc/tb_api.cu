@@ -4,6 +4,7 @@
 #include "kernels_extra.cuh"
 #include "ozaki.cuh"
 #include "factor.cuh"
+#include "lbfgs.cuh"
 
 using namespace tb;
 namespace tb {
@@ -2006,6 +2007,110 @@ int tb_acq_argmax(tb_gp* gp, int acq, double param, const void* Xc, int64_t M, v
   TB_TRY(tb_acq_argmax_f64(gp, acq, param, xd, M, od, &best, best_index));
   *(float*)best_value = (float)best;
   return br.finish();
+}
+
+// ---- device-side multi-start L-BFGS (acquisition/optimizer.py:566-745) ----
+__global__ void lbfgs_finish_kernel(tb::lb::State s, int64_t P, double* __restrict__ f_out, int32_t* __restrict__ success,
+                                    int64_t* __restrict__ nfev) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  f_out[p] = -s.f[p];
+  success[p] = s.status[p] == tb::lb::ST_SUCCESS ? 1 : 0;
+  nfev[p] = (int64_t)s.nfev[p];
+}
+
+int tb_acq_maximize(tb_gp* gp, int acq, double param, const double* lower, const double* upper, const double* starts, int64_t P,
+                    int maxcor, int maxiter, int maxls, double gtol, double ftol, double* x_out, double* f_out,
+                    int32_t* success, int64_t* nfev) {
+  TB_CHECK(gp && lower && upper, "tb_acq_maximize: null argument");
+  TB_CHECK(P >= 0 && P < ((int64_t)1 << 31), "tb_acq_maximize: number of starts out of range");
+  TB_CHECK(P == 0 || (starts && x_out && f_out && success && nfev), "tb_acq_maximize: null argument");
+  TB_CHECK(acq >= TB_ACQ_EI && acq <= TB_ACQ_MES, "tb_acq_maximize: unknown acquisition kind");
+  if (acq == TB_ACQ_LCB || acq == TB_ACQ_NEG_LCB)
+    TB_CHECK(param >= 0.0, "Standard deviation scaling parameter beta must not be negative");
+  if (acq == TB_ACQ_MES) TB_CHECK(gp->mesS > 0, "min-value entropy search: set the min-value samples first (tb_acq_set_min_value_samples)");
+  TB_CHECK(maxcor >= 1 && maxcor <= tb::lb::MMAX, "tb_acq_maximize: maxcor must be in [1, " + std::to_string(tb::lb::MMAX) + "]");
+  TB_CHECK(maxiter >= 1 && maxls >= 1, "tb_acq_maximize: maxiter and maxls must be positive");
+  TB_CHECK(gtol >= 0.0 && ftol >= 0.0, "tb_acq_maximize: tolerances must be non-negative");
+  TB_CHECK(gp->cache_valid, "posterior cache is not built: call tb_gp_update_posterior_cache first");
+  if (P == 0) return 0;
+  TB_CUDA(cudaSetDevice(gp->device));
+  cudaStream_t st = gp->stream;
+  const int D = gp->D, m = maxcor;
+  const size_t PD = (size_t)P * D;
+  // per-problem state + compact evaluation buffers (freed on return)
+  tb::DevBuf bx, bf, bg, bd, bt, bS, bY, brho, bgam, bint, bnfev, btrial, bidx, bxt, bval, bgrad, bbox, bcount, bres;
+  struct Release {
+    std::vector<tb::DevBuf*> v;
+    ~Release() { for (auto* b : v) b->release(); }
+  } rel{{&bx, &bf, &bg, &bd, &bt, &bS, &bY, &brho, &bgam, &bint, &bnfev, &btrial, &bidx, &bxt, &bval, &bgrad, &bbox, &bcount, &bres}};
+  TB_TRY(bx.reserve(8 * PD)); TB_TRY(bg.reserve(8 * PD)); TB_TRY(bd.reserve(8 * PD)); TB_TRY(btrial.reserve(8 * PD));
+  TB_TRY(bf.reserve(8 * (size_t)P)); TB_TRY(bt.reserve(8 * (size_t)P)); TB_TRY(bgam.reserve(8 * (size_t)P));
+  TB_TRY(bS.reserve(8 * PD * m)); TB_TRY(bY.reserve(8 * PD * m)); TB_TRY(brho.reserve(8 * (size_t)P * m));
+  TB_TRY(bint.reserve(sizeof(int) * 6 * (size_t)P)); TB_TRY(bnfev.reserve(8 * (size_t)P));
+  TB_TRY(bidx.reserve(sizeof(int) * (size_t)P)); TB_TRY(bxt.reserve(8 * PD)); TB_TRY(bval.reserve(8 * (size_t)P));
+  TB_TRY(bgrad.reserve(8 * PD)); TB_TRY(bbox.reserve(8 * 2 * (size_t)D)); TB_TRY(bcount.reserve(sizeof(int)));
+  tb::lb::State s;
+  s.x = bx.as<double>(); s.f = bf.as<double>(); s.g = bg.as<double>(); s.d = bd.as<double>(); s.t = bt.as<double>();
+  s.S = bS.as<double>(); s.Y = bY.as<double>(); s.rho = brho.as<double>(); s.gam = bgam.as<double>();
+  int* ints = bint.as<int>();
+  s.npairs = ints; s.head = ints + P; s.ls = ints + 2 * P; s.iters = ints + 3 * P; s.phase = ints + 4 * P; s.status = ints + 5 * P;
+  s.nfev = bnfev.as<long long>();
+  s.xtrial = btrial.as<double>();
+  double* dlo = bbox.as<double>();
+  double* dup = dlo + D;
+  TB_CUDA(cudaMemcpyAsync(dlo, lower, 8 * (size_t)D, cudaMemcpyDefault, st));
+  TB_CUDA(cudaMemcpyAsync(dup, upper, 8 * (size_t)D, cudaMemcpyDefault, st));
+  TB_CUDA(cudaMemcpyAsync(bxt.p, starts, 8 * PD, cudaMemcpyDefault, st));  // staged through the trial buffer
+  TB_CUDA(cudaMemsetAsync(bS.p, 0, 8 * PD * m, st));
+  TB_CUDA(cudaMemsetAsync(bY.p, 0, 8 * PD * m, st));
+  TB_CUDA(cudaMemsetAsync(brho.p, 0, 8 * (size_t)P * m, st));
+  tb::lb::lbfgs_init_kernel<<<(unsigned)((PD + 255) / 256), 256, 0, st>>>(bxt.as<double>(), P, D, dlo, dup, s);
+  TB_LAUNCHED();
+  tb::lb::Options o{D, m, maxiter, maxls, gtol, ftol};
+  int n_active = 0;
+  auto compact = [&]() -> int {
+    tb::lb::lbfgs_compact_kernel<<<1, 1024, 0, st>>>(s.status, P, bidx.as<int>(), bcount.as<int>());
+    TB_LAUNCHED();
+    TB_CUDA(cudaMemcpyAsync(&n_active, bcount.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    if (n_active > 0) {
+      tb::lb::lbfgs_gather_kernel<<<(unsigned)(((size_t)n_active * D + 255) / 256), 256, 0, st>>>(s.xtrial, bidx.as<int>(), n_active, D,
+                                                                                                 bxt.as<double>());
+      TB_LAUNCHED();
+    }
+    return 0;
+  };
+  TB_TRY(compact());
+  // every problem ends after at most maxiter accepted steps of at most maxls trials each
+  const int64_t max_rounds = (int64_t)maxiter * (int64_t)maxls + 2;
+  for (int64_t round = 0; n_active > 0 && round < max_rounds; ++round) {
+    tb::EvalRequest rq;
+    rq.acq = acq;
+    rq.param = param;
+    rq.Xc = bxt.as<double>();
+    rq.M = n_active;
+    rq.out_vals = bval.as<double>();
+    rq.out_grad = bgrad.as<double>();
+    TB_TRY(tb::run_eval(gp, rq));
+    tb::lb::lbfgs_step_kernel<<<(unsigned)((n_active + 7) / 8), 256, 0, st>>>(s, o, n_active, bidx.as<int>(), bxt.as<double>(),
+                                                                             bval.as<double>(), bgrad.as<double>(), dlo, dup);
+    TB_LAUNCHED();
+    TB_TRY(compact());
+  }
+  TB_TRY(bres.reserve((8 + 4 + 8) * (size_t)P));
+  double* rf = bres.as<double>();
+  int64_t* rn = reinterpret_cast<int64_t*>(rf + P);
+  int32_t* rs = reinterpret_cast<int32_t*>(rn + P);
+  lbfgs_finish_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(s, P, rf, rs, rn);
+  TB_LAUNCHED();
+  TB_CUDA(cudaMemcpyAsync(x_out, s.x, 8 * PD, cudaMemcpyDefault, st));
+  TB_CUDA(cudaMemcpyAsync(f_out, rf, 8 * (size_t)P, cudaMemcpyDefault, st));
+  TB_CUDA(cudaMemcpyAsync(nfev, rn, 8 * (size_t)P, cudaMemcpyDefault, st));
+  TB_CUDA(cudaMemcpyAsync(success, rs, 4 * (size_t)P, cudaMemcpyDefault, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int tb_gp_predict_joint(tb_gp* gp, const void* Xc, int64_t B, int q, void* mean, void* cov) {
