@@ -151,7 +151,7 @@ int tb_rff_eval(tb_rff* r, const void* Xc, int64_t M, void* out, double* min_val
  * adds the canonical features  sum_j v[b][j] k(x, X_j)  to trajectory b.  X [N,D] raw training inputs (host),
  * v [nb,N] column layout [trajectory][training point] (host or device).  N = 0 switches the term off. */
 int tb_rff_set_canonical(tb_rff* r, int kernel, const double* X, int64_t N, const double* v, int nb);
-/* (K(X,X) + noise I)^-1 B through the cached Cholesky factor: B, out [nrhs][N] (each right-hand side contiguous);
+/* (K(X,X) + noise I)^-1 B = Linv^T (Linv B) through the cached triangular inverse: B, out [nrhs][N] (each right-hand side contiguous);
  * the v-weights of a decoupled trajectory (sampler.py:716, gpflux compute_A_inv_b).  fp64, host or device. */
 int tb_gp_kinv_apply(tb_gp* gp, const double* B, int nrhs, double* out);
 

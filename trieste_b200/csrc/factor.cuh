@@ -66,10 +66,12 @@ __device__ __forceinline__ void zero_acc(double (&acc)[8][4][2]) {
 }
 
 // ---- Cholesky ---------------------------------------------------------------------------------
-// diagonal block j: unblocked Cholesky in shared memory + its inverse; one CTA.  info = first failing pivot (1-based)
+// diagonal block j: left-looking column Cholesky in shared memory + its inverse; one CTA, thread r owns row r (threads
+// >= 128 only take part in the barriers).  info = first failing pivot (1-based)
 __global__ void __launch_bounds__(THREADS)
 chol_diag_kernel(double* __restrict__ A, int64_t N, int j0, double* __restrict__ Dinv, int* __restrict__ info) {
   extern __shared__ __align__(16) double S[];  // [FB][FB + 1]
+  __shared__ double xd[FB];
   const int nb = (int)min((int64_t)FB, N - j0);
   const int ld = FB + 1;
   for (int e = threadIdx.x; e < FB * FB; e += THREADS) {
@@ -77,47 +79,69 @@ chol_diag_kernel(double* __restrict__ A, int64_t N, int j0, double* __restrict__
     S[r * ld + c] = (r < nb && c < nb && r >= c) ? A[(j0 + r) + (int64_t)(j0 + c) * N] : 0.0;
   }
   __syncthreads();
+  const int r = threadIdx.x;
+  const double* Sr = S + r * ld;
   for (int k = 0; k < nb; ++k) {
+    // column k: S[r][k] -= sum_{j<k} S[r][j] S[k][j]  (row r against the already-final row k)
+    double s = 0.0;
+    if (r >= k && r < nb) {
+      const double* Sk = S + k * ld;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int j = 0;
+      for (; j + 4 <= k; j += 4) {
+        s0 = fma(Sr[j], Sk[j], s0);
+        s1 = fma(Sr[j + 1], Sk[j + 1], s1);
+        s2 = fma(Sr[j + 2], Sk[j + 2], s2);
+        s3 = fma(Sr[j + 3], Sk[j + 3], s3);
+      }
+      for (; j < k; ++j) s0 = fma(Sr[j], Sk[j], s0);
+      s = Sr[k] - ((s0 + s1) + (s2 + s3));
+    }
+    __syncthreads();  // every read of row k is done before its diagonal entry changes
+    if (r == k) S[k * ld + k] = s;
+    __syncthreads();
     const double piv = S[k * ld + k];
     if (!(piv > 0.0)) {  // uniform across the CTA
       if (threadIdx.x == 0) atomicCAS(info, 0, j0 + k + 1);
       return;
     }
     const double d = sqrt(piv);
+    if (r > k && r < nb) S[r * ld + k] = s / d;
     __syncthreads();
-    for (int r = k + threadIdx.x; r < nb; r += THREADS) S[r * ld + k] = (r == k) ? d : S[r * ld + k] / d;
-    __syncthreads();
-    // trailing update of the lower triangle: S[r][c] -= S[r][k] S[c][k], k < c <= r
-    const int m = nb - k - 1;
-    for (int e = threadIdx.x; e < m * m; e += THREADS) {
-      const int r = k + 1 + e % m, c = k + 1 + e / m;
-      if (r >= c) S[r * ld + c] = fma(-S[r * ld + k], S[c * ld + k], S[r * ld + c]);
-    }
-    __syncthreads();
+    if (r == k) S[k * ld + k] = d;
   }
+  __syncthreads();
   for (int e = threadIdx.x; e < nb * nb; e += THREADS) {
-    const int r = e % nb, c = e / nb;
-    A[(j0 + r) + (int64_t)(j0 + c) * N] = (r >= c) ? S[r * ld + c] : 0.0;
+    const int rr = e % nb, c = e / nb;
+    A[(j0 + rr) + (int64_t)(j0 + c) * N] = (rr >= c) ? S[rr * ld + c] : 0.0;
   }
   // inverse of the lower-triangular block by forward substitution, one column per thread.  X[r][c] (r > c) lives in the
-  // unused strict upper triangle of S (at S[c][r]), the diagonal in xd: every operand of the dependent FMA chain is in smem
-  __shared__ double xd[FB];
+  // unused strict upper triangle of S (at S[c][r]), the diagonal in xd: every operand of the FMA chains is in smem
   __syncthreads();
   for (int c = threadIdx.x; c < nb; c += THREADS) {
     xd[c] = 1.0 / S[c * ld + c];
-    for (int r = c + 1; r < nb; ++r) {
-      double s = -S[r * ld + c] * xd[c];
-      for (int k = c + 1; k < r; ++k) s = fma(-S[r * ld + k], S[c * ld + k], s);
-      S[c * ld + r] = s / S[r * ld + r];
+    double* Xc = S + c * ld;  // Xc[r] = X[r][c] for r > c
+    for (int rr = c + 1; rr < nb; ++rr) {
+      const double* Lr = S + rr * ld;
+      double s0 = -Lr[c] * xd[c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int k = c + 1;
+      for (; k + 4 <= rr; k += 4) {
+        s0 = fma(-Lr[k], Xc[k], s0);
+        s1 = fma(-Lr[k + 1], Xc[k + 1], s1);
+        s2 = fma(-Lr[k + 2], Xc[k + 2], s2);
+        s3 = fma(-Lr[k + 3], Xc[k + 3], s3);
+      }
+      for (; k < rr; ++k) s0 = fma(-Lr[k], Xc[k], s0);
+      Xc[rr] = ((s0 + s1) + (s2 + s3)) / Lr[rr];
     }
   }
   __syncthreads();
   double* X = Dinv + (int64_t)(j0 / FB) * FB * FB;  // column-major [FB][FB]
   for (int e = threadIdx.x; e < FB * FB; e += THREADS) {
-    const int r = e % FB, c = e / FB;
+    const int rr = e % FB, c = e / FB;
     double v = 0.0;
-    if (r < nb && c < nb) v = (r == c) ? xd[c] : (r > c ? S[c * ld + r] : 0.0);
-    X[r + (int64_t)c * FB] = v;
+    if (rr < nb && c < nb) v = (rr == c) ? xd[c] : (rr > c ? S[c * ld + rr] : 0.0);
+    X[rr + (int64_t)c * FB] = v;
   }
 }
 

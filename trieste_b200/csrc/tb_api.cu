@@ -275,10 +275,6 @@ int tb_gp_create(tb_gp** out, int device, int dtype) {
     TB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
     TB_CUDA(cudaStreamCreateWithPriority(&gp->stream, cudaStreamNonBlocking, greatest));
   }
-  TB_CUBLAS(cublasCreate(&gp->cublas));
-  TB_CUBLAS(cublasSetStream(gp->cublas, gp->stream));
-  TB_CUSOLVER(cusolverDnCreate(&gp->cusolver));
-  TB_CUSOLVER(cusolverDnSetStream(gp->cusolver, gp->stream));
   TB_TRY(tb::kernels_init());
   *out = gp;
   return 0;
@@ -368,6 +364,20 @@ static int scale_inputs(tb_gp* gp) {
   scale_inputs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, gp->stream>>>(gp->dX.as<double>(), gp->dInvLs.as<double>(), gp->N, D,
                                                                             DP, rows, gp->dXs.as<double>());
   TB_LAUNCHED();
+  return 0;
+}
+
+// cuSOLVER / cuBLAS handles exist only for the TB_FACTOR=cusolver cross-check path: created on first use
+static int ensure_library_handles(tb_gp* gp) {
+  if (gp->cublas && gp->cusolver) return 0;
+  if (!gp->cublas) {
+    TB_CUBLAS(cublasCreate(&gp->cublas));
+    TB_CUBLAS(cublasSetStream(gp->cublas, gp->stream));
+  }
+  if (!gp->cusolver) {
+    TB_CUSOLVER(cusolverDnCreate(&gp->cusolver));
+    TB_CUSOLVER(cusolverDnSetStream(gp->cusolver, gp->stream));
+  }
   return 0;
 }
 
@@ -484,6 +494,7 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
     TB_TRY(alpha_from_linv(gp));
   } else {
     // ---- library path (TB_FACTOR=cusolver): cuSOLVER potrf / potrs + cuBLAS trsm; kept as a cross-check ----
+    TB_TRY(ensure_library_handles(gp));
     int lwork = 0;
     TB_CUSOLVER(cusolverDnDpotrf_bufferSize(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dL.as<double>(), (int)N, &lwork));
     TB_TRY(gp->dWork.reserve(sizeof(double) * (size_t)std::max(lwork, 1)));
@@ -813,6 +824,7 @@ static int ensure_kinv_digits(tb_gp* gp) {
     fac::kinv_kernel<<<dim3(t, t), fac::THREADS, fac::GEMM_SMEM, st>>>(gp->dLinv.as<double>(), gp->dKinv.as<double>(), N);
     TB_LAUNCHED();
   } else {
+  TB_TRY(ensure_library_handles(gp));
   TB_CUDA(cudaMemcpyAsync(gp->dKinv.p, gp->dL.p, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, st));
   int lwork = 0;
   cusolverStatus_t cs = cusolverDnDpotri_bufferSize(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, &lwork);
@@ -1296,14 +1308,20 @@ int tb_gp_kinv_apply(tb_gp* gp, const double* B, int nrhs, double* out) {
   TB_CHECK(nrhs >= 1, "tb_gp_kinv_apply: need at least one right-hand side");
   TB_CUDA(cudaSetDevice(gp->device));
   const int64_t N = gp->N;
-  TB_TRY(gp->sMisc.reserve(sizeof(double) * N * nrhs));
-  TB_CUDA(cudaMemcpyAsync(gp->sMisc.p, B, sizeof(double) * N * nrhs, cudaMemcpyDefault, gp->stream));
-  // (K + noise I)^-1 B through the cached Cholesky factor (cuSOLVER potrs: once per trajectory, off the candidate path)
-  cusolverStatus_t st = cusolverDnDpotrs(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, nrhs, gp->dL.as<double>(), (int)N,
-                                         gp->sMisc.as<double>(), (int)N, gp->dInfo.as<int>());
-  TB_CHECK(st == CUSOLVER_STATUS_SUCCESS, "tb_gp_kinv_apply: cusolverDnDpotrs failed");
-  TB_CUDA(cudaMemcpyAsync(out, gp->sMisc.p, sizeof(double) * N * nrhs, cudaMemcpyDefault, gp->stream));
-  TB_CUDA(cudaStreamSynchronize(gp->stream));
+  cudaStream_t st = gp->stream;
+  TB_TRY(gp->sMisc.reserve(sizeof(double) * 2 * N * nrhs));
+  double* rhs = gp->sMisc.as<double>();
+  double* tmp = rhs + N * nrhs;
+  TB_CUDA(cudaMemcpyAsync(rhs, B, sizeof(double) * N * nrhs, cudaMemcpyDefault, st));
+  // (K + noise I)^-1 B = Linv^T (Linv B) through the cached triangular inverse: two batched triangular mat-vecs
+  // (once per trajectory, off the candidate path)
+  trmv_lower_cols_kernel<<<dim3((unsigned)((N + 127) / 128), (unsigned)nrhs), 128, 0, st>>>(gp->dLinv.as<double>(), N, N, rhs, N, tmp, N);
+  TB_LAUNCHED();
+  trmv_lower_t_cols_kernel<<<dim3((unsigned)((N + 7) / 8), (unsigned)nrhs), 256, 0, st>>>(gp->dLinv.as<double>(), N, N, tmp, N, rhs, N);
+  TB_LAUNCHED();
+  TB_CUDA(cudaMemcpyAsync(out, rhs, sizeof(double) * N * nrhs, cudaMemcpyDefault, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
   return 0;
 }
 int tb_gp_stream(tb_gp* gp, void** stream) {
