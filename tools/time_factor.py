@@ -24,10 +24,10 @@ for N in (1024, 4096, 8192):
 os.environ["TB_FACTOR"] = "own"
 for N in (1024, 4096, 8192):
     rng = np.random.default_rng(0)
-    X = rng.uniform(size=(N + 40, 10)); y = ackley(X)
+    X = rng.uniform(size=(N + 50, 10)); y = ackley(X)
     spec = tb.build_gpr(tb.Dataset(X[:N], y[:N]), tb.Box([0.0] * 10, [1.0] * 10))
     m = tb.GaussianProcessRegression(spec)
-    for step, add in ((1, 1), (2, 1), (3, 8), (4, 30)):
+    for step, add in ((1, 1), (2, 1), (3, 1), (4, 1), (5, 8), (6, 30)):
         n1 = m.get_internal_data().query_points.shape[0] + add
         torch.cuda.synchronize()
         t0 = time.perf_counter(); m.update(tb.Dataset(X[:n1], y[:n1])); torch.cuda.synchronize(); dt = time.perf_counter() - t0

@@ -97,6 +97,7 @@ struct tb_gp {
   // per-call scratch
   tb::DevBuf sKs, sPartial, sMean, sVals, sVar, sXc, sBlkBest, sBlkIdx, sRun;
   tb::DevBuf sA, sV, sGrad, sMisc;  // A / V panels (joint + gradient paths), misc staging
+  tb::DevBuf dXspare, dyspare, dLspare, dLinvSpare;  // ping-pong partners of dX / dy / dL / dLinv (tb_gp_append_data)
   tb::DevBuf dMes;              // min-value samples of TB_ACQ_MES (tb_acq_set_min_value_samples)
   int mesS = 0;
 

@@ -287,7 +287,7 @@ int tb_gp_destroy(tb_gp* gp) {
   for (tb::DevBuf* b : {&gp->dX, &gp->dy, &gp->dXs, &gp->dInvLs, &gp->dAlpha, &gp->dL, &gp->dLinv,
                         &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->dKinv, &gp->dKinvS, &gp->dKinvScale, &gp->dDinv, &gp->sKs2, &gp->sMean2, &gp->sPartial2, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
                         &gp->sVals, &gp->sVar, &gp->sXc, &gp->sBlkBest, &gp->sBlkIdx, &gp->sRun,
-                        &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc, &gp->dMes})
+                        &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc, &gp->dMes, &gp->dXspare, &gp->dyspare, &gp->dLspare, &gp->dLinvSpare})
     b->release();
   for (auto& ev : gp->prof_events) {
     cudaEventDestroy(ev.first);
@@ -537,12 +537,15 @@ static int tb_gp_append_data_f64(tb_gp* gp, const double* Xnew, const double* yn
   TB_CUDA(cudaSetDevice(gp->device));
   cudaStream_t st = gp->stream;
   const int D = gp->D, DP = gp->DP;
-  // grow the raw data and the two triangular factors (leading dimension N0 -> N)
-  tb::DevBuf nX, ny, nL, nLinv;
-  TB_TRY(nX.reserve(sizeof(double) * N * D));
-  TB_TRY(ny.reserve(sizeof(double) * N));
-  TB_TRY(nL.reserve(sizeof(double) * N * N));
-  TB_TRY(nLinv.reserve(sizeof(double) * N * N));
+  // grow the raw data and the two triangular factors (leading dimension N0 -> N) into the handle's spare buffers, which are
+  // sized with slack (next multiple of 256 rows + 256) and ping-pong with the live ones: after the second append of a run
+  // no cudaMalloc / cudaFree (both device-synchronising) is left on this path
+  const int64_t cap_rows = ((N + 255) / 256) * 256 + 256;
+  tb::DevBuf &nX = gp->dXspare, &ny = gp->dyspare, &nL = gp->dLspare, &nLinv = gp->dLinvSpare;
+  TB_TRY(nX.reserve(sizeof(double) * cap_rows * D));
+  TB_TRY(ny.reserve(sizeof(double) * cap_rows));
+  TB_TRY(nL.reserve(sizeof(double) * cap_rows * cap_rows));
+  TB_TRY(nLinv.reserve(sizeof(double) * cap_rows * cap_rows));
   TB_CUDA(cudaMemcpyAsync(nX.p, gp->dX.p, sizeof(double) * N0 * D, cudaMemcpyDeviceToDevice, st));
   TB_CUDA(cudaMemcpyAsync(nX.as<double>() + N0 * D, Xnew, sizeof(double) * m * D, cudaMemcpyDefault, st));
   TB_CUDA(cudaMemcpyAsync(ny.p, gp->dy.p, sizeof(double) * N0, cudaMemcpyDeviceToDevice, st));
@@ -558,7 +561,6 @@ static int tb_gp_append_data_f64(tb_gp* gp, const double* Xnew, const double* yn
   std::swap(gp->dy, ny);
   std::swap(gp->dL, nL);
   std::swap(gp->dLinv, nLinv);
-  nX.release(); ny.release(); nL.release(); nLinv.release();
   gp->N = N;
   gp->nkc = (int)((N + BK - 1) / BK);
   gp->NB = (int)((N + BM - 1) / BM);
