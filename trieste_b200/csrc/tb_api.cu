@@ -569,7 +569,8 @@ static int tb_gp_append_data_f64(tb_gp* gp, const double* Xnew, const double* yn
   TB_TRY(scale_inputs(gp));
   TB_TRY(gp->dAlpha.reserve(sizeof(double) * rows));
   // scratch: W (cross kernel block), Y = Linv0 B, U = Linv0^T Y as [N, m] column-major; S, R as [m, m]
-  TB_TRY(gp->sA.reserve(sizeof(double) * (3 * N * m + 2 * m * m)));
+  // sized for the largest append at the spare buffers' row capacity: no reallocation while the capacity lasts
+  TB_TRY(gp->sA.reserve(sizeof(double) * (3 * cap_rows * APPEND_MAX + 2 * APPEND_MAX * APPEND_MAX)));
   double* W = gp->sA.as<double>();
   double* Y = W + N * m;
   double* U = Y + N * m;
