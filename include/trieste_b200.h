@@ -123,6 +123,13 @@ int tb_acq_maximize(tb_gp* gp, int acq, double param, const double* lower, const
 int tb_acq_batch_mc_ei(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S,
                        double eta, double jitter, void* out);
 
+/* The same value together with its gradient w.r.t. the query batches — what tfp.math.value_and_gradient
+ * (acquisition/optimizer.py:621-629) differentiates when a batch function is maximised through batchify_joint
+ * (:897-936): reduce_min routes to the arg-min sample, maximum(., 0) to the active ones, the Cholesky of the joint
+ * covariance by its reverse-mode rule.  out [B], grad [B,q,D].  int8 engine only (N ≤ 16384). */
+int tb_acq_batch_mc_ei_grad(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S, double eta,
+                            double jitter, void* out, void* grad);
+
 /* BatchReparametrizationSampler.sample (sampler.py:208-287): → samples [B,S,q]. */
 int tb_gp_reparam_sample(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S,
                          double jitter, void* samples);

@@ -341,6 +341,63 @@ def batch_monte_carlo_expected_improvement(m: GPRModel, Xq, eps, eta, jitter=JIT
     return improvement.mean(-1, keepdims=True)
 
 
+def _kernel_dr2(kind: str, r2: np.ndarray, variance: float) -> np.ndarray:
+    """d k / d r^2 of the stationary kernels (r^2 in lengthscale-scaled coordinates)."""
+    if kind == "rbf":
+        return -0.5 * variance * np.exp(-0.5 * r2)
+    r = np.sqrt(np.maximum(r2, 1e-36))
+    if kind == "matern12":
+        return -variance * np.exp(-r) / (2.0 * r)
+    if kind == "matern32":
+        return -variance * 1.5 * np.exp(-math.sqrt(3.0) * r)
+    s5 = math.sqrt(5.0)
+    return -variance * (5.0 / 6.0) * (1.0 + s5 * r) * np.exp(-s5 * r)
+
+
+def batch_mc_ei_gradient(m: GPRModel, Xb: np.ndarray, eps: np.ndarray, eta: float, jitter: float = JITTER):
+    """Value and d/dX of :func:`batch_monte_carlo_expected_improvement` for ONE query batch Xb [q, D] with base samples
+    eps [q, S] — what TensorFlow's autodiff returns for function.py:1181-1186 through sampler.py:262-287 (reduce_min
+    passes the gradient to the arg-min sample, maximum(., 0) to the active ones, Cholesky by its reverse-mode rule
+    Sigma_bar = L^-T sym(Phi(L^T L_bar)) L^-1, Murray 2016).  Returns (value, grad [q, D])."""
+    Xb = np.asarray(Xb, dtype=np.float64)
+    q, D = Xb.shape
+    S = eps.shape[1]
+    mean, cov = predict_joint(m, Xb[None])  # [1,q,1], [1,1,q,q]
+    mu = mean[0, :, 0]
+    Sigma = cov[0, 0] + jitter * np.eye(q)
+    C = np.linalg.cholesky(Sigma)
+    f = mu[:, None] + C @ eps  # [q, S]
+    jstar = np.argmin(f, axis=0)
+    imp = eta - f[jstar, np.arange(S)]
+    active = imp > 0.0
+    value = np.maximum(imp, 0.0).mean()
+    G_mu = np.zeros(q)
+    G_C = np.zeros((q, q))
+    for s in np.nonzero(active)[0]:
+        j = jstar[s]
+        G_mu[j] -= 1.0 / S
+        G_C[j, : j + 1] -= eps[: j + 1, s] / S
+    P = np.tril(C.T @ G_C)
+    P[np.diag_indices(q)] *= 0.5
+    Msym = 0.5 * (P + P.T)
+    Sbar = sla.solve_triangular(C.T, sla.solve_triangular(C.T, Msym, lower=False).T, lower=False).T  # C^-T M C^-1
+    # d mu_j / d x_j and d Sigma[j,k] / d x_j
+    ls = m.lengthscales
+    Xt, Xq = m.X / ls, Xb / ls
+    diff_n = Xq[:, None, :] - Xt[None, :, :]  # [q, N, D]
+    dk_n = _kernel_dr2(m.kind, np.square(diff_n).sum(-1), m.variance)[:, :, None] * 2.0 * diff_n / ls  # [q, N, D]
+    alpha = sla.cho_solve((m.L, True), m.err, check_finite=False)[:, 0]
+    V = sla.cho_solve((m.L, True), kernel_matrix(m.kind, m.X, Xb, m.variance, ls), check_finite=False)  # [N, q]
+    diff_q = Xq[:, None, :] - Xq[None, :, :]  # [q, q, D]
+    dk_q = _kernel_dr2(m.kind, np.square(diff_q).sum(-1), m.variance)[:, :, None] * 2.0 * diff_q / ls
+    dk_q[np.arange(q), np.arange(q)] = 0.0  # k(x, x) is constant
+    grad = np.zeros((q, D))
+    for j in range(q):
+        w = G_mu[j] * alpha - 2.0 * (V @ Sbar[j])  # [N]
+        grad[j] = dk_n[j].T @ w + 2.0 * (Sbar[j][:, None] * dk_q[j]).sum(0)
+    return value, grad
+
+
 # --------------------------------------------------------------------------------------------
 # A5. Random Fourier features + theta posterior + trajectory
 # (EXT gpflux 0.4.4 RandomFourierFeaturesCosine; trieste/models/gpflow/sampler.py:529-591,741-806,

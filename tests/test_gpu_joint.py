@@ -155,3 +155,54 @@ def test_monte_carlo_expected_improvement_single_point():
     assert not np.array_equal(fn._sampler._get_eps(1), eps)  # update resets the sampler (function.py:866)
     with pytest.raises(ValueError):
         MonteCarloExpectedImprovement(0)
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern32", "matern52"])
+@pytest.mark.parametrize("N,D,q,S", [(200, 6, 4, 64), (300, 6, 8, 512), (150, 3, 1, 32), (260, 10, 11, 100)])
+def test_batch_mc_ei_value_and_gradient_matches_oracle(N, D, q, S, kind):
+    # reverse pass of function.py:1181-1186 (what the reference gets from TF autodiff) against the oracle's analytic
+    # restatement (itself pinned by finite differences, tests/test_oracle.py)
+    from trieste_b200 import Dataset
+    from trieste_b200.acquisition import BatchMonteCarloExpectedImprovement
+
+    obj = o.hartmann_6 if D == 6 else o.ackley
+    om, nm = model_pair(obj, N, D, kind=kind)
+    fn = BatchMonteCarloExpectedImprovement(S, jitter=1e-6).prepare_acquisition_function(nm, Dataset(om.X, om.y))
+    eps = np.random.default_rng(3).standard_normal((q, S))
+    fn._sampler.set_eps(eps)
+    fn._eta = float(np.median(om.y))  # plenty of active samples
+    nb = 37
+    X = candidates(nb * q, D).reshape(nb, q, D)
+    val, grad = fn.value_and_gradient(X)
+    assert val.shape == (nb, 1) and grad.shape == (nb, q, D)
+    np.testing.assert_allclose(val, fn(X), rtol=1e-9, atol=1e-13)
+    for b in range(0, nb, 6):
+        oval, ograd = o.batch_mc_ei_gradient(om, X[b], eps, fn._eta, 1e-6)
+        np.testing.assert_allclose(val[b, 0], oval, rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(grad[b], ograd, rtol=1e-5, atol=1e-7 * max(np.abs(ograd).max(), 1e-30))
+
+
+def test_batch_mc_ei_gradient_drives_the_joint_optimizer():
+    # batchify_joint + continuous optimiser over space ** q (optimizer.py:897-936): ends at a point no worse than the
+    # best random q-batch and the starts it refined
+    import trieste_b200 as tb
+    from trieste_b200.acquisition import BatchMonteCarloExpectedImprovement
+    from trieste_b200.acquisition.optimizer import batchify_joint, generate_continuous_optimizer
+
+    om, nm = model_pair(o.hartmann_6, 150, 6)
+    ds = tb.Dataset(om.X, om.y)
+    fn = BatchMonteCarloExpectedImprovement(256).prepare_acquisition_function(nm, ds)
+    space = tb.Box([0.0] * 6, [1.0] * 6)
+    opt = batchify_joint(generate_continuous_optimizer(num_initial_samples=400, num_optimization_runs=6,
+                                                       optimizer_args={"maxiter": 60}), 3)
+    pts = opt(space, fn)
+    assert pts.shape == (3, 6) and space.contains(pts).all()
+    rnd = space.sample(400 * 3, seed=2).reshape(400, 3, 6)
+    assert fn(pts[None])[0, 0] >= fn(rnd).max() - 1e-12
+    # leading dimensions and argument errors
+    v, g = fn.value_and_gradient(rnd[:6].reshape(2, 3, 3, 6))
+    assert v.shape == (2, 3, 1) and g.shape == (2, 3, 3, 6)
+    nm.set_engine("fp64")
+    with pytest.raises(ValueError):
+        fn.value_and_gradient(rnd[:2])
+    nm.set_engine("int8")

@@ -262,3 +262,36 @@ def test_gumbel_fit_and_sampler_argument_checks():
         ThompsonSamplerFromTrajectory().sample(object(), 1, np.zeros((3, 2)))  # no trajectory_sampler
     with pytest.raises(ValueError):
         ThompsonSamplerFromTrajectory().sample(object(), 1, np.zeros(3))  # at must be [N, D]
+
+
+def test_batchify_joint_passes_gradients_through_the_reshape():
+    # optimizer.py:897-936: a batch function maximised over space ** q by the continuous optimiser
+    from trieste_b200.acquisition.optimizer import batchify_joint, generate_continuous_optimizer
+
+    centres = np.array([[0.2, 0.7], [0.9, 0.1], [0.5, 0.5]])
+
+    class BatchQuadratic:
+        def __call__(self, x):
+            return self.value_and_gradient(x)[0]
+
+        def value_and_gradient(self, x):
+            x = np.asarray(x)  # [..., 3, 2]
+            diff = x - centres
+            return -np.sum(diff * diff, axis=(-1, -2))[..., None], -2.0 * diff
+
+    space = Box([0.0, 0.0], [1.0, 1.0])
+
+    def inner(expanded, f):  # the multi-start loop of generate_continuous_optimizer without its GPU top-k of the starts
+        assert expanded.dimension == 6
+        x0 = np.random.default_rng(0).uniform(size=(4, 1, 6))
+        val, grad = f.value_and_gradient(x0)
+        assert val.shape == (4, 1) and grad.shape == x0.shape
+        ok, fun, xs, _ = _perform_parallel_continuous_optimization(f, expanded.lower, expanded.upper, x0, {})
+        assert ok.all()
+        return xs[np.argmax(fun[:, 0]), 0][None, :]
+
+    pts = batchify_joint(inner, 3)(space, BatchQuadratic())
+    assert pts.shape == (3, 2)
+    np.testing.assert_allclose(pts, centres, atol=1e-4)
+    with pytest.raises(ValueError):
+        batchify_joint(generate_continuous_optimizer(), 0)

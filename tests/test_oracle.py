@@ -221,3 +221,26 @@ def test_gumbel_sampler_restatement_matches_empirical_minimum_quartiles():
     g = o.gumbel_samples(a, b, np.array([0.25, 0.75]))[:, 0]
     np.testing.assert_allclose(g, [q1, q2], atol=0.01)
     assert b > 0
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern32", "matern52"])
+def test_batch_mc_ei_gradient_restatement_matches_finite_differences(kind):
+    # the reverse pass of function.py:1181-1186 (arg-min routing, Cholesky reverse mode) against central differences
+    m = o.synthetic_model(o.hartmann_6, 40, 6, kind=kind)
+    rng = np.random.default_rng(1)
+    q, S = 4, 96
+    eps = rng.standard_normal((q, S))
+    Xb = rng.uniform(size=(q, 6))
+    eta = float(np.median(m.y))
+    val, g = o.batch_mc_ei_gradient(m, Xb, eps, eta)
+    np.testing.assert_allclose(val, o.batch_monte_carlo_expected_improvement(m, Xb[None], eps[None], eta)[0, 0], rtol=1e-12)
+    h = 1e-6
+    fd = np.zeros_like(g)
+    for j in range(q):
+        for d in range(6):
+            Xp, Xm = Xb.copy(), Xb.copy()
+            Xp[j, d] += h
+            Xm[j, d] -= h
+            fd[j, d] = (o.batch_monte_carlo_expected_improvement(m, Xp[None], eps[None], eta)[0, 0]
+                        - o.batch_monte_carlo_expected_improvement(m, Xm[None], eps[None], eta)[0, 0]) / (2 * h)
+    np.testing.assert_allclose(g, fd, rtol=1e-5, atol=1e-7 * np.abs(g).max())

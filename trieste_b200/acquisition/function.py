@@ -400,6 +400,25 @@ class batch_monte_carlo_expected_improvement(AcquisitionFunctionClass):
         )
         return out.reshape(lead + (1,))
 
+    def value_and_gradient(self, x):
+        """[..., B, D] -> (values [..., 1], d values / d x [..., B, D]): the reverse pass TensorFlow's autodiff performs
+        when the reference maximises this function over ``space ** B`` (batchify_joint, optimizer.py:897-936)."""
+        x, _ = _lib.as_contiguous(x, self._model.dtype)
+        if x.ndim < 2:
+            raise ValueError(f"expected [..., B, D] query batches, got shape {tuple(x.shape)}")
+        self._model._check_dim(x)
+        flat, lead = _flatten_leading(x, 2)
+        nb, q, D = flat.shape
+        eps = np.ascontiguousarray(self._sampler._get_eps(q), dtype=self._model.dtype)
+        out, po = _lib.empty_like_kind(flat, (nb, 1), self._model.dtype)
+        grad, pg = _lib.empty_like_kind(flat, (nb, q, D), self._model.dtype)
+        _lib.check(
+            _lib.lib().tb_acq_batch_mc_ei_grad(
+                self._model.handle, _ptr(flat), nb, q, eps.ctypes.data, eps.shape[1], self._eta, self._jitter, po, pg
+            )
+        )
+        return out.reshape(lead + (1,)), grad.reshape(lead + (q, D))
+
 
 class monte_carlo_expected_improvement(batch_monte_carlo_expected_improvement):
     """function.py:883-920: ``mean_S max(eta - f_s(x), 0)`` over reparametrised samples, batch size one.  For a GPR the

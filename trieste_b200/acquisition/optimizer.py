@@ -353,10 +353,22 @@ def batchify_joint(batch_size_one_optimizer, batch_size: int):
             raise ValueError("batchify_joint does not support vectorised acquisition functions")
         expanded = space**batch_size
 
-        def target_on_expanded(x):
-            x = np.asarray(x)
-            return fn(x.reshape(x.shape[:-2] + (batch_size, -1)))
+        class _Expanded:
+            """``fn`` seen through ``space ** q``: [..., 1, q*D] <-> [..., q, D] (values and, when the function offers
+            them, gradients — the reference differentiates through the reshape)."""
 
+            def __call__(self, x):
+                x = _to_numpy(x)
+                return fn(x.reshape(x.shape[:-2] + (batch_size, -1)))
+
+            if hasattr(fn, "value_and_gradient"):
+
+                def value_and_gradient(self, x):
+                    x = _to_numpy(x)
+                    val, grad = fn.value_and_gradient(x.reshape(x.shape[:-2] + (batch_size, -1)))
+                    return val, _to_numpy(grad).reshape(x.shape)
+
+        target_on_expanded = _Expanded()
         vectorized_points = batch_size_one_optimizer(expanded, target_on_expanded)  # [1, q*D]
         return vectorized_points.reshape(batch_size, -1)
 

@@ -161,6 +161,175 @@ joint_kernel(const double* __restrict__ Aplain, int64_t lda, int Nrows,  // [can
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2g: reverse pass of the batch Monte-Carlo EI of one q-batch (function.py:1181-1186 through sampler.py:262-287), i.e.
+// what TensorFlow's autodiff produces for  mean_s max(eta - min_j (mu + C eps_s)_j, 0),  C = chol(cov + jitter I):
+//   G_mu[j]   = -(1/S) #{s active, argmin = j}            G_C[j][k] = -(1/S) sum_{s active, argmin = j} eps[k][s]  (k <= j)
+//   Sigma_bar = C^-T sym(Phi(C^T G_C)) C^-1               (Cholesky reverse mode, Murray 2016; Phi = tril, diagonal halved)
+// One warp per batch; outputs the value, c_mu = G_mu (and c_var = 1) for the gradient assembly, and Sigma_bar [q,q].
+// Shared memory per warp: 3 q^2 + 2 q doubles.
+// ------------------------------------------------------------------------------------------------
+constexpr int QEIG_WARPS = 4;
+
+__global__ void __launch_bounds__(QEIG_WARPS * 32)
+qei_backward_kernel(const double* __restrict__ mean_in, const double* __restrict__ cov_in, int64_t nb, int q,
+                    const double* __restrict__ eps, int S, double eta, double jitter, double* __restrict__ out_val,
+                    double* __restrict__ cmu, double* __restrict__ cvar, double* __restrict__ sbar, int* __restrict__ err_flag) {
+  extern __shared__ __align__(16) unsigned char qsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qq = q * q;
+  double* Cs = reinterpret_cast<double*>(qsm) + (size_t)warp * (3 * qq + 2 * q);
+  double* Gs = Cs + qq;
+  double* Ts = Gs + qq;
+  double* mu = Ts + qq;
+  double* gmu = mu + q;
+  const int64_t b = (int64_t)blockIdx.x * QEIG_WARPS + warp;
+  if (b >= nb) return;
+  const int64_t t0 = b * q;
+  for (int e = lane; e < qq; e += 32) {
+    Cs[e] = cov_in[b * qq + e] + ((e / q == e % q) ? jitter : 0.0);
+    Gs[e] = 0.0;
+  }
+  for (int e = lane; e < q; e += 32) {
+    mu[e] = mean_in[t0 + e];
+    gmu[e] = 0.0;
+  }
+  __syncwarp();
+  // in-place Cholesky (lower), as in joint_kernel
+  bool bad = false;
+  for (int j = 0; j < q; ++j) {
+    double djj = 0.0;
+    if (lane == 0) {
+      double sdiag = Cs[j * q + j];
+      for (int k = 0; k < j; ++k) sdiag = fma(-Cs[j * q + k], Cs[j * q + k], sdiag);
+      djj = sqrt(sdiag);
+      Cs[j * q + j] = djj;
+    }
+    djj = __shfl_sync(0xffffffffu, djj, 0);
+    if (!(djj > 0.0)) bad = true;
+    __syncwarp();
+    for (int i = j + 1 + lane; i < q; i += 32) {
+      double v = Cs[i * q + j];
+      for (int k = 0; k < j; ++k) v = fma(-Cs[i * q + k], Cs[j * q + k], v);
+      Cs[i * q + j] = v / djj;
+    }
+    __syncwarp();
+  }
+  if (bad) {
+    if (lane == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  // forward over the base samples; the active arg-min entries feed G_mu / G_C
+  const double invS = 1.0 / (double)S;
+  double acc = 0.0;
+  for (int s = lane; s < S; s += 32) {
+    double mn = DBL_MAX;
+    int arg = 0;
+    for (int i = 0; i < q; ++i) {
+      double f = mu[i];
+      for (int k = 0; k <= i; ++k) f = fma(Cs[i * q + k], __ldg(eps + (int64_t)k * S + s), f);
+      if (f < mn) {  // first minimum wins (tf.reduce_min / argmin)
+        mn = f;
+        arg = i;
+      }
+    }
+    const double imp = eta - mn;
+    if (imp > 0.0) {
+      acc += imp;
+      atomicAdd(&gmu[arg], -invS);
+      for (int k = 0; k <= arg; ++k) atomicAdd(&Gs[arg * q + k], -invS * __ldg(eps + (int64_t)k * S + s));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __syncwarp();
+  // P = Phi(C^T G) (lower, diagonal halved) -> Ts
+  for (int e = lane; e < qq; e += 32) {
+    const int a = e / q, c = e % q;
+    double v = 0.0;
+    if (a >= c) {
+      for (int i = a; i < q; ++i) v = fma(Cs[i * q + a], Gs[i * q + c], v);
+      if (a == c) v *= 0.5;
+    }
+    Ts[e] = v;
+  }
+  __syncwarp();
+  // M = (P + P^T) / 2 (symmetric) -> Gs
+  for (int e = lane; e < qq; e += 32) {
+    const int a = e / q, c = e % q;
+    Gs[e] = (a == c) ? Ts[e] : 0.5 * (a > c ? Ts[a * q + c] : Ts[c * q + a]);
+  }
+  __syncwarp();
+  // T1 = C^-T M: back substitution of C^T T1 = M, lane = column -> Ts
+  for (int c = lane; c < q; c += 32) {
+    for (int a = q - 1; a >= 0; --a) {
+      double v = Gs[a * q + c];
+      for (int i = a + 1; i < q; ++i) v = fma(-Cs[i * q + a], Ts[i * q + c], v);
+      Ts[a * q + c] = v / Cs[a * q + a];
+    }
+  }
+  __syncwarp();
+  // Sigma_bar = T1 C^-1: row r solves C^T x = T1[r][:]^T, lane = row -> Gs
+  for (int r = lane; r < q; r += 32) {
+    for (int a = q - 1; a >= 0; --a) {
+      double v = Ts[r * q + a];
+      for (int i = a + 1; i < q; ++i) v = fma(-Cs[i * q + a], Gs[r * q + i], v);
+      Gs[r * q + a] = v / Cs[a * q + a];
+    }
+  }
+  __syncwarp();
+  if (lane == 0) out_val[b] = acc * invS;
+  for (int e = lane; e < q; e += 32) {
+    cmu[t0 + e] = gmu[e];
+    cvar[t0 + e] = 1.0;
+  }
+  for (int e = lane; e < qq; e += 32) sbar[b * qq + e] = Gs[e];
+}
+
+// V~[j][n] = sum_k Sigma_bar[b][j][k] V[k][n] inside every batch, in place (V plain [point][ldv]); grid (ceil(N/256), nb)
+__global__ void __launch_bounds__(256)
+qei_mix_kernel(double* __restrict__ V, int64_t ldv, int N, int q, const double* __restrict__ sbar) {
+  __shared__ double sb[32 * 32];
+  const int64_t b = blockIdx.y;
+  for (int e = threadIdx.x; e < q * q; e += blockDim.x) sb[e] = sbar[b * q * q + e];
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double v[32];
+  double* base = V + b * q * ldv + n;
+  for (int k = 0; k < q; ++k) v[k] = base[(int64_t)k * ldv];
+  for (int j = 0; j < q; ++j) {
+    double acc = 0.0;
+    for (int k = 0; k < q; ++k) acc = fma(sb[j * q + k], v[k], acc);
+    base[(int64_t)j * ldv] = acc;
+  }
+}
+
+// grad[t][d] += 2 sum_{k != j} Sigma_bar[b][j][k] dk(x_j, x_k)/dx_j,d (the K(x_b, x_b) term of the joint covariance);
+// one thread per query point
+template <int KIND>
+__global__ void __launch_bounds__(128)
+qei_cross_kernel(const double* __restrict__ Xc, const double* __restrict__ inv_ls, int D, int64_t npts, int q,
+                 const double* __restrict__ sbar, double variance, double* __restrict__ grad) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npts) return;
+  const int64_t b = t / q;
+  const int j = (int)(t % q);
+  double g[32];
+  for (int d = 0; d < D; ++d) g[d] = 0.0;
+  for (int k = 0; k < q; ++k) {
+    if (k == j) continue;
+    double r2 = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double df = (Xc[t * D + d] - Xc[(b * q + k) * D + d]) * inv_ls[d];
+      r2 = fma(df, df, r2);
+    }
+    const double w = 4.0 * sbar[b * q * q + j * q + k] * kernel_dr2<KIND>(r2, variance);
+    for (int d = 0; d < D; ++d) g[d] = fma(w, (Xc[t * D + d] - Xc[(b * q + k) * D + d]) * inv_ls[d] * inv_ls[d], g[d]);
+  }
+  for (int d = 0; d < D; ++d) grad[t * D + d] += g[d];
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1g: gradient assembly.  grad[t][d] = sum_k dk/dr2(k,t) * 2 (x~_t,d - x~_k,d) / l_d *
 //                                       (c_mu[t] alpha[k] - 2 c_var[t] V[k,t])
 //   with V = K^-1 k* = Linv^T (Linv k*) (plain layout [t][ldv]).  One warp per candidate.

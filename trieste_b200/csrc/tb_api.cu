@@ -1495,6 +1495,141 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
   return 0;
 }
 
+// ---- value AND gradient of the batch Monte-Carlo EI (reverse pass of function.py:1181-1186) ----
+// chunk pipeline: K* digits -> A = Linv K* (stored) -> per-batch mean / cov (joint_kernel) -> qei_backward_kernel
+// (value, G_mu, Sigma_bar) -> V = K^-1 K* (dense digit GEMM over the same K* digits) -> per-batch mix V~ = Sigma_bar V
+// -> grad_kernel (the training-point sums) -> qei_cross_kernel (the K(x_b, x_b) term).
+template <int KIND>
+static void launch_qei_cross(tb_gp* gp, const double* xc, int64_t npts, int q, const double* sbar, double* grad) {
+  qei_cross_kernel<KIND><<<(unsigned)((npts + 127) / 128), 128, 0, gp->stream>>>(xc, gp->dInvLs.as<double>(), gp->D, npts, q, sbar,
+                                                                                 gp->variance, grad);
+}
+
+static int run_qei_grad(tb_gp* gp, const double* Xc, int64_t B, int q, const double* eps, int S, double eta, double jitter,
+                        double* out_val, double* out_grad) {
+  TB_CHECK(gp->cache_valid, "posterior cache is not built: call tb_gp_update_posterior_cache first");
+  TB_CHECK(q >= 1 && q <= 32, "batch size q must be in [1, 32]");
+  TB_CHECK(B >= 0, "negative batch count");
+  TB_CHECK(S >= 1 && eps, "need S >= 1 base samples");
+  TB_CHECK(jitter >= 0.0, "jitter must be non-negative");
+  TB_CHECK(gp->engine == 1 && gp->N <= 16384,
+           "gradients of the batch Monte-Carlo EI run on the int8 engine only (engine int8, N <= 16384)");
+  if (B == 0) return 0;
+  TB_CUDA(cudaSetDevice(gp->device));
+  cudaStream_t st = gp->stream;
+  const int D = gp->D;
+  const int QT = (q + 7) / 8, QP = QT * 8;
+  const int64_t lda = (int64_t)gp->NB * BM;
+  TB_TRY(ensure_ozaki(gp));
+  TB_TRY(ensure_kinv_digits(gp));
+  const int64_t max_tiles = chunk_tiles(gp);
+  int64_t nbc_cap = std::min<int64_t>(std::max<int64_t>(1, (max_tiles * BT) / q), B);
+  const int64_t cand_cap = nbc_cap * q;
+  const int64_t tiles_cap = (cand_cap + BT - 1) / BT;
+  TB_TRY(gp->sKs.reserve((size_t)tiles_cap * gp->nst * oz::S * oz::TILE));
+  TB_TRY(gp->sA.reserve((size_t)tiles_cap * BT * lda * sizeof(double)));  // A plain
+  TB_TRY(gp->sV.reserve((size_t)tiles_cap * BT * lda * sizeof(double)));  // V plain
+  TB_TRY(gp->sMean.reserve(sizeof(double) * tiles_cap * BT));
+  TB_TRY(gp->sMisc.reserve(sizeof(double) * 2 * cand_cap));  // c_mu, c_var
+  const bool xc_dev = is_device_ptr(Xc), val_dev = is_device_ptr(out_val), grad_dev = is_device_ptr(out_grad);
+  if (!xc_dev) TB_TRY(gp->sXc.reserve(sizeof(double) * cand_cap * D));
+  if (!grad_dev) TB_TRY(gp->sGrad.reserve(sizeof(double) * cand_cap * D));
+  tb::DevBuf beps, bcov, bmu, bsbar, bval;
+  struct Release {
+    std::vector<tb::DevBuf*> v;
+    ~Release() { for (auto* b : v) b->release(); }
+  } rel{{&beps, &bcov, &bmu, &bsbar, &bval}};
+  const double* eps_dev = eps;
+  if (!is_device_ptr(eps)) {
+    TB_TRY(beps.reserve(sizeof(double) * (size_t)q * S));
+    TB_CUDA(cudaMemcpyAsync(beps.p, eps, sizeof(double) * (size_t)q * S, cudaMemcpyHostToDevice, st));
+    eps_dev = beps.as<double>();
+  }
+  TB_TRY(bcov.reserve(sizeof(double) * (size_t)nbc_cap * q * q));
+  TB_TRY(bsbar.reserve(sizeof(double) * (size_t)nbc_cap * q * q));
+  TB_TRY(bmu.reserve(sizeof(double) * (size_t)cand_cap));
+  TB_TRY(bval.reserve(sizeof(double) * (size_t)nbc_cap));
+  TB_TRY(gp->sRun.reserve(16));
+  int* err = reinterpret_cast<int*>(gp->sRun.p);
+  TB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+  const size_t smem_joint = (size_t)JOINT_WARPS * (QP * QP + QP * D + QP) * sizeof(double);
+  const size_t smem_back = (size_t)QEIG_WARPS * (3 * q * q + 2 * q) * sizeof(double);
+  TB_CUDA(cudaFuncSetAttribute(qei_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_back));
+  JointRequest jr;
+  jr.mode = JOINT_PREDICT;
+  jr.q = q;
+
+  for (int64_t b0 = 0; b0 < B; b0 += nbc_cap) {
+    const int64_t nbc = std::min<int64_t>(nbc_cap, B - b0);
+    const int64_t mc = nbc * q;
+    const int tiles = (int)((mc + BT - 1) / BT);
+    const int64_t McPad = (int64_t)tiles * BT;
+    const double* xc_chunk;
+    if (xc_dev) {
+      xc_chunk = Xc + b0 * q * D;
+    } else {
+      TB_CUDA(cudaMemcpyAsync(gp->sXc.p, Xc + b0 * q * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, st));
+      xc_chunk = gp->sXc.as<double>();
+    }
+    TB_TRY(launch_kstar_digits(gp, xc_chunk, mc, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
+    const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
+    oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Goz, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
+        gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, Goz, McPad, gp->oz_out_scale,
+        oz_npass(gp), 0, nullptr, gp->sA.as<double>(), lda);
+    TB_LAUNCHED();
+    const int Gv = std::max(1, std::min(gp->NB, std::max((gp->NB + 7) / 8, (2 * 148 + tiles - 1) / tiles)));
+    oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Gv, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
+        gp->dKinvS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dKinvScale.as<double>(), gp->NB, gp->nst, Gv, McPad, gp->oz_out_scale,
+        oz_npass(gp), 1, nullptr, gp->sV.as<double>(), lda);
+    TB_LAUNCHED();
+    TB_CUDA(cudaGetLastError());
+    const int jblocks = (int)((nbc + JOINT_WARPS - 1) / JOINT_WARPS);
+    const int Nrows = (int)lda;
+    double* dmu = bmu.as<double>();
+    double* dcov = bcov.as<double>();
+    switch (gp->kernel) {
+      case TB_RBF: TB_TRY(launch_joint<TB_RBF>(gp, QT, jblocks, smem_joint, gp->sA.as<double>(), lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, jr, nullptr, dmu, dcov, nullptr, nullptr, err)); break;
+      case TB_MATERN12: TB_TRY(launch_joint<TB_MATERN12>(gp, QT, jblocks, smem_joint, gp->sA.as<double>(), lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, jr, nullptr, dmu, dcov, nullptr, nullptr, err)); break;
+      case TB_MATERN32: TB_TRY(launch_joint<TB_MATERN32>(gp, QT, jblocks, smem_joint, gp->sA.as<double>(), lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, jr, nullptr, dmu, dcov, nullptr, nullptr, err)); break;
+      default: TB_TRY(launch_joint<TB_MATERN52>(gp, QT, jblocks, smem_joint, gp->sA.as<double>(), lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, jr, nullptr, dmu, dcov, nullptr, nullptr, err)); break;
+    }
+    double* cmu = gp->sMisc.as<double>();
+    double* dval = val_dev ? out_val + b0 : bval.as<double>();
+    qei_backward_kernel<<<(unsigned)((nbc + QEIG_WARPS - 1) / QEIG_WARPS), QEIG_WARPS * 32, smem_back, st>>>(
+        dmu, dcov, nbc, q, eps_dev, S, eta, jitter, dval, cmu, cmu + mc, bsbar.as<double>(), err);
+    TB_LAUNCHED();
+    qei_mix_kernel<<<dim3((unsigned)((gp->N + 255) / 256), (unsigned)nbc), 256, 0, st>>>(gp->sV.as<double>(), lda, (int)gp->N, q,
+                                                                                        bsbar.as<double>());
+    TB_LAUNCHED();
+    double* gd = grad_dev ? out_grad + b0 * q * D : gp->sGrad.as<double>();
+    switch (gp->kernel) {
+      case TB_RBF: launch_grad_dp<TB_RBF>(gp, xc_chunk, mc, gd); break;
+      case TB_MATERN12: launch_grad_dp<TB_MATERN12>(gp, xc_chunk, mc, gd); break;
+      case TB_MATERN32: launch_grad_dp<TB_MATERN32>(gp, xc_chunk, mc, gd); break;
+      default: launch_grad_dp<TB_MATERN52>(gp, xc_chunk, mc, gd); break;
+    }
+    TB_LAUNCHED();
+    switch (gp->kernel) {
+      case TB_RBF: launch_qei_cross<TB_RBF>(gp, xc_chunk, mc, q, bsbar.as<double>(), gd); break;
+      case TB_MATERN12: launch_qei_cross<TB_MATERN12>(gp, xc_chunk, mc, q, bsbar.as<double>(), gd); break;
+      case TB_MATERN32: launch_qei_cross<TB_MATERN32>(gp, xc_chunk, mc, q, bsbar.as<double>(), gd); break;
+      default: launch_qei_cross<TB_MATERN52>(gp, xc_chunk, mc, q, bsbar.as<double>(), gd); break;
+    }
+    TB_LAUNCHED();
+    TB_CUDA(cudaGetLastError());
+    if (!val_dev) TB_CUDA(cudaMemcpyAsync(out_val + b0, bval.p, sizeof(double) * nbc, cudaMemcpyDeviceToHost, st));
+    if (!grad_dev) TB_CUDA(cudaMemcpyAsync(out_grad + b0 * q * D, gd, sizeof(double) * mc * D, cudaMemcpyDeviceToHost, st));
+    if (!xc_dev || !val_dev || !grad_dev) TB_CUDA(cudaStreamSynchronize(st));
+  }
+  int herr = 0;
+  TB_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
+  TB_CHECK(herr == 0, "Cholesky decomposition was not successful. The input might not be valid "
+                      "(covariance + jitter*I of a query batch is not positive definite)");
+  return 0;
+}
+
 }  // namespace tb
 
 extern "C" {
@@ -2164,6 +2299,25 @@ int tb_acq_batch_mc_ei(tb_gp* gp, const void* Xc, int64_t B, int q, const void* 
   TB_TRY(br.in(eps, (int64_t)q * S, &ed));
   TB_TRY(br.out(out, B, &od));
   TB_TRY(tb_acq_batch_mc_ei_f64(gp, xd, B, q, ed, S, eta, jitter, od));
+  return br.finish();
+}
+
+int tb_acq_batch_mc_ei_grad(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S, double eta, double jitter,
+                            void* out, void* grad) {
+  TB_CHECK(gp && (B == 0 || (Xc && eps && out && grad)), "tb_acq_batch_mc_ei_grad: null argument");
+  if (gp->dtype == TB_F64)
+    return tb::run_qei_grad(gp, (const double*)Xc, B, q, (const double*)eps, S, eta, jitter, (double*)out, (double*)grad);
+  if (B == 0) return 0;
+  TB_CHECK(q >= 1 && q <= 32 && S >= 1, "batch size q must be in [1, 32] and S >= 1");
+  TB_CUDA(cudaSetDevice(gp->device));
+  tb::F32Bridge br(gp);
+  const double *xd, *ed;
+  double *od, *gd;
+  TB_TRY(br.in(Xc, B * q * gp->D, &xd));
+  TB_TRY(br.in(eps, (int64_t)q * S, &ed));
+  TB_TRY(br.out(out, B, &od));
+  TB_TRY(br.out(grad, B * q * gp->D, &gd));
+  TB_TRY(tb::run_qei_grad(gp, xd, B, q, ed, S, eta, jitter, od, gd));
   return br.finish();
 }
 
