@@ -67,3 +67,31 @@ def test_bayesian_optimizer_driver_runs_the_readme_example():
     assert res.error is not None and len(res.history) == 0
     with pytest.raises(RuntimeError):
         res.try_get_final_dataset()
+
+
+def test_batch_ego_with_monte_carlo_qei_and_joint_gradient_optimizer():
+    # rule.py:291-297: a batch builder + num_query_points > 1 goes through batchify_joint over space ** q, driven by the
+    # device-side value+gradient of the MC-qEI; each step appends q rows to the cached factors
+    tb, space, ds, spec = _loop_setup()
+    from trieste_b200.acquisition import BatchMonteCarloExpectedImprovement
+    from trieste_b200.acquisition.optimizer import generate_continuous_optimizer
+    from trieste_b200.bayesian_optimizer import BayesianOptimizer
+    from trieste_b200.rule import EfficientGlobalOptimization
+
+    model = tb.GaussianProcessRegression(spec)
+    rule = EfficientGlobalOptimization(
+        BatchMonteCarloExpectedImprovement(128),
+        generate_continuous_optimizer(num_initial_samples=500, num_optimization_runs=8, optimizer_args={"maxiter": 40}),
+        num_query_points=3,
+    )
+    result = BayesianOptimizer(o.branin, space).optimize(4, ds, model, rule)
+    assert result.error is None, result.error
+    final = result.try_get_final_dataset()
+    assert len(final) == 5 + 4 * 3 and all(h.shape == (3, 2) for h in result.history)
+    assert model.last_update_appended  # the BO steps extended the cache instead of refactorising
+    assert final.observations.min() < ds.observations.min()
+    # the appended cache equals a from-scratch one on the final data
+    k = spec.kernel
+    om = o.build_model("matern52", final.query_points, final.observations, k.variance, k.lengthscales, spec.noise_variance,
+                       spec.mean_function.c)
+    np.testing.assert_allclose(model.get_cholesky(), om.L, rtol=0, atol=1e-5 * np.sqrt(k.variance))  # noise 1e-7: cond ~1e9

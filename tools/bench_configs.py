@@ -62,8 +62,12 @@ def c3():
     fn._sampler.set_eps(np.random.default_rng(3).standard_normal((q, S)))
     xd = torch.rand(B, q, 10, dtype=torch.float64, device="cuda")
     td = timed(lambda: fn(xd), reps=2)
+    Bg = 8192
+    xg = xd[:Bg]
+    tg = timed(lambda: fn.value_and_gradient(xg), reps=2)
     return {"config": "C3 Ackley-10 GPR N=4096 fp64 BatchMonteCarloExpectedImprovement q=8 S=512, 65536 q-batches",
-            "batches_per_s": B / td, "points_per_s": B * q / td, "ms": td * 1e3}
+            "batches_per_s": B / td, "points_per_s": B * q / td, "ms": td * 1e3,
+            "value_and_gradient_batches_per_s": Bg / tg, "value_and_gradient_points_per_s": Bg * q / tg, "ms_grad": tg * 1e3}
 
 
 def c4():

@@ -255,8 +255,10 @@ class GaussianProcessRegression:
         """Hyper-parameter training (models.py:256-292) is the once-per-step model fit and is OUT OF
         SCOPE of this engine: hyper-parameters are set through
         :meth:`set_hyperparameters`; the cache refresh that follows training in the reference
-        (models.py:290-291) is kept."""
-        self.update_posterior_cache()
+        (models.py:290-291) is kept — and skipped when the cache already matches the data and hyper-parameters (e.g. right
+        after an appending :meth:`update`)."""
+        if not getattr(self, "_cache_current", False):
+            self.update_posterior_cache()
 
     def set_hyperparameters(self, kernel: Optional[Stationary] = None, noise_variance: Optional[float] = None,
                             mean_constant: Optional[float] = None) -> None:
