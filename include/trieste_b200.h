@@ -134,6 +134,13 @@ int tb_acq_batch_mc_ei_grad(tb_gp* gp, const void* Xc, int64_t B, int q, const v
 int tb_gp_reparam_sample(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S,
                          double jitter, void* samples);
 
+/* model.sample over a large point set (GPflowPredictor.sample, interface.py:135-138 -> gpflow predict_f_samples: joint
+ * mean / full covariance, Cholesky of cov + jitter I, mean + L z) — the call behind ExactThompsonSampler
+ * (acquisition/sampler.py:85-123).  Xc [M,D] (handle dtype), z [S,M] standard-normal draws (double), out [S,M] (handle
+ * dtype).  1 ≤ M ≤ 16384; the covariance is built and factorised on the device (DMMA Gram + the blocked Cholesky of the
+ * cache build). */
+int tb_gp_sample_joint(tb_gp* gp, const void* Xc, int64_t M, const double* z, int S, double jitter, void* out);
+
 /* ---- streaming reductions over candidate scores ----------------------------------------------
  * tf.math.top_k as used by generate_initial_points (optimizer.py:321-335): values [M] →
  * top values [k] (descending, ties → lower index), indices [k].  Host or device pointers. */

@@ -206,3 +206,74 @@ def test_batch_mc_ei_gradient_drives_the_joint_optimizer():
     with pytest.raises(ValueError):
         fn.value_and_gradient(rnd[:2])
     nm.set_engine("int8")
+
+
+def test_independent_reparametrization_sampler_matches_its_definition():
+    # sampler.py:82-164: mean + sqrt(var + jitter) * eps, eps [S, 1] fixed until reset
+    from trieste_b200.sampler import IndependentReparametrizationSampler
+
+    om, nm = model_pair(o.hartmann_6, 120, 6)
+    s = IndependentReparametrizationSampler(50, nm, seed=1)
+    X = candidates(40, 6)
+    out = s.sample(X[:, None, :], jitter=1e-6)
+    assert out.shape == (40, 50, 1, 1)
+    eps = np.random.default_rng(1).standard_normal((50, 1))
+    mean, var = o.predict(om, X)
+    ref = mean[:, None, :, None] + np.sqrt(var + 1e-6)[:, None, :, None] * eps[None, :, :, None]
+    np.testing.assert_allclose(out, ref, rtol=1e-8, atol=1e-9 * np.sqrt(om.variance))
+    np.testing.assert_array_equal(out, s.sample(X[:, None, :], jitter=1e-6))  # same draws until reset
+    s.reset_sampler()
+    assert not np.array_equal(out, s.sample(X[:, None, :], jitter=1e-6))
+    with pytest.raises(ValueError):
+        s.sample(X.reshape(20, 2, 6))
+    with pytest.raises(ValueError):
+        IndependentReparametrizationSampler(0, nm)
+
+
+@pytest.mark.parametrize("engine", ["int8", "fp64"])
+@pytest.mark.parametrize("M", [33, 128, 300, 1000])
+def test_large_joint_samples_follow_the_oracle_posterior(M, engine):
+    # model.sample over more than 32 points (interface.py:135-138 -> predict_f_samples): the device path must reproduce
+    # mean + chol(cov + 1e-6 I) z for the z it drew
+    om, nm = model_pair(o.hartmann_6, 200, 6, engine=engine)
+    X = candidates(M, 6)
+    S = 7
+    out = nm.sample(X, S, seed=11)
+    assert out.shape == (S, M, 1)
+    z = np.random.default_rng(11).standard_normal((S, M))
+    mean, cov = o.predict_joint(om, X)
+    L = np.linalg.cholesky(cov[0] + 1e-6 * np.eye(M))
+    ref = mean[None, :, 0] + z @ L.T
+    np.testing.assert_allclose(out[..., 0], ref, rtol=0, atol=1e-6 * np.sqrt(om.variance))
+    with pytest.raises(ValueError):
+        nm.sample(X, 0)
+
+
+def test_exact_thompson_sampler_and_rule_default():
+    # acquisition/sampler.py:85-123 and rule.py:938-943
+    import trieste_b200 as tb
+    from trieste_b200.acquisition import MinValueEntropySearch
+    from trieste_b200.acquisition.sampler import ExactThompsonSampler, GumbelSampler
+    from trieste_b200.rule import DiscreteThompsonSampling
+
+    om, nm = model_pair(o.hartmann_6, 100, 6)
+    at = candidates(500, 6)
+    pts = ExactThompsonSampler().sample(nm, 5, at, seed=0)
+    assert pts.shape == (5, 6) and all(any(np.array_equal(p, a) for a in at) for p in pts)
+    mins = ExactThompsonSampler(sample_min_value=True).sample(nm, 5, at, seed=0)
+    assert mins.shape == (5, 1)
+    # same seed -> the minimum values belong to the minimisers drawn above
+    samples = nm.sample(at, 5, seed=0)[..., 0]
+    np.testing.assert_array_equal(mins[:, 0], samples.min(axis=1))
+    np.testing.assert_array_equal(pts, at[samples.argmin(axis=1)])
+    # sample minima are below the posterior-mean minimum on average (they include the posterior spread)
+    assert mins.mean() < o.predict(om, at)[0].min() + 1e-9
+    rule = DiscreteThompsonSampling(400, 3)
+    q = rule.acquire_single(tb.Box([0.0] * 6, [1.0] * 6), nm, tb.Dataset(om.X, om.y))
+    assert q.shape == (3, 6)
+    with pytest.raises(ValueError):
+        DiscreteThompsonSampling(400, 3, thompson_sampler=GumbelSampler(True))
+    # the reference's default min-value sampler for MES now works too
+    builder = MinValueEntropySearch(tb.Box([0.0] * 6, [1.0] * 6), 4, 300, min_value_sampler=ExactThompsonSampler(True))
+    fn = builder.prepare_acquisition_function(nm, tb.Dataset(om.X, om.y))
+    assert fn.samples.shape == (4, 1) and np.isfinite(fn(at[:, None, :])).all()

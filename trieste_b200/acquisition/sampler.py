@@ -1,5 +1,6 @@
 """Thompson samplers over a discrete candidate set — mirrors trieste/acquisition/sampler.py
-(``ThompsonSampler`` :34-82, ``GumbelSampler`` :126-211, ``ThompsonSamplerFromTrajectory`` :214-273)."""
+(``ThompsonSampler`` :34-82, ``ExactThompsonSampler`` :85-123, ``GumbelSampler`` :126-211,
+``ThompsonSamplerFromTrajectory`` :214-273)."""
 from __future__ import annotations
 
 import math
@@ -30,6 +31,20 @@ class ThompsonSampler:
         if at_np.ndim != 2:
             raise ValueError(f"at must have shape [N, D], got {at_np.shape}")
         return at_np
+
+
+class ExactThompsonSampler(ThompsonSampler):
+    """sampler.py:85-123: joint samples of the model at all ``at`` points (``model.sample``: full covariance + Cholesky,
+    O(N^3) in the number of points — the reference's default for DiscreteThompsonSampling and MinValueEntropySearch,
+    practical up to a few thousand points; at most 16384 here), reduced per sample to the minimum value ([S, 1]) or
+    the minimiser ([S, D])."""
+
+    def sample(self, model, sample_size: int, at, select_output=None, seed: Optional[int] = None) -> np.ndarray:
+        at_np = self._check(sample_size, at)
+        samples = np.asarray(model.sample(at_np, sample_size, seed=seed), dtype=np.float64)[..., 0]  # [S, N]
+        if self._sample_min_value:
+            return samples.min(axis=1, keepdims=True)  # [S, 1]
+        return at_np[np.argmin(samples, axis=1)]  # [S, D]
 
 
 class ThompsonSamplerFromTrajectory(ThompsonSampler):

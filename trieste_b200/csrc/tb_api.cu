@@ -1495,6 +1495,154 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
   return 0;
 }
 
+// ---- joint samples over a LARGE point set (interface.py:135-138 -> gpflow predict_f_samples; the ExactThompsonSampler's
+// model.sample, acquisition/sampler.py:85-123): full posterior covariance, blocked Cholesky, mean + L z ----
+// cov[i][j] = k(x_i, x_j) - sum_k A[i][k] A[j][k]  (+ jitter on the clipped diagonal); lower 128-tiles, mirrored
+template <int KIND>
+__global__ void __launch_bounds__(fac::THREADS)
+posterior_cov_kernel(const double* __restrict__ A, int64_t lda, int Nk, const double* __restrict__ Xc,
+                     const double* __restrict__ inv_ls, int D, int64_t M, double variance, double jitter,
+                     double* __restrict__ cov) {
+  extern __shared__ __align__(16) double sm[];
+  const int tj = blockIdx.x, ti = blockIdx.y;
+  if (ti < tj) return;
+  const int64_t r0 = (int64_t)ti * fac::FB, c0 = (int64_t)tj * fac::FB;
+  double acc[8][4][2];
+  fac::zero_acc(acc);
+  fac::dmma_tile<true, true>([&](int m, int k) { return (r0 + m < M) ? A[(r0 + m) * lda + k] : 0.0; },
+                             [&](int k, int n) { return (c0 + n < M) ? A[(c0 + n) * lda + k] : 0.0; }, 0, Nk, acc, sm);
+  fac::for_each_acc(acc, [&](int m, int n, double& v) {
+    const int64_t i = r0 + m, j = c0 + n;
+    if (i >= M || j >= M || i < j) return;
+    double val;
+    if (i == j) {
+      val = fmax(variance - v, 1e-12) + jitter;
+    } else {
+      double r2 = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const double df = (Xc[i * D + d] - Xc[j * D + d]) * inv_ls[d];
+        r2 = fma(df, df, r2);
+      }
+      val = kernel_from_r2<KIND>(r2, variance) - v;
+    }
+    cov[i + j * M] = val;
+    cov[j + i * M] = val;
+  });
+}
+
+// out[s][i] += mean[i]
+__global__ void add_mean_rows_kernel(double* __restrict__ out, const double* __restrict__ mean, int64_t M, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < total) out[e] += mean[e % M];
+}
+
+static int run_sample_joint(tb_gp* gp, const double* Xc, int64_t M, const double* z, int S, double jitter, double* out) {
+  TB_CHECK(gp->cache_valid, "posterior cache is not built: call tb_gp_update_posterior_cache first");
+  TB_CHECK(M >= 1 && M <= 16384, "tb_gp_sample_joint: between 1 and 16384 points");
+  TB_CHECK(S >= 1 && z && out && Xc, "tb_gp_sample_joint: need S >= 1 standard-normal draws per point");
+  TB_CHECK(jitter >= 0.0, "jitter must be non-negative");
+  TB_CUDA(cudaSetDevice(gp->device));
+  cudaStream_t st = gp->stream;
+  const int D = gp->D;
+  const int64_t lda = (int64_t)gp->NB * BM;
+  const int tiles = (int)((M + BT - 1) / BT);
+  const int64_t McPad = (int64_t)tiles * BT;
+  const bool oz_path = gp->engine == 1 && gp->N <= 16384;
+  if (oz_path) TB_TRY(ensure_ozaki(gp));
+  TB_TRY(gp->sKs.reserve(std::max((size_t)tiles * gp->nkc * PANEL * sizeof(double), (size_t)tiles * gp->nst * oz::S * oz::TILE)));
+  TB_TRY(gp->sA.reserve((size_t)McPad * lda * sizeof(double)));
+  TB_TRY(gp->sMean.reserve(sizeof(double) * McPad));
+  tb::DevBuf bx, bcov, bz, bout, bdinv;
+  struct Release {
+    std::vector<tb::DevBuf*> v;
+    ~Release() { for (auto* b : v) b->release(); }
+  } rel{{&bx, &bcov, &bz, &bout, &bdinv}};
+  const double* xc = Xc;
+  if (!is_device_ptr(Xc)) {
+    TB_TRY(bx.reserve(sizeof(double) * M * D));
+    TB_CUDA(cudaMemcpyAsync(bx.p, Xc, sizeof(double) * M * D, cudaMemcpyHostToDevice, st));
+    xc = bx.as<double>();
+  }
+  if (oz_path) {
+    TB_TRY(launch_kstar_digits(gp, xc, M, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
+    const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
+    oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Goz, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
+        gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, Goz, McPad, gp->oz_out_scale,
+        oz_npass(gp), 0, nullptr, gp->sA.as<double>(), lda);
+  } else {
+    const int G = pick_groups(gp, tiles);
+    TB_TRY(launch_kstar(gp, xc, M, tiles, gp->sKs.as<double>(), gp->sMean.as<double>()));
+    trigemm_kernel<false, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
+        gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, nullptr, nullptr, gp->sA.as<double>(), lda);
+  }
+  TB_LAUNCHED();
+  TB_TRY(bcov.reserve(sizeof(double) * M * M));
+  {
+    const unsigned t = (unsigned)((M + fac::FB - 1) / fac::FB);
+    const double* A = gp->sA.as<double>();
+    const double* il = gp->dInvLs.as<double>();
+    double* cov = bcov.as<double>();
+#define TB_PCOV(KIND)                                                                                                              TB_CUDA(cudaFuncSetAttribute(posterior_cov_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));   posterior_cov_kernel<KIND><<<dim3(t, t), fac::THREADS, fac::GEMM_SMEM, st>>>(A, lda, (int)lda, xc, il, D, M, gp->variance, jitter, cov)
+    switch (gp->kernel) {
+      case TB_RBF: TB_PCOV(TB_RBF); break;
+      case TB_MATERN12: TB_PCOV(TB_MATERN12); break;
+      case TB_MATERN32: TB_PCOV(TB_MATERN32); break;
+      default: TB_PCOV(TB_MATERN52); break;
+    }
+#undef TB_PCOV
+    TB_LAUNCHED();
+  }
+  // blocked Cholesky of the covariance with the cache-build kernels (factor.cuh)
+  const int nbk = (int)((M + fac::FB - 1) / fac::FB);
+  TB_TRY(bdinv.reserve(sizeof(double) * (size_t)nbk * fac::FB * fac::FB));
+  TB_TRY(gp->dInfo.reserve(sizeof(int)));
+  TB_CUDA(cudaMemsetAsync(gp->dInfo.p, 0, sizeof(int), st));
+  {
+    double* C = bcov.as<double>();
+    const size_t diag_smem = sizeof(double) * fac::FB * (fac::FB + 1);
+    for (int jb = 0; jb < nbk; ++jb) {
+      const int j0 = jb * fac::FB;
+      fac::chol_diag_kernel<<<1, fac::THREADS, diag_smem, st>>>(C, M, j0, bdinv.as<double>(), gp->dInfo.as<int>());
+      TB_LAUNCHED();
+      const int64_t below = M - (int64_t)(j0 + fac::FB);
+      if (below > 0) {
+        const unsigned t = (unsigned)((below + fac::FB - 1) / fac::FB);
+        fac::chol_panel_kernel<<<t, fac::THREADS, fac::GEMM_SMEM, st>>>(C, M, j0, bdinv.as<double>());
+        TB_LAUNCHED();
+        fac::chol_syrk_kernel<<<dim3(t, t), fac::THREADS, fac::GEMM_SMEM, st>>>(C, M, j0);
+        TB_LAUNCHED();
+      }
+    }
+  }
+  int info = 0;
+  TB_CUDA(cudaMemcpyAsync(&info, gp->dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
+  TB_CHECK(info == 0, "Cholesky decomposition was not successful. The input might not be valid "
+                      "(joint covariance + jitter*I is not positive definite at leading minor " + std::to_string(info) + ")");
+  // samples = mean + L z
+  const double* zd = z;
+  if (!is_device_ptr(z)) {
+    TB_TRY(bz.reserve(sizeof(double) * (size_t)S * M));
+    TB_CUDA(cudaMemcpyAsync(bz.p, z, sizeof(double) * (size_t)S * M, cudaMemcpyHostToDevice, st));
+    zd = bz.as<double>();
+  }
+  const bool out_dev = is_device_ptr(out);
+  double* od = out;
+  if (!out_dev) {
+    TB_TRY(bout.reserve(sizeof(double) * (size_t)S * M));
+    od = bout.as<double>();
+  }
+  trmv_lower_cols_kernel<<<dim3((unsigned)((M + 127) / 128), (unsigned)S), 128, 0, st>>>(bcov.as<double>(), M, M, zd, M, od, M);
+  TB_LAUNCHED();
+  add_mean_rows_kernel<<<(unsigned)(((int64_t)S * M + 255) / 256), 256, 0, st>>>(od, gp->sMean.as<double>(), M, (int64_t)S * M);
+  TB_LAUNCHED();
+  if (!out_dev) TB_CUDA(cudaMemcpyAsync(out, od, sizeof(double) * (size_t)S * M, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---- value AND gradient of the batch Monte-Carlo EI (reverse pass of function.py:1181-1186) ----
 // chunk pipeline: K* digits -> A = Linv K* (stored) -> per-batch mean / cov (joint_kernel) -> qei_backward_kernel
 // (value, G_mu, Sigma_bar) -> V = K^-1 K* (dense digit GEMM over the same K* digits) -> per-batch mix V~ = Sigma_bar V
@@ -2299,6 +2447,20 @@ int tb_acq_batch_mc_ei(tb_gp* gp, const void* Xc, int64_t B, int q, const void* 
   TB_TRY(br.in(eps, (int64_t)q * S, &ed));
   TB_TRY(br.out(out, B, &od));
   TB_TRY(tb_acq_batch_mc_ei_f64(gp, xd, B, q, ed, S, eta, jitter, od));
+  return br.finish();
+}
+
+int tb_gp_sample_joint(tb_gp* gp, const void* Xc, int64_t M, const double* z, int S, double jitter, void* out) {
+  TB_CHECK(gp && Xc && z && out, "tb_gp_sample_joint: null argument");
+  if (gp->dtype == TB_F64) return tb::run_sample_joint(gp, (const double*)Xc, M, z, S, jitter, (double*)out);
+  TB_CHECK(M >= 1 && S >= 1, "tb_gp_sample_joint: need at least one point and one draw");
+  TB_CUDA(cudaSetDevice(gp->device));
+  tb::F32Bridge br(gp);
+  const double* xd;
+  double* od;
+  TB_TRY(br.in(Xc, M * gp->D, &xd));
+  TB_TRY(br.out(out, (int64_t)S * M, &od));
+  TB_TRY(tb::run_sample_joint(gp, xd, M, z, S, jitter, od));
   return br.finish();
 }
 

@@ -206,16 +206,30 @@ class GaussianProcessRegression:
         return mean, var + self._spec.noise_variance
 
     def sample(self, query_points, num_samples: int, seed: Optional[int] = None):
-        """[..., N, D] -> [..., S, N, 1]: joint samples through ``predict_joint`` + Cholesky
-        (interface.py:135-138 -> gpflow predict_f_samples)."""
+        """[..., N, D] -> [..., S, N, 1]: joint samples (interface.py:135-138 -> gpflow predict_f_samples: full covariance
+        + jitter 1e-6, Cholesky, mean + L z).  Sets of up to 32 points go through the batched ``predict_joint`` kernels,
+        larger ones (the ExactThompsonSampler's case) through ``tb_gp_sample_joint`` — covariance and Cholesky on the
+        device, one set at a time."""
         if num_samples <= 0:
             raise ValueError(f"num_samples must be positive, got {num_samples}")
         x = np.asarray(query_points, dtype=self._dtype)
+        if x.ndim < 2:
+            raise ValueError(f"query points must have rank >= 2, got shape {x.shape}")
+        self._check_dim(x)
         q = x.shape[-2]
-        eps = np.random.default_rng(seed).standard_normal((q, num_samples))
-        from .sampler import _reparam_sample
+        rng = np.random.default_rng(seed)
+        if q <= 32:
+            from .sampler import _reparam_sample
 
-        return _reparam_sample(self, x, eps, 1e-6)
+            return _reparam_sample(self, x, rng.standard_normal((q, num_samples)), 1e-6)
+        flat = np.ascontiguousarray(x.reshape((-1,) + x.shape[-2:]))
+        out = np.empty((flat.shape[0], num_samples, q), dtype=self._dtype)
+        for i in range(flat.shape[0]):
+            z = np.ascontiguousarray(rng.standard_normal((num_samples, q)))
+            _lib.check(
+                _lib.lib().tb_gp_sample_joint(self._h, flat[i].ctypes.data, q, z.ctypes.data, num_samples, 1e-6, out[i].ctypes.data)
+            )
+        return out.reshape(x.shape[:-2] + (num_samples, q, 1))
 
     def log(self, dataset: Optional[Dataset] = None) -> None:
         """TensorBoard summaries in the reference (models/utils.py:33-107): observability only."""

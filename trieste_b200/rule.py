@@ -10,7 +10,7 @@ import numpy as np
 from .acquisition.function import ExpectedImprovement
 from .acquisition.interface import OBJECTIVE, AcquisitionFunctionBuilder, SingleModelAcquisitionBuilder
 from .acquisition.optimizer import automatic_optimizer_selector, batchify_joint
-from .acquisition.sampler import ThompsonSamplerFromTrajectory
+from .acquisition.sampler import ExactThompsonSampler, ThompsonSamplerFromTrajectory  # noqa: F401
 from .data import Dataset
 from .space import SearchSpace
 
@@ -66,7 +66,17 @@ class DiscreteThompsonSampling:
             raise ValueError(f"Search space must be greater than 0, got {num_search_space_samples}")
         if not num_query_points > 0:
             raise ValueError(f"Number of query points must be greater than 0, got {num_query_points}")
-        self._thompson_sampler = thompson_sampler if thompson_sampler is not None else ThompsonSamplerFromTrajectory()
+        if thompson_sampler is not None:
+            if thompson_sampler.sample_min_value:
+                raise ValueError(
+                    "Thompson sampling requires a thompson_sampler that samples minimizers, not just minimum values. "
+                    "However the passed sampler has sample_min_value=True."
+                )
+        else:
+            # rule.py:942-943: the reference default — exact joint samples, O(M^3) in the candidate count; pass
+            # ThompsonSamplerFromTrajectory() for large candidate sets (BASELINE config 4)
+            thompson_sampler = ExactThompsonSampler(sample_min_value=False)
+        self._thompson_sampler = thompson_sampler
         self._num_search_space_samples = num_search_space_samples
         self._num_query_points = num_query_points
 

@@ -27,6 +27,47 @@ def _reparam_sample(model: GaussianProcessRegression, at, eps: np.ndarray, jitte
     return out.reshape(lead + (S, q, 1))
 
 
+class IndependentReparametrizationSampler:
+    """sampler.py:82-164: ``x -> mu(x) + eps * sigma(x)`` with base samples eps [S, 1] fixed until
+    :meth:`reset_sampler`; batch size one only.  One batched GPU ``predict`` per call; the S-fold broadcast is host
+    arithmetic on the [..., 1] outputs (the reference's ``qmc=True`` Sobol option is not provided — draws are from a
+    NumPy generator or injected with :meth:`set_eps`)."""
+
+    def __init__(self, sample_size: int, model, seed: Optional[int] = None):
+        if sample_size <= 0:
+            raise ValueError(f"sample_size must be positive, got {sample_size}")
+        self._sample_size = sample_size
+        self._model = model
+        self._rng = np.random.default_rng(seed)
+        self._eps: Optional[np.ndarray] = None  # [S, 1]
+        self._initialized = False
+
+    def set_eps(self, eps) -> None:
+        eps = np.asarray(eps, dtype=np.float64).reshape(-1, 1)
+        if eps.shape[0] != self._sample_size:
+            raise ValueError(f"eps must hold {self._sample_size} base samples, got {eps.shape[0]}")
+        self._eps = eps
+        self._initialized = True
+
+    def sample(self, at, *, jitter: float = JITTER):
+        """at [..., 1, D] -> [..., S, 1, 1]."""
+        shape = tuple(np.shape(at))
+        if len(shape) < 2 or shape[-2] != 1:
+            raise ValueError(f"IndependentReparametrizationSampler only supports batch sizes of one, got shape {shape}")
+        if jitter < 0:
+            raise ValueError(f"jitter must be non-negative, got {jitter}")
+        x = at.detach().cpu().numpy() if hasattr(at, "detach") else np.asarray(at)
+        mean, var = self._model.predict(x[..., None, :, :])  # [..., 1, 1, 1]
+        mean, var = np.asarray(mean, dtype=np.float64), np.asarray(var, dtype=np.float64)
+        if not self._initialized or self._eps is None:
+            self._eps = self._rng.standard_normal((self._sample_size, 1))
+            self._initialized = True
+        return mean + np.sqrt(var + jitter) * self._eps[:, None, :]  # [..., S, 1, 1]
+
+    def reset_sampler(self) -> None:
+        self._initialized = False
+
+
 class BatchReparametrizationSampler:
     """sampler.py:167-287.  The base samples ``eps`` [L=1, q, S] are drawn once (NumPy generator —
     the reference uses tf.random.normal; RNG streams are never bit-compatible, so ``eps`` can also be
