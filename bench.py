@@ -388,6 +388,9 @@ def main():
                 "kernel": kernel_name, "launches_timed": tg_n.value,
                 "avg_launch_ms": avg_launch_s * 1e3, "candidates_per_launch": cand_per_launch,
                 "peak_source": peak_src,
+                # transparency: the same achieved figure against the two other candidates for an int8 denominator
+                "frac_of_nominal_int8_4500": (achieved / 4500.0) if args.engine == "int8" else None,
+                "frac_of_measured_int8_burst_3838": (achieved / 3838.0) if args.engine == "int8" else None,
                 "fp64_equivalent_tflops": fp64_eq_tf, "fp64_dgemm_peak_tflops": dgemm_tf,
                 "hbm": {"algorithmic_bytes_per_candidate": bytes_per_cand,
                         "achieved_gbs": bytes_per_cand * cand_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else None,
