@@ -141,6 +141,11 @@ int tb_gp_reparam_sample(tb_gp* gp, const void* Xc, int64_t B, int q, const void
  * cache build). */
 int tb_gp_sample_joint(tb_gp* gp, const void* Xc, int64_t M, const double* z, int S, double jitter, void* out);
 
+/* covariance_between_points_encoded (models/gpflow/models.py:188-254): posterior covariance between two point sets,
+ * K12 − Kx1 (K + σ²I)⁻¹ Kx2, no clipping.  X1 [M1,D], X2 [M2,D], out [M1,M2] row-major (handle dtype); M1 + M2 ≤ 16384.
+ * (The reference's leading dimensions of X1 are flattened into M1 by the caller.) */
+int tb_gp_covariance_between_points(tb_gp* gp, const void* X1, int64_t M1, const void* X2, int64_t M2, void* out);
+
 /* ---- streaming reductions over candidate scores ----------------------------------------------
  * tf.math.top_k as used by generate_initial_points (optimizer.py:321-335): values [M] →
  * top values [k] (descending, ties → lower index), indices [k].  Host or device pointers. */

@@ -156,6 +156,19 @@ def predict_batched(m: GPRModel, Xq: np.ndarray, chunk: int = 16384):
     return np.concatenate(means), np.concatenate(vars_)
 
 
+def covariance_between_points(m: GPRModel, X1: np.ndarray, X2: np.ndarray) -> np.ndarray:
+    """trieste/models/gpflow/models.py:188-254: ``K12 - Kx1 (K + noise I)^-1 Kx2`` via two triangular solves against
+    L = chol(K + noise I).  X1 [..., N, D], X2 [M, D] -> [..., 1, N, M] (no clipping)."""
+    X1 = np.asarray(X1, dtype=m.dtype)
+    X2 = np.asarray(X2, dtype=m.dtype)
+    lead, n = X1.shape[:-2], X1.shape[-2]
+    flat = X1.reshape(-1, X1.shape[-1])
+    A1 = sla.solve_triangular(m.L, kernel_matrix(m.kind, m.X, flat, m.variance, m.lengthscales), lower=True, check_finite=False)
+    A2 = sla.solve_triangular(m.L, kernel_matrix(m.kind, m.X, X2, m.variance, m.lengthscales), lower=True, check_finite=False)
+    cov = kernel_matrix(m.kind, flat, X2, m.variance, m.lengthscales) - A1.T @ A2
+    return cov.reshape(lead + (n, X2.shape[0]))[..., None, :, :]
+
+
 def posterior_gradients(m: GPRModel, Xq: np.ndarray):
     """d mean / d x* and d var / d x* (what ``tfp.math.value_and_gradient`` differentiates at
     trieste/acquisition/optimizer.py:621-629).  Analytic: dmean = (dk*/dx)^T alpha,

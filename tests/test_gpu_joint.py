@@ -277,3 +277,24 @@ def test_exact_thompson_sampler_and_rule_default():
     builder = MinValueEntropySearch(tb.Box([0.0] * 6, [1.0] * 6), 4, 300, min_value_sampler=ExactThompsonSampler(True))
     fn = builder.prepare_acquisition_function(nm, tb.Dataset(om.X, om.y))
     assert fn.samples.shape == (4, 1) and np.isfinite(fn(at[:, None, :])).all()
+
+
+@pytest.mark.parametrize("engine", ["int8", "fp64"])
+@pytest.mark.parametrize("kind", ["rbf", "matern52"])
+def test_covariance_between_points_matches_oracle(kind, engine):
+    # models.py:188-254 (reference test: tests/unit/models/gpflow/test_models.py:282-305)
+    om, nm = model_pair(o.hartmann_6, 300, 6, kind=kind, engine=engine)
+    rng = np.random.default_rng(0)
+    X1 = rng.uniform(size=(3, 50, 6))
+    X2 = np.concatenate([rng.uniform(size=(200, 6)), X1[0, :5]])  # shared points: the exact posterior variance on them
+    cov = nm.covariance_between_points(X1, X2)
+    ref = o.covariance_between_points(om, X1, X2)
+    assert cov.shape == (3, 1, 50, 205)
+    np.testing.assert_allclose(cov, ref, rtol=0, atol=1e-9 * om.variance)
+    one = nm.covariance_between_points(X1[0, :1], X2[:1])
+    assert one.shape == (1, 1, 1)
+    np.testing.assert_allclose(one, ref[0, :, :1, :1], rtol=0, atol=1e-9 * om.variance)
+    with pytest.raises(ValueError):
+        nm.covariance_between_points(X1, X2[None])  # query_points_2 must have rank two
+    with pytest.raises(ValueError):
+        nm.covariance_between_points(X1[..., :5], X2)  # wrong input dimension

@@ -244,3 +244,16 @@ def test_batch_mc_ei_gradient_restatement_matches_finite_differences(kind):
             fd[j, d] = (o.batch_monte_carlo_expected_improvement(m, Xp[None], eps[None], eta)[0, 0]
                         - o.batch_monte_carlo_expected_improvement(m, Xm[None], eps[None], eta)[0, 0]) / (2 * h)
     np.testing.assert_allclose(g, fd, rtol=1e-5, atol=1e-7 * np.abs(g).max())
+
+
+def test_covariance_between_points_restatement_is_consistent_with_predict_joint():
+    # reference test_gpflow_models_pairwise_covariance (tests/unit/models/gpflow/test_models.py:282-305): the pairwise
+    # covariance of a set with itself equals the off-diagonal blocks of the joint prediction over the union
+    m = o.synthetic_model(o.hartmann_6, 50, 6)
+    rng = np.random.default_rng(0)
+    X1, X2 = rng.uniform(size=(2, 4, 6)), rng.uniform(size=(3, 6))
+    cov = o.covariance_between_points(m, X1, X2)
+    assert cov.shape == (2, 1, 4, 3)
+    for b in range(2):
+        _, joint = o.predict_f(m, np.concatenate([X1[b], X2]), full_cov=True)
+        np.testing.assert_allclose(cov[b, 0], joint[:4, 4:], rtol=1e-10, atol=1e-12)

@@ -1495,6 +1495,105 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
   return 0;
 }
 
+// A = Linv K(X, Xc) for M device-resident points, stored plain ([point][lda], lda = NB*128) in gp->sA; posterior means in
+// gp->sMean.  One launch over all M points (callers bound M).
+static int compute_a_plain(tb_gp* gp, const double* xc_dev, int64_t M) {
+  cudaStream_t st = gp->stream;
+  const int64_t lda = (int64_t)gp->NB * BM;
+  const int tiles = (int)((M + BT - 1) / BT);
+  const int64_t McPad = (int64_t)tiles * BT;
+  const bool oz_path = gp->engine == 1 && gp->N <= 16384;
+  if (oz_path) TB_TRY(ensure_ozaki(gp));
+  TB_TRY(gp->sKs.reserve(std::max((size_t)tiles * gp->nkc * PANEL * sizeof(double), (size_t)tiles * gp->nst * oz::S * oz::TILE)));
+  TB_TRY(gp->sA.reserve((size_t)McPad * lda * sizeof(double)));
+  TB_TRY(gp->sMean.reserve(sizeof(double) * McPad));
+  if (oz_path) {
+    TB_TRY(launch_kstar_digits(gp, xc_dev, M, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
+    const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
+    oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Goz, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
+        gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, Goz, McPad, gp->oz_out_scale,
+        oz_npass(gp), 0, nullptr, gp->sA.as<double>(), lda);
+  } else {
+    const int G = pick_groups(gp, tiles);
+    TB_TRY(launch_kstar(gp, xc_dev, M, tiles, gp->sKs.as<double>(), gp->sMean.as<double>()));
+    trigemm_kernel<false, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
+        gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, nullptr, nullptr, gp->sA.as<double>(), lda);
+  }
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// out[i][j] = k(x1_i, x2_j) - sum_k A1[i][k] A2[j][k]: posterior covariance between two point sets, row-major [M1, M2]
+// (covariance_between_points_encoded, models/gpflow/models.py:188-254: K12 - Kx1 (K + s^2 I)^-1 Kx2, no clipping)
+template <int KIND>
+__global__ void __launch_bounds__(fac::THREADS)
+cross_cov_kernel(const double* __restrict__ A1, const double* __restrict__ A2, int64_t lda, int Nk, const double* __restrict__ X1,
+                 const double* __restrict__ X2, const double* __restrict__ inv_ls, int D, int64_t M1, int64_t M2, double variance,
+                 double* __restrict__ out) {
+  extern __shared__ __align__(16) double sm[];
+  const int64_t r0 = (int64_t)blockIdx.y * fac::FB, c0 = (int64_t)blockIdx.x * fac::FB;
+  double acc[8][4][2];
+  fac::zero_acc(acc);
+  fac::dmma_tile<true, true>([&](int m, int k) { return (r0 + m < M1) ? A1[(r0 + m) * lda + k] : 0.0; },
+                             [&](int k, int n) { return (c0 + n < M2) ? A2[(c0 + n) * lda + k] : 0.0; }, 0, Nk, acc, sm);
+  fac::for_each_acc(acc, [&](int m, int n, double& v) {
+    const int64_t i = r0 + m, j = c0 + n;
+    if (i >= M1 || j >= M2) return;
+    double r2 = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double df = (X1[i * D + d] - X2[j * D + d]) * inv_ls[d];
+      r2 = fma(df, df, r2);
+    }
+    out[i * M2 + j] = kernel_from_r2<KIND>(r2, variance) - v;
+  });
+}
+
+static int run_cross_cov(tb_gp* gp, const double* X1, int64_t M1, const double* X2, int64_t M2, double* out) {
+  TB_CHECK(gp->cache_valid, "posterior cache is not built: call tb_gp_update_posterior_cache first");
+  TB_CHECK(M1 >= 1 && M2 >= 1 && M1 + M2 <= 16384, "tb_gp_covariance_between_points: between 1 and 16384 points in total");
+  TB_CUDA(cudaSetDevice(gp->device));
+  cudaStream_t st = gp->stream;
+  const int D = gp->D;
+  const int64_t lda = (int64_t)gp->NB * BM, M = M1 + M2;
+  tb::DevBuf bx, bout;
+  struct Release {
+    std::vector<tb::DevBuf*> v;
+    ~Release() { for (auto* b : v) b->release(); }
+  } rel{{&bx, &bout}};
+  TB_TRY(bx.reserve(sizeof(double) * M * D));  // [X1; X2] contiguous on the device
+  TB_CUDA(cudaMemcpyAsync(bx.p, X1, sizeof(double) * M1 * D, cudaMemcpyDefault, st));
+  TB_CUDA(cudaMemcpyAsync(bx.as<double>() + M1 * D, X2, sizeof(double) * M2 * D, cudaMemcpyDefault, st));
+  TB_TRY(compute_a_plain(gp, bx.as<double>(), M));
+  const bool out_dev = is_device_ptr(out);
+  double* od = out;
+  if (!out_dev) {
+    TB_TRY(bout.reserve(sizeof(double) * (size_t)M1 * M2));
+    od = bout.as<double>();
+  }
+  const double* A1 = gp->sA.as<double>();
+  const double* A2 = A1 + M1 * lda;
+  const double* x1 = bx.as<double>();
+  const double* x2 = x1 + M1 * D;
+  const double* il = gp->dInvLs.as<double>();
+  const dim3 grid((unsigned)((M2 + fac::FB - 1) / fac::FB), (unsigned)((M1 + fac::FB - 1) / fac::FB));
+#define TB_CCOV(KIND)                                                                                                        \
+  TB_CUDA(cudaFuncSetAttribute(cross_cov_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM)); \
+  cross_cov_kernel<KIND><<<grid, fac::THREADS, fac::GEMM_SMEM, st>>>(A1, A2, lda, (int)lda, x1, x2, il, D, M1, M2, gp->variance, od)
+  switch (gp->kernel) {
+    case TB_RBF: TB_CCOV(TB_RBF); break;
+    case TB_MATERN12: TB_CCOV(TB_MATERN12); break;
+    case TB_MATERN32: TB_CCOV(TB_MATERN32); break;
+    default: TB_CCOV(TB_MATERN52); break;
+  }
+#undef TB_CCOV
+  TB_LAUNCHED();
+  if (!out_dev) TB_CUDA(cudaMemcpyAsync(out, od, sizeof(double) * (size_t)M1 * M2, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---- joint samples over a LARGE point set (interface.py:135-138 -> gpflow predict_f_samples; the ExactThompsonSampler's
 // model.sample, acquisition/sampler.py:85-123): full posterior covariance, blocked Cholesky, mean + L z ----
 // cov[i][j] = k(x_i, x_j) - sum_k A[i][k] A[j][k]  (+ jitter on the clipped diagonal); lower 128-tiles, mirrored
@@ -1545,13 +1644,6 @@ static int run_sample_joint(tb_gp* gp, const double* Xc, int64_t M, const double
   cudaStream_t st = gp->stream;
   const int D = gp->D;
   const int64_t lda = (int64_t)gp->NB * BM;
-  const int tiles = (int)((M + BT - 1) / BT);
-  const int64_t McPad = (int64_t)tiles * BT;
-  const bool oz_path = gp->engine == 1 && gp->N <= 16384;
-  if (oz_path) TB_TRY(ensure_ozaki(gp));
-  TB_TRY(gp->sKs.reserve(std::max((size_t)tiles * gp->nkc * PANEL * sizeof(double), (size_t)tiles * gp->nst * oz::S * oz::TILE)));
-  TB_TRY(gp->sA.reserve((size_t)McPad * lda * sizeof(double)));
-  TB_TRY(gp->sMean.reserve(sizeof(double) * McPad));
   tb::DevBuf bx, bcov, bz, bout, bdinv;
   struct Release {
     std::vector<tb::DevBuf*> v;
@@ -1563,26 +1655,16 @@ static int run_sample_joint(tb_gp* gp, const double* Xc, int64_t M, const double
     TB_CUDA(cudaMemcpyAsync(bx.p, Xc, sizeof(double) * M * D, cudaMemcpyHostToDevice, st));
     xc = bx.as<double>();
   }
-  if (oz_path) {
-    TB_TRY(launch_kstar_digits(gp, xc, M, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
-    const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
-    oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Goz, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
-        gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, Goz, McPad, gp->oz_out_scale,
-        oz_npass(gp), 0, nullptr, gp->sA.as<double>(), lda);
-  } else {
-    const int G = pick_groups(gp, tiles);
-    TB_TRY(launch_kstar(gp, xc, M, tiles, gp->sKs.as<double>(), gp->sMean.as<double>()));
-    trigemm_kernel<false, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
-        gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, nullptr, nullptr, gp->sA.as<double>(), lda);
-  }
-  TB_LAUNCHED();
+  TB_TRY(compute_a_plain(gp, xc, M));
   TB_TRY(bcov.reserve(sizeof(double) * M * M));
   {
     const unsigned t = (unsigned)((M + fac::FB - 1) / fac::FB);
     const double* A = gp->sA.as<double>();
     const double* il = gp->dInvLs.as<double>();
     double* cov = bcov.as<double>();
-#define TB_PCOV(KIND)                                                                                                              TB_CUDA(cudaFuncSetAttribute(posterior_cov_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM));   posterior_cov_kernel<KIND><<<dim3(t, t), fac::THREADS, fac::GEMM_SMEM, st>>>(A, lda, (int)lda, xc, il, D, M, gp->variance, jitter, cov)
+#define TB_PCOV(KIND)                                                                                                            \
+  TB_CUDA(cudaFuncSetAttribute(posterior_cov_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac::GEMM_SMEM)); \
+  posterior_cov_kernel<KIND><<<dim3(t, t), fac::THREADS, fac::GEMM_SMEM, st>>>(A, lda, (int)lda, xc, il, D, M, gp->variance, jitter, cov)
     switch (gp->kernel) {
       case TB_RBF: TB_PCOV(TB_RBF); break;
       case TB_MATERN12: TB_PCOV(TB_MATERN12); break;
@@ -2447,6 +2529,21 @@ int tb_acq_batch_mc_ei(tb_gp* gp, const void* Xc, int64_t B, int q, const void* 
   TB_TRY(br.in(eps, (int64_t)q * S, &ed));
   TB_TRY(br.out(out, B, &od));
   TB_TRY(tb_acq_batch_mc_ei_f64(gp, xd, B, q, ed, S, eta, jitter, od));
+  return br.finish();
+}
+
+int tb_gp_covariance_between_points(tb_gp* gp, const void* X1, int64_t M1, const void* X2, int64_t M2, void* out) {
+  TB_CHECK(gp && X1 && X2 && out, "tb_gp_covariance_between_points: null argument");
+  if (gp->dtype == TB_F64) return tb::run_cross_cov(gp, (const double*)X1, M1, (const double*)X2, M2, (double*)out);
+  TB_CHECK(M1 >= 1 && M2 >= 1, "tb_gp_covariance_between_points: need at least one point in each set");
+  TB_CUDA(cudaSetDevice(gp->device));
+  tb::F32Bridge br(gp);
+  const double *x1, *x2;
+  double* od;
+  TB_TRY(br.in(X1, M1 * gp->D, &x1));
+  TB_TRY(br.in(X2, M2 * gp->D, &x2));
+  TB_TRY(br.out(out, M1 * M2, &od));
+  TB_TRY(tb::run_cross_cov(gp, x1, M1, x2, M2, od));
   return br.finish();
 }
 

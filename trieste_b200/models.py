@@ -200,6 +200,24 @@ class GaussianProcessRegression:
         _lib.check(_lib.lib().tb_gp_predict_joint(self._h, _ptr(flat), nb, q, pm, pc))
         return mean.reshape(lead + (q, 1)), cov.reshape(lead + (1, q, q))
 
+    def covariance_between_points(self, query_points_1, query_points_2) -> np.ndarray:
+        """[..., N, D], [M, D] -> [..., 1, N, M]: posterior covariance between two sets of points,
+        ``K12 - Kx1 (K + noise I)^-1 Kx2`` (models.py:188-254; SupportsCovarianceBetweenPoints, interfaces.py:143-163)."""
+        x1 = np.ascontiguousarray(np.asarray(query_points_1, dtype=self._dtype))
+        x2 = np.ascontiguousarray(np.asarray(query_points_2, dtype=self._dtype))
+        if x1.ndim < 2 or x2.ndim != 2:
+            raise ValueError(f"expected query_points_1 [..., N, D] and query_points_2 [M, D], got {x1.shape} and {x2.shape}")
+        self._check_dim(x1)
+        self._check_dim(x2)
+        lead, n, m = x1.shape[:-2], x1.shape[-2], x2.shape[0]
+        flat = x1.reshape(-1, x1.shape[-1])
+        out = np.empty((flat.shape[0], m), dtype=self._dtype)
+        if flat.shape[0] and m:
+            _lib.check(
+                _lib.lib().tb_gp_covariance_between_points(self._h, flat.ctypes.data, flat.shape[0], x2.ctypes.data, m, out.ctypes.data)
+            )
+        return out.reshape(lead + (n, m))[..., None, :, :]
+
     def predict_y(self, query_points):
         """Gaussian likelihood: adds the observation noise to the variance (models.py:126-131)."""
         mean, var = self.predict(query_points)
