@@ -126,7 +126,7 @@ int tb_acq_batch_mc_ei(tb_gp* gp, const void* Xc, int64_t B, int q, const void* 
 /* The same value together with its gradient w.r.t. the query batches — what tfp.math.value_and_gradient
  * (acquisition/optimizer.py:621-629) differentiates when a batch function is maximised through batchify_joint
  * (:897-936): reduce_min routes to the arg-min sample, maximum(., 0) to the active ones, the Cholesky of the joint
- * covariance by its reverse-mode rule.  out [B], grad [B,q,D].  int8 engine only (N ≤ 16384). */
+ * covariance by its reverse-mode rule.  out [B], grad [B,q,D]. */
 int tb_acq_batch_mc_ei_grad(tb_gp* gp, const void* Xc, int64_t B, int q, const void* eps, int S, double eta,
                             double jitter, void* out, void* grad);
 

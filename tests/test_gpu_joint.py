@@ -157,16 +157,17 @@ def test_monte_carlo_expected_improvement_single_point():
         MonteCarloExpectedImprovement(0)
 
 
+@pytest.mark.parametrize("engine", ["int8", "fp64"])
 @pytest.mark.parametrize("kind", ["rbf", "matern32", "matern52"])
 @pytest.mark.parametrize("N,D,q,S", [(200, 6, 4, 64), (300, 6, 8, 512), (150, 3, 1, 32), (260, 10, 11, 100)])
-def test_batch_mc_ei_value_and_gradient_matches_oracle(N, D, q, S, kind):
+def test_batch_mc_ei_value_and_gradient_matches_oracle(N, D, q, S, kind, engine):
     # reverse pass of function.py:1181-1186 (what the reference gets from TF autodiff) against the oracle's analytic
     # restatement (itself pinned by finite differences, tests/test_oracle.py)
     from trieste_b200 import Dataset
     from trieste_b200.acquisition import BatchMonteCarloExpectedImprovement
 
     obj = o.hartmann_6 if D == 6 else o.ackley
-    om, nm = model_pair(obj, N, D, kind=kind)
+    om, nm = model_pair(obj, N, D, kind=kind, engine=engine)
     fn = BatchMonteCarloExpectedImprovement(S, jitter=1e-6).prepare_acquisition_function(nm, Dataset(om.X, om.y))
     eps = np.random.default_rng(3).standard_normal((q, S))
     fn._sampler.set_eps(eps)
@@ -202,10 +203,11 @@ def test_batch_mc_ei_gradient_drives_the_joint_optimizer():
     # leading dimensions and argument errors
     v, g = fn.value_and_gradient(rnd[:6].reshape(2, 3, 3, 6))
     assert v.shape == (2, 3, 1) and g.shape == (2, 3, 3, 6)
-    nm.set_engine("fp64")
-    with pytest.raises(ValueError):
-        fn.value_and_gradient(rnd[:2])
+    nm.set_engine("fp64")  # the native fp64 engine computes the same reverse pass
+    v64, g64 = fn.value_and_gradient(rnd[:6].reshape(2, 3, 3, 6))
     nm.set_engine("int8")
+    np.testing.assert_allclose(v64, v, rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(g64, g, rtol=1e-6, atol=1e-9 * np.abs(g).max())
 
 
 def test_independent_reparametrization_sampler_matches_its_definition():

@@ -1742,22 +1742,37 @@ static int run_qei_grad(tb_gp* gp, const double* Xc, int64_t B, int q, const dou
   TB_CHECK(B >= 0, "negative batch count");
   TB_CHECK(S >= 1 && eps, "need S >= 1 base samples");
   TB_CHECK(jitter >= 0.0, "jitter must be non-negative");
-  TB_CHECK(gp->engine == 1 && gp->N <= 16384,
-           "gradients of the batch Monte-Carlo EI run on the int8 engine only (engine int8, N <= 16384)");
   if (B == 0) return 0;
+  const bool oz_path = gp->engine == 1 && gp->N <= 16384;  // else: native fp64 DMMA kernels
   TB_CUDA(cudaSetDevice(gp->device));
   cudaStream_t st = gp->stream;
   const int D = gp->D;
   const int QT = (q + 7) / 8, QP = QT * 8;
   const int64_t lda = (int64_t)gp->NB * BM;
-  TB_TRY(ensure_ozaki(gp));
-  TB_TRY(ensure_kinv_digits(gp));
+  if (oz_path) {
+    TB_TRY(ensure_ozaki(gp));
+    TB_TRY(ensure_kinv_digits(gp));
+  } else {
+    TB_TRY(ensure_upper_panels(gp));
+  }
   const int64_t max_tiles = chunk_tiles(gp);
   int64_t nbc_cap = std::min<int64_t>(std::max<int64_t>(1, (max_tiles * BT) / q), B);
   const int64_t cand_cap = nbc_cap * q;
   const int64_t tiles_cap = (cand_cap + BT - 1) / BT;
-  TB_TRY(gp->sKs.reserve((size_t)tiles_cap * gp->nst * oz::S * oz::TILE));
-  TB_TRY(gp->sA.reserve((size_t)tiles_cap * BT * lda * sizeof(double)));  // A plain
+  tb::DevBuf baplain;  // fp64 engine: plain copy of A for the Gram kernel (sA holds the packed panels the upper GEMM reads)
+  struct ReleaseA {
+    tb::DevBuf* b;
+    ~ReleaseA() { b->release(); }
+  } rel_a{&baplain};
+  if (oz_path) {
+    TB_TRY(gp->sKs.reserve((size_t)tiles_cap * gp->nst * oz::S * oz::TILE));
+    TB_TRY(gp->sA.reserve((size_t)tiles_cap * BT * lda * sizeof(double)));  // A plain
+  } else {
+    TB_TRY(gp->sKs.reserve((size_t)tiles_cap * gp->nkc * PANEL * sizeof(double)));
+    TB_TRY(gp->sA.reserve((size_t)tiles_cap * gp->NB * (BM / BK) * PANEL * sizeof(double)));  // A packed
+    TB_TRY(baplain.reserve((size_t)tiles_cap * BT * lda * sizeof(double)));
+    TB_TRY(gp->sPartial.reserve(sizeof(double) * (size_t)gp->NB * tiles_cap * BT));
+  }
   TB_TRY(gp->sV.reserve((size_t)tiles_cap * BT * lda * sizeof(double)));  // V plain
   TB_TRY(gp->sMean.reserve(sizeof(double) * tiles_cap * BT));
   TB_TRY(gp->sMisc.reserve(sizeof(double) * 2 * cand_cap));  // c_mu, c_var
@@ -1801,27 +1816,47 @@ static int run_qei_grad(tb_gp* gp, const double* Xc, int64_t B, int q, const dou
       TB_CUDA(cudaMemcpyAsync(gp->sXc.p, Xc + b0 * q * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, st));
       xc_chunk = gp->sXc.as<double>();
     }
-    TB_TRY(launch_kstar_digits(gp, xc_chunk, mc, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
-    const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
-    oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Goz, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
-        gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, Goz, McPad, gp->oz_out_scale,
-        oz_npass(gp), 0, nullptr, gp->sA.as<double>(), lda);
-    TB_LAUNCHED();
-    const int Gv = std::max(1, std::min(gp->NB, std::max((gp->NB + 7) / 8, (2 * 148 + tiles - 1) / tiles)));
-    oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Gv, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
-        gp->dKinvS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dKinvScale.as<double>(), gp->NB, gp->nst, Gv, McPad, gp->oz_out_scale,
-        oz_npass(gp), 1, nullptr, gp->sV.as<double>(), lda);
-    TB_LAUNCHED();
+    const double* a_plain;
+    if (oz_path) {
+      TB_TRY(launch_kstar_digits(gp, xc_chunk, mc, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
+      const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
+      oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Goz, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
+          gp->dAS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, Goz, McPad, gp->oz_out_scale,
+          oz_npass(gp), 0, nullptr, gp->sA.as<double>(), lda);
+      TB_LAUNCHED();
+      const int Gv = std::max(1, std::min(gp->NB, std::max((gp->NB + 7) / 8, (2 * 148 + tiles - 1) / tiles)));
+      oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Gv, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
+          gp->dKinvS.as<int8_t>(), gp->sKs.as<int8_t>(), gp->dKinvScale.as<double>(), gp->NB, gp->nst, Gv, McPad, gp->oz_out_scale,
+          oz_npass(gp), 1, nullptr, gp->sV.as<double>(), lda);
+      TB_LAUNCHED();
+      a_plain = gp->sA.as<double>();
+    } else {
+      // native fp64 engine: A twice (plain for the Gram kernel, packed panels for the upper GEMM), then V = Linv^T A
+      const int G = pick_groups(gp, tiles);
+      TB_TRY(launch_kstar(gp, xc_chunk, mc, tiles, gp->sKs.as<double>(), gp->sMean.as<double>()));
+      trigemm_kernel<false, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
+          gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, nullptr, nullptr, baplain.as<double>(), lda);
+      TB_LAUNCHED();
+      trigemm_kernel<false, EPI_SUMSQ_PACKED><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
+          gp->dLinvP.as<double>(), gp->sKs.as<double>(), gp->NB, gp->nkc, G, McPad, gp->sPartial.as<double>(), gp->sA.as<double>(),
+          nullptr, 0);
+      TB_LAUNCHED();
+      const int nkB = gp->NB * (BM / BK);
+      trigemm_kernel<true, EPI_PLAIN><<<dim3(tiles, G), TG_THREADS, TG_SMEM, st>>>(
+          gp->dLinvTP.as<double>(), gp->sA.as<double>(), gp->NB, nkB, G, McPad, nullptr, nullptr, gp->sV.as<double>(), lda);
+      TB_LAUNCHED();
+      a_plain = baplain.as<double>();
+    }
     TB_CUDA(cudaGetLastError());
     const int jblocks = (int)((nbc + JOINT_WARPS - 1) / JOINT_WARPS);
     const int Nrows = (int)lda;
     double* dmu = bmu.as<double>();
     double* dcov = bcov.as<double>();
     switch (gp->kernel) {
-      case TB_RBF: TB_TRY(launch_joint<TB_RBF>(gp, QT, jblocks, smem_joint, gp->sA.as<double>(), lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, jr, nullptr, dmu, dcov, nullptr, nullptr, err)); break;
-      case TB_MATERN12: TB_TRY(launch_joint<TB_MATERN12>(gp, QT, jblocks, smem_joint, gp->sA.as<double>(), lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, jr, nullptr, dmu, dcov, nullptr, nullptr, err)); break;
-      case TB_MATERN32: TB_TRY(launch_joint<TB_MATERN32>(gp, QT, jblocks, smem_joint, gp->sA.as<double>(), lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, jr, nullptr, dmu, dcov, nullptr, nullptr, err)); break;
-      default: TB_TRY(launch_joint<TB_MATERN52>(gp, QT, jblocks, smem_joint, gp->sA.as<double>(), lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, jr, nullptr, dmu, dcov, nullptr, nullptr, err)); break;
+      case TB_RBF: TB_TRY(launch_joint<TB_RBF>(gp, QT, jblocks, smem_joint, a_plain, lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, jr, nullptr, dmu, dcov, nullptr, nullptr, err)); break;
+      case TB_MATERN12: TB_TRY(launch_joint<TB_MATERN12>(gp, QT, jblocks, smem_joint, a_plain, lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, jr, nullptr, dmu, dcov, nullptr, nullptr, err)); break;
+      case TB_MATERN32: TB_TRY(launch_joint<TB_MATERN32>(gp, QT, jblocks, smem_joint, a_plain, lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, jr, nullptr, dmu, dcov, nullptr, nullptr, err)); break;
+      default: TB_TRY(launch_joint<TB_MATERN52>(gp, QT, jblocks, smem_joint, a_plain, lda, Nrows, gp->sMean.as<double>(), xc_chunk, nbc, jr, nullptr, dmu, dcov, nullptr, nullptr, err)); break;
     }
     double* cmu = gp->sMisc.as<double>();
     double* dval = val_dev ? out_val + b0 : bval.as<double>();
