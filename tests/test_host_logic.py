@@ -295,3 +295,45 @@ def test_batchify_joint_passes_gradients_through_the_reshape():
     np.testing.assert_allclose(pts, centres, atol=1e-4)
     with pytest.raises(ValueError):
         batchify_joint(generate_continuous_optimizer(), 0)
+
+
+class _FakeModel:
+    """predict / sample of a fixed independent Gaussian: mean = sum(x), var = 0.25 (host logic only)."""
+
+    def predict(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        return x.sum(-1, keepdims=True), np.full(x.shape[:-1] + (1,), 0.25)
+
+    def sample(self, at, num_samples, seed=None):
+        at = np.asarray(at, dtype=np.float64)
+        z = np.random.default_rng(seed).standard_normal((num_samples, at.shape[0]))
+        return (at.sum(-1)[None, :] + 0.5 * z)[..., None]
+
+
+def test_independent_sampler_and_exact_thompson_sampler_host_logic():
+    # models/gpflow/sampler.py:82-164 and acquisition/sampler.py:85-123 on a stand-in model (no GPU)
+    from trieste_b200.acquisition.sampler import ExactThompsonSampler
+    from trieste_b200.sampler import IndependentReparametrizationSampler
+
+    m = _FakeModel()
+    s = IndependentReparametrizationSampler(8, m, seed=0)
+    x = np.random.default_rng(1).uniform(size=(5, 1, 3))
+    out = s.sample(x, jitter=0.0)
+    assert out.shape == (5, 8, 1, 1)
+    eps = np.random.default_rng(0).standard_normal((8, 1))
+    np.testing.assert_allclose(out[:, :, 0, 0], x.sum(-1) + 0.5 * eps[:, 0][None, :])
+    np.testing.assert_array_equal(out, s.sample(x, jitter=0.0))
+    s.set_eps(np.zeros(8))
+    np.testing.assert_allclose(s.sample(x)[:, :, 0, 0], np.broadcast_to(x.sum(-1), (5, 8)))
+    with pytest.raises(ValueError):
+        s.set_eps(np.zeros(7))
+    with pytest.raises(ValueError):
+        s.sample(x, jitter=-1.0)
+    at = np.random.default_rng(2).uniform(size=(50, 3))
+    pts = ExactThompsonSampler().sample(m, 6, at, seed=3)
+    mins = ExactThompsonSampler(True).sample(m, 6, at, seed=3)
+    draws = m.sample(at, 6, seed=3)[..., 0]
+    np.testing.assert_array_equal(pts, at[draws.argmin(1)])
+    np.testing.assert_array_equal(mins[:, 0], draws.min(1))
+    with pytest.raises(ValueError):
+        ExactThompsonSampler().sample(m, 0, at)
