@@ -285,14 +285,15 @@ qei_backward_kernel(const double* __restrict__ mean_in, const double* __restrict
   for (int e = lane; e < qq; e += 32) sbar[b * qq + e] = Gs[e];
 }
 
-// V~[j][n] = sum_k Sigma_bar[b][j][k] V[k][n] inside every batch, in place (V plain [point][ldv]); grid (ceil(N/256), nb)
+// V~[j][n] = sum_k Sigma_bar[b][j][k] V[k][n] inside every batch, in place (V plain [point][ldv]); grid (nb, ceil(N/256)):
+// the batch index rides on grid.x (no 65535 limit)
 __global__ void __launch_bounds__(256)
 qei_mix_kernel(double* __restrict__ V, int64_t ldv, int N, int q, const double* __restrict__ sbar) {
   __shared__ double sb[32 * 32];
-  const int64_t b = blockIdx.y;
+  const int64_t b = blockIdx.x;
   for (int e = threadIdx.x; e < q * q; e += blockDim.x) sb[e] = sbar[b * q * q + e];
   __syncthreads();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y * blockDim.x + threadIdx.x;
   if (n >= N) return;
   double v[32];
   double* base = V + b * q * ldv + n;

@@ -312,7 +312,7 @@ static int tb_gp_set_data_f64(tb_gp* gp, const void* X, const void* y, int64_t N
   TB_CHECK(gp && X && y, "tb_gp_set_data: null argument");
   TB_CHECK(N > 0, "tb_gp_set_data: dataset must be populated (N > 0)");
   TB_CHECK(D > 0 && tb::pick_dp(D) > 0, "tb_gp_set_data: input dimension must be in [1, 32]");
-  TB_CHECK(N <= 65536, "tb_gp_set_data: N > 65536 is not supported");
+  TB_CHECK(N <= 65535, "tb_gp_set_data: N > 65535 is not supported");  // grid.y of the per-column kernels
   TB_CUDA(cudaSetDevice(gp->device));
   gp->N = N;
   gp->D = D;
@@ -533,7 +533,7 @@ static int tb_gp_append_data_f64(tb_gp* gp, const double* Xnew, const double* yn
   TB_CHECK(gp->cache_valid, "tb_gp_append_data: posterior cache is not built: call tb_gp_update_posterior_cache first");
   TB_CHECK(m > 0 && m <= APPEND_MAX, "tb_gp_append_data: between 1 and " + std::to_string(APPEND_MAX) + " new points per call");
   const int64_t N0 = gp->N, N = N0 + m;
-  TB_CHECK(N <= 65536, "tb_gp_append_data: N > 65536 is not supported");
+  TB_CHECK(N <= 65535, "tb_gp_append_data: N > 65535 is not supported");
   TB_CUDA(cudaSetDevice(gp->device));
   cudaStream_t st = gp->stream;
   const int D = gp->D, DP = gp->DP;
@@ -1863,7 +1863,7 @@ static int run_qei_grad(tb_gp* gp, const double* Xc, int64_t B, int q, const dou
     qei_backward_kernel<<<(unsigned)((nbc + QEIG_WARPS - 1) / QEIG_WARPS), QEIG_WARPS * 32, smem_back, st>>>(
         dmu, dcov, nbc, q, eps_dev, S, eta, jitter, dval, cmu, cmu + mc, bsbar.as<double>(), err);
     TB_LAUNCHED();
-    qei_mix_kernel<<<dim3((unsigned)((gp->N + 255) / 256), (unsigned)nbc), 256, 0, st>>>(gp->sV.as<double>(), lda, (int)gp->N, q,
+    qei_mix_kernel<<<dim3((unsigned)nbc, (unsigned)((gp->N + 255) / 256)), 256, 0, st>>>(gp->sV.as<double>(), lda, (int)gp->N, q,
                                                                                         bsbar.as<double>());
     TB_LAUNCHED();
     double* gd = grad_dev ? out_grad + b0 * q * D : gp->sGrad.as<double>();
