@@ -118,3 +118,39 @@ def test_append_in_single_precision_models():
     omean, ovar = o.predict(full64, Xq.astype(np.float64))
     np.testing.assert_allclose(mean, omean, rtol=1e-4, atol=1e-4 * np.sqrt(full.variance))
     np.testing.assert_allclose(var, ovar, rtol=0, atol=1e-4 * full.variance)
+
+
+@pytest.mark.parametrize("n2", [1, 3, 40])
+def test_conditional_predictions_equal_a_model_updated_with_the_additional_data(n2):
+    # models.py:355-525 (reference test: test_gpflow_models_conditional_predict, tests/unit/models/gpflow/test_models.py):
+    # the exact update formulas must reproduce the posterior of a model that has seen the additional data
+    import trieste_b200 as tb
+
+    head, full = _grown(o.hartmann_6, 150, n2, 6)
+    nm = native_from_oracle(head)
+    Xq = candidates(257, 6)
+    add = tb.Dataset(full.X[150:], full.y[150:])
+    mean, var = nm.conditional_predict_f(Xq, add)
+    omean, ovar = o.predict_f(full, Xq)
+    assert mean.shape == (257, 1) and var.shape == (257, 1)
+    np.testing.assert_allclose(mean, omean, rtol=1e-8, atol=1e-8 * np.sqrt(full.variance))
+    np.testing.assert_allclose(var, ovar, rtol=0, atol=1e-8 * full.variance)
+    my, vy = nm.conditional_predict_y(Xq, add)
+    np.testing.assert_allclose(vy, ovar + full.noise, rtol=0, atol=1e-8 * full.variance)
+    mj, cj = nm.conditional_predict_joint(Xq[:50], add)
+    _, ocov = o.predict_f(full, Xq[:50], full_cov=True)
+    assert mj.shape == (50, 1) and cj.shape == (1, 50, 50)
+    np.testing.assert_allclose(cj[0], ocov, rtol=0, atol=1e-8 * full.variance)
+    np.testing.assert_allclose(mj, omean[:50], rtol=1e-8, atol=1e-8 * np.sqrt(full.variance))
+    # leading dimensions: two different fantasised observation sets at the same points
+    Xa = np.stack([full.X[150:], full.X[150:]])
+    Ya = np.stack([full.y[150:], full.y[150:] + 1.0])
+    m2, v2 = nm.conditional_predict_f(Xq, tb.Dataset(Xa, Ya))
+    assert m2.shape == (2, 257, 1) and v2.shape == (2, 257, 1)
+    np.testing.assert_allclose(m2[0], mean, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(v2[1], var, rtol=1e-8, atol=1e-10)  # the variance does not depend on the observations
+    assert not np.allclose(m2[1], mean)
+    with pytest.raises(ValueError):
+        nm.conditional_predict_f(Xq[None], add)  # query points must be [M, D]
+    # the model itself is untouched
+    np.testing.assert_allclose(nm.predict(Xq)[0], o.predict(head, Xq)[0], rtol=1e-9)

@@ -337,3 +337,54 @@ def test_independent_sampler_and_exact_thompson_sampler_host_logic():
     np.testing.assert_array_equal(mins[:, 0], draws.min(1))
     with pytest.raises(ValueError):
         ExactThompsonSampler().sample(m, 0, at)
+
+
+def test_conditional_predict_host_algebra_reproduces_an_updated_model():
+    # models.py:355-525: the N2 x N2 update algebra of conditional_predict_* (host side of the native model), with the
+    # device calls replaced by the oracle: must equal the posterior of a model that has seen the additional data
+    from oracle import gp_oracle as o
+    from trieste_b200.data import Dataset
+    from trieste_b200.models import GaussianProcessRegression as G
+
+    class OracleBacked:
+        def __init__(self, om):
+            self.om, self._dtype = om, np.float64
+            self._spec = type("S", (), {"noise_variance": om.noise})()
+
+        def _check_dim(self, x):
+            pass
+
+        def predict(self, x):
+            return o.predict(self.om, np.asarray(x))
+
+        def predict_joint(self, x):
+            return o.predict_joint(self.om, np.asarray(x))
+
+        def covariance_between_points(self, a, b):
+            return o.covariance_between_points(self.om, np.asarray(a), np.asarray(b))
+
+        _conditional_parts = G._conditional_parts
+        conditional_predict_f = G.conditional_predict_f
+        conditional_predict_joint = G.conditional_predict_joint
+        conditional_predict_y = G.conditional_predict_y
+
+    for n2 in (1, 3, 40):
+        full = o.synthetic_model(o.hartmann_6, 80 + n2, 6)
+        head = o.build_model("matern52", full.X[:80], full.y[:80], full.variance, full.lengthscales, full.noise, full.mean_const)
+        f = OracleBacked(head)
+        Xq = np.random.default_rng(1).uniform(size=(33, 6))
+        add = Dataset(full.X[80:], full.y[80:])
+        mean, var = f.conditional_predict_f(Xq, add)
+        omean, ovar = o.predict_f(full, Xq)
+        np.testing.assert_allclose(mean, omean, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(var, ovar, rtol=0, atol=1e-12 * full.variance)
+        _, vy = f.conditional_predict_y(Xq, add)
+        np.testing.assert_allclose(vy, ovar + full.noise, rtol=0, atol=1e-12 * full.variance)
+        mj, cj = f.conditional_predict_joint(Xq, add)
+        np.testing.assert_allclose(cj[0], o.predict_f(full, Xq, full_cov=True)[1], rtol=0, atol=1e-12 * full.variance)
+        m2, v2 = f.conditional_predict_f(Xq, Dataset(np.stack([full.X[80:]] * 2), np.stack([full.y[80:], full.y[80:] + 1.0])))
+        assert m2.shape == (2, 33, 1)
+        np.testing.assert_allclose(m2[0], mean, rtol=1e-12)
+        np.testing.assert_allclose(v2[1], var, rtol=1e-12, atol=1e-15)
+    with pytest.raises(ValueError):
+        f.conditional_predict_f(Xq[None], add)

@@ -218,6 +218,72 @@ class GaussianProcessRegression:
             )
         return out.reshape(lead + (n, m))[..., None, :, :]
 
+    # ---- conditioning on additional (fantasised) data: models.py:355-525 ------------------------------
+    def _conditional_parts(self, query_points, additional_data: Dataset):
+        xq = np.ascontiguousarray(np.asarray(query_points, dtype=self._dtype))
+        xa = np.ascontiguousarray(np.asarray(additional_data.query_points, dtype=self._dtype))
+        ya = np.asarray(additional_data.observations, dtype=np.float64)
+        if xq.ndim != 2 or xa.ndim < 2 or ya.shape != xa.shape[:-1] + (1,):
+            raise ValueError(
+                "additional_data must have query_points with shape [..., N, D] and observations with shape [..., N, 1], "
+                f"and query_points should have shape [M, D]; got {xa.shape}, {ya.shape} and {xq.shape}"
+            )
+        self._check_dim(xq)
+        self._check_dim(xa)
+        n2 = xa.shape[-2]
+        lead = xa.shape[:-2]
+        flat_a = xa.reshape(-1, xa.shape[-1])
+        # posterior moments of the additional points (joint, per leading batch) and their covariance with the queries;
+        # all O(N^2)-per-point work is on the device, the N2 x N2 algebra below is host arithmetic
+        xa3 = xa.reshape((-1, n2, xa.shape[-1]))
+        nbatch = xa3.shape[0]
+        if n2 <= 32:  # the batched joint kernels (the reference calls predict_joint here too, models.py:383-385)
+            mean_add, cov_add = self.predict_joint(xa3)
+            mean_add = np.asarray(mean_add, dtype=np.float64)[..., 0]  # [B, N2]
+            cov_add = np.asarray(cov_add, dtype=np.float64)[:, 0]  # [B, N2, N2]
+        else:
+            mean_add = np.asarray(self.predict(flat_a)[0], dtype=np.float64).reshape(nbatch, n2)
+            cov_add = np.stack([np.asarray(self.covariance_between_points(xa3[b], xa3[b]), dtype=np.float64)[0]
+                                for b in range(nbatch)])
+        limit = 16384 - flat_a.shape[0]
+        if limit < 1:
+            raise ValueError("too many additional points (at most 16383 over all leading dimensions)")
+        cross = [np.asarray(self.covariance_between_points(flat_a, xq[i:i + limit]), dtype=np.float64)[0]
+                 for i in range(0, xq.shape[0], limit)]
+        cov_cross = np.concatenate(cross, axis=-1).reshape(nbatch, n2, xq.shape[0])  # [B, N2, M]
+        L_add = np.linalg.cholesky(cov_add + self._spec.noise_variance * np.eye(n2))
+        A = np.linalg.solve(L_add, cov_cross)  # [B, N2, M]
+        AM = np.linalg.solve(L_add, (ya.reshape(nbatch, n2) - mean_add)[..., None])  # [B, N2, 1]
+        return xq, lead, A, AM
+
+    def conditional_predict_f(self, query_points, additional_data: Dataset):
+        """Marginal posterior at ``query_points`` [M, D] conditioned on the model's data AND ``additional_data``
+        ([..., N, D], [..., N, 1]) by the exact update formulas (models.py:355-425; Chevalier et al. 2014, eqs. 8-10):
+        returns (mean [..., M, 1], var [..., M, 1])."""
+        xq, lead, A, AM = self._conditional_parts(query_points, additional_data)
+        mean_qp, var_qp = self.predict(xq)
+        mean_qp, var_qp = np.asarray(mean_qp, dtype=np.float64)[:, 0], np.asarray(var_qp, dtype=np.float64)[:, 0]
+        var_new = var_qp[None, :] - np.sum(A * A, axis=-2)  # [B, M]
+        mean_new = mean_qp[None, :] + np.einsum("bnm,bn->bm", A, AM[..., 0])
+        shape = lead + (xq.shape[0], 1)
+        return mean_new.reshape(shape).astype(self._dtype), var_new.reshape(shape).astype(self._dtype)
+
+    def conditional_predict_joint(self, query_points, additional_data: Dataset):
+        """Joint posterior at ``query_points`` [M, D] conditioned on ``additional_data`` (models.py:427-500):
+        returns (mean [..., M, 1], cov [..., 1, M, M]); M at most 8192."""
+        xq, lead, A, AM = self._conditional_parts(query_points, additional_data)
+        cov_qp = np.asarray(self.covariance_between_points(xq, xq), dtype=np.float64)[0]  # [M, M]
+        mean_qp = np.asarray(self.predict(xq)[0], dtype=np.float64)[:, 0]
+        cov_new = cov_qp[None] - np.einsum("bnm,bnk->bmk", A, A)
+        mean_new = mean_qp[None, :] + np.einsum("bnm,bn->bm", A, AM[..., 0])
+        M = xq.shape[0]
+        return (mean_new.reshape(lead + (M, 1)).astype(self._dtype), cov_new.reshape(lead + (1, M, M)).astype(self._dtype))
+
+    def conditional_predict_y(self, query_points, additional_data: Dataset):
+        """models.py:502-525: :meth:`conditional_predict_f` plus the observation noise."""
+        mean, var = self.conditional_predict_f(query_points, additional_data)
+        return mean, var + self._spec.noise_variance
+
     def predict_y(self, query_points):
         """Gaussian likelihood: adds the observation noise to the variance (models.py:126-131)."""
         mean, var = self.predict(query_points)
