@@ -288,10 +288,10 @@ class LogExpectedImprovement(ExpectedImprovement):
 
 class MinValueEntropySearch(SingleModelAcquisitionBuilder):
     """entropy.py:52-164.  The min-value samples come from ``min_value_sampler`` evaluated on the data plus
-    ``grid_size`` random points of the search space (:134-137).  The reference's default sampler is
-    ``ExactThompsonSampler`` — joint samples over all N + grid_size points, an (N + grid)^3 Cholesky outside this
-    engine's q <= 32 joint path; the default here is the :class:`GumbelSampler` the reference also offers (and the one
-    Wang & Jegelka recommend), or any sampler with ``sample_min_value=True`` (e.g. ``ThompsonSamplerFromTrajectory``)."""
+    ``grid_size`` random points of the search space (:134-137).  Default as in the reference (:111):
+    ``ExactThompsonSampler(sample_min_value=True)`` — joint samples over all N + grid_size points, drawn on the device
+    (``tb_gp_sample_joint``); above its 16384-point limit the :class:`GumbelSampler` takes over.  Any sampler with
+    ``sample_min_value=True`` can be passed (``GumbelSampler``, ``ThompsonSamplerFromTrajectory``)."""
 
     def __init__(self, search_space, num_samples: int = 5, grid_size: int = 1000, min_value_sampler=None, seed=None):
         if num_samples <= 0:
@@ -304,11 +304,8 @@ class MinValueEntropySearch(SingleModelAcquisitionBuilder):
                     "Minvalue Entropy Search requires a min_value_sampler that samples minimum values, "
                     "however the passed sampler has sample_min_value=False."
                 )
-        else:
-            from .sampler import GumbelSampler
-
-            min_value_sampler = GumbelSampler(sample_min_value=True, seed=seed)
-        self._min_value_sampler = min_value_sampler
+        self._seed = seed
+        self._min_value_sampler = min_value_sampler  # None: chosen per draw (see _draw)
         self._search_space = search_space
         self._num_samples = num_samples
         self._grid_size = grid_size
@@ -317,10 +314,22 @@ class MinValueEntropySearch(SingleModelAcquisitionBuilder):
         return (f"MinValueEntropySearch({self._search_space!r}, {self._num_samples!r}, {self._grid_size!r}, "
                 f"{self._min_value_sampler!r})")
 
+    MAX_EXACT_POINTS = 16384  # tb_gp_sample_joint's limit on the jointly sampled point set
+
     def _draw(self, model, dataset: Dataset) -> np.ndarray:
         grid = np.asarray(self._search_space.sample(self._grid_size))
         query_points = np.concatenate([np.asarray(dataset.query_points, dtype=grid.dtype), grid], axis=0)
-        return self._min_value_sampler.sample(model, self._num_samples, query_points)
+        sampler = self._min_value_sampler
+        if sampler is None:
+            # entropy.py:111: the reference default is ExactThompsonSampler(sample_min_value=True) — joint samples over the
+            # data and the grid; beyond the device path's point limit the Gumbel sampler (marginals only) takes over
+            from .sampler import ExactThompsonSampler, GumbelSampler
+
+            if query_points.shape[0] <= self.MAX_EXACT_POINTS:
+                sampler = ExactThompsonSampler(sample_min_value=True)
+            else:
+                sampler = GumbelSampler(sample_min_value=True, seed=self._seed)
+        return sampler.sample(model, self._num_samples, query_points)
 
     def prepare_acquisition_function(self, model, dataset: Optional[Dataset] = None):
         dataset = _check_populated(dataset)
