@@ -9,9 +9,10 @@
  * binding a trieste maintainer would add.
  *
  * Conventions
- *   - every function returns 0 on success, non-zero on failure; tb_last_error() returns the
- *     thread-local message (the Python layer raises ValueError / RuntimeError from it);
- *     nothing aborts the process (the BO loop records exceptions, bayesian_optimizer.py:855-875).
+ *   - every function returns a tb_status: 0 on success, otherwise the class of the failure (below);
+ *     tb_last_error() returns the thread-local message.  The Python layer maps the CODE (not the text) to the
+ *     exception the reference raises for the same condition; nothing aborts the process (the BO loop records
+ *     exceptions, bayesian_optimizer.py:855-875).
  *   - plain pointers + sizes only.  Every array pointer may be a HOST pointer or a DEVICE pointer
  *     on the handle's GPU (detected with cudaPointerGetAttributes); host buffers are staged
  *     through the handle's stream inside the call.
@@ -32,6 +33,13 @@ extern "C" {
 typedef struct tb_gp tb_gp;   /* exact-GPR posterior: owns device copies of X, Linv, alpha, hyper-params */
 typedef struct tb_rff tb_rff; /* random-Fourier-feature trajectory: owns W, b, theta */
 
+enum tb_status {
+  TB_OK = 0,
+  TB_ERR_INVALID = 1, /* bad argument / unmet precondition: ValueError (tf.errors.InvalidArgumentError in the reference) */
+  TB_ERR_RUNTIME = 2, /* CUDA or library failure, no GPU: RuntimeError (there is no CPU fallback) */
+  TB_ERR_NUMERIC = 3  /* a Cholesky factorisation met a non-positive-definite matrix: ValueError, like tf.linalg.cholesky's
+                         InvalidArgumentError ("Cholesky decomposition was not successful") */
+};
 enum tb_dtype { TB_F64 = 0, TB_F32 = 1 };
 /* gpflow.kernels.{SquaredExponential,Matern12,Matern32,Matern52}; trieste default Matern52
  * (models/gpflow/builders.py:399) */
@@ -181,8 +189,16 @@ int tb_gp_kinv_apply(tb_gp* gp, const double* B, int nrhs, double* out);
 int64_t tb_launch_count(void);
 void tb_launch_count_reset(void);
 /* engine of the variance GEMM: 0 = native fp64 (DMMA), 1 = fp64-accurate emulation on the INT8 tensor cores
- * (Ozaki splitting, tcgen05 kind::i8; same stated tolerances).  Gradient / joint paths always use engine 0. */
+ * (Ozaki splitting, tcgen05 kind::i8; same stated tolerances; N <= 16384, larger models fall back to engine 0), 2 = engine 1
+ * with the number of digit products pinned to the full 21 (engine 1 drops to 15 — fp32 handles: 6 — when the a-priori error
+ * estimate of the cache allows it; csrc/ozaki5.cuh).  The
+ * engine serves every path: predict / acquisition values, gradients (V = K^-1 k* as a dense digit GEMM) and the joint
+ * paths (predict_joint / reparam samples / MC-qEI through the store-A epilogue). */
 int tb_gp_set_engine(tb_gp* gp, int engine);
+/* what the variance GEMM of this handle runs right now: int8 digit products per k-step (15 or 21; fp32 handles 6 or 10;
+ * 0 = native fp64 engine) and, for the reduced modes, the a-priori estimate of max |Δvar| / σ_f² that admitted them.
+ * Needs a valid cache.  Either output may be NULL. */
+int tb_gp_engine_info(tb_gp* gp, int* digit_products, double* error_estimate);
 int tb_gp_profile(tb_gp* gp, int enable);
 /* the handle's CUDA stream (cudaStream_t as void*), so callers can record CUDA events on the stream the
  * kernels are launched on (torch.cuda.ExternalStream in bench.py). */

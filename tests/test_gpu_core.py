@@ -27,7 +27,7 @@ def _check_predict(om, nm, Xq):
     return mean, var, omean, ovar
 
 
-@pytest.mark.parametrize("engine", ["int8", "fp64"])
+@pytest.mark.parametrize("engine", ["int8", "int8x21", "fp64"])
 @pytest.mark.parametrize("kind", ["matern52", "rbf", "matern32", "matern12"])
 @pytest.mark.parametrize("N,D", [(5, 2), (20, 2), (127, 3), (128, 6), (129, 6), (300, 6), (1024, 6)])
 def test_predict_matches_oracle(kind, N, D, engine):
@@ -67,7 +67,7 @@ def test_config2_slice_n1024_large_batch():
     np.testing.assert_allclose(var[idx], ovar, rtol=0, atol=1e-9 * om.variance)
 
 
-@pytest.mark.parametrize("engine", ["int8", "fp64"])
+@pytest.mark.parametrize("engine", ["int8", "int8x21", "fp64"])
 def test_headline_n4096_d10(engine):
     om, nm = model_pair(o.ackley, 4096, 10, engine=engine)
     Xq = candidates(3000, 10)

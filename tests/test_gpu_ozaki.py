@@ -10,18 +10,27 @@ pytestmark = pytest.mark.gpu
 
 
 def _check(om, nm, Xq):
-    nm.set_engine("int8")
-    mean, var = nm.predict(Xq)
+    """Both product counts of the int8 engine ("int8" = picked from the a-priori estimate: 15 or 21; "int8x21" = pinned)
+    against the oracle at the stated bar, and against the native engine: tighter still."""
     nm.set_engine("fp64")
     mean64, var64 = nm.predict(Xq)
     omean, ovar = o.predict_batched(om, Xq)
     sf = np.sqrt(om.variance)
-    np.testing.assert_allclose(mean, omean, rtol=1e-9, atol=1e-9 * sf)
-    np.testing.assert_allclose(var, ovar, rtol=0, atol=1e-9 * om.variance)
-    # and against the native engine: tighter still
-    np.testing.assert_allclose(var, var64, rtol=0, atol=2e-10 * om.variance)
-    assert var.min() >= 1e-12
-    return np.abs(var - ovar).max() / om.variance
+    worst = 0.0
+    for engine in ("int8", "int8x21"):
+        nm.set_engine(engine)
+        products, est = nm.engine_info()
+        assert products == 21 if engine == "int8x21" else products in (15, 21)
+        mean, var = nm.predict(Xq)
+        np.testing.assert_allclose(mean, omean, rtol=1e-9, atol=1e-9 * sf)
+        np.testing.assert_allclose(var, ovar, rtol=0, atol=1e-9 * om.variance)
+        np.testing.assert_allclose(var, var64, rtol=0, atol=(5e-10 if products == 15 else 2e-10) * om.variance)
+        if products == 15:  # the estimate that admitted the reduced mode must cover what is measured
+            assert est <= 3e-10 and np.abs(var - var64).max() <= max(est, 1e-11) * om.variance
+        assert var.min() >= 1e-12
+        worst = max(worst, np.abs(var - ovar).max() / om.variance)
+    nm.set_engine("int8")
+    return worst
 
 
 @pytest.mark.parametrize("kind", ["matern52", "rbf"])
@@ -37,6 +46,24 @@ def test_int8_engine_headline_n4096_and_near_training_points():
     Xq = np.concatenate([candidates(2500, 10), om.X[:300] + 1e-7, om.X[300:500]])
     err = _check(om, nm, Xq)
     print(f"max |dvar| / sigma_f^2 at N=4096: {err:.3e}")
+
+
+def test_int8_engine_picks_the_product_count_from_the_error_estimate():
+    # the benchmark configurations run the 15-product single-pass kernel ...
+    for obj, N, D in [(o.ackley, 4096, 10), (o.hartmann_6, 1024, 6)]:
+        om, nm = model_pair(obj, N, D)
+        products, est = nm.engine_info()
+        assert products == 15 and 0 < est <= 3e-10, (N, products, est)
+        nm.set_engine("int8x21")
+        assert nm.engine_info()[0] == 21
+        nm.set_engine("fp64")
+        assert nm.engine_info()[0] == 0
+    # ... a badly scaled factor (little noise on a smooth kernel: huge rows of Linv; estimate 3e-9) keeps the full 21 products
+    var = o.synthetic_model(o.branin, 300, 2, kind="rbf").variance
+    om, nm = model_pair(o.branin, 300, 2, kind="rbf", noise=1e-5 * var)
+    products, est = nm.engine_info()
+    assert products == 21, (products, est)
+    _check(om, nm, candidates(500, 2))
 
 
 def test_int8_engine_low_noise_clip_and_multi_chunk():

@@ -56,6 +56,7 @@ SIGNATURES = {
     "tb_launch_count": (_i64, []),
     "tb_launch_count_reset": (None, []),
     "tb_gp_set_engine": (_i32, [_vp, _i32]),
+    "tb_gp_engine_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_f64)]),
     "tb_gp_profile": (_i32, [_vp, _i32]),
     "tb_gp_stream": (_i32, [_vp, C.POINTER(_vp)]),
     "tb_gp_profile_read": (_i32, [_vp, C.POINTER(_f64), C.POINTER(_i64), C.POINTER(_f64)]),
@@ -90,14 +91,30 @@ def last_error() -> str:
     return lib().tb_last_error().decode("utf-8", "replace")
 
 
+# enum tb_status (include/trieste_b200.h)
+TB_OK, TB_ERR_INVALID, TB_ERR_RUNTIME, TB_ERR_NUMERIC = 0, 1, 2, 3
+
+
 def check(status: int, exc=ValueError) -> None:
-    """Non-zero status -> Python exception carrying the C side's message (the reference raises
-    ValueError / InvalidArgumentError for the same conditions)."""
-    if status != 0:
-        msg = last_error()
-        if "cuda" in msg.lower() or "cusolver" in msg.lower() or "cublas" in msg.lower() or "no CUDA device" in msg:
-            raise NativeLibraryError(msg)
-        raise exc(msg)
+    """Non-zero status -> Python exception carrying the C side's message, chosen by the status CODE: invalid arguments
+    and failed factorisations raise ``exc`` (ValueError: the reference raises ValueError / InvalidArgumentError for the
+    same conditions), CUDA / library failures raise NativeLibraryError (there is nothing to fall back to)."""
+    if status == TB_OK:
+        return
+    msg = last_error()
+    if status == TB_ERR_RUNTIME:
+        raise NativeLibraryError(msg)
+    raise exc(msg)
+
+
+def sync_torch_stream(x) -> None:
+    """Order the library's (non-blocking) stream after torch's current stream.  The ABI reads device pointers on the
+    handle's own stream, so everything torch has queued on its stream — the producer of a tensor passed in, or a
+    pending reader of a caching-allocator block about to be handed out as an output — must have finished first.  The
+    ABI returns only after its stream has drained, so nothing is needed on the way out."""
+    import torch
+
+    torch.cuda.current_stream(x.device).synchronize()
 
 
 def device_count() -> int:
@@ -130,6 +147,8 @@ def as_contiguous(x, dtype=np.float64):
         if t.dtype != tdt:
             t = t.to(tdt)
         t = t.contiguous()
+        if t.is_cuda:
+            sync_torch_stream(t)
         return t, t.data_ptr()
     a = np.ascontiguousarray(np.asarray(x, dtype=dtype))
     return a, a.ctypes.data
@@ -146,6 +165,8 @@ def empty_like_kind(ref, shape, dtype=np.float64):
 
         tdt = {np.float64: torch.float64, np.float32: torch.float32, np.int64: torch.int64}[dtype]
         t = torch.empty(shape, dtype=tdt, device=ref.device)
+        if t.is_cuda:
+            sync_torch_stream(t)
         return t, t.data_ptr()
     a = np.empty(shape, dtype=dtype)
     return a, a.ctypes.data

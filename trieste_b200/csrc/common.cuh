@@ -13,20 +13,28 @@ inline std::string& last_error() {
   thread_local std::string e;
   return e;
 }
-inline int fail(const std::string& msg) {
+// status codes of the C-ABI (include/trieste_b200.h, enum tb_status)
+constexpr int ERR_INVALID = 1;   // bad argument / precondition: the Python layer raises ValueError (the reference's InvalidArgumentError)
+constexpr int ERR_RUNTIME = 2;   // CUDA / library failure: NativeLibraryError (there is no CPU fallback to retry on)
+constexpr int ERR_NUMERIC = 3;   // a factorisation met a non-positive-definite matrix: ValueError, as tf.linalg.cholesky's InvalidArgumentError
+inline int fail(const std::string& msg, int code = ERR_INVALID) {
   last_error() = msg;
-  return 1;
+  return code;
 }
 #define TB_CUDA(expr)                                                                        \
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \
     if (_e != cudaSuccess)                                                                   \
       return ::tb::fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ + \
-                        ":" + std::to_string(__LINE__) + ")");                               \
+                        ":" + std::to_string(__LINE__) + ")", ::tb::ERR_RUNTIME);            \
   } while (0)
 #define TB_CHECK(cond, msg)              \
   do {                                   \
     if (!(cond)) return ::tb::fail(msg); \
+  } while (0)
+#define TB_CHECK_CODE(cond, msg, code)         \
+  do {                                         \
+    if (!(cond)) return ::tb::fail(msg, code); \
   } while (0)
 #define TB_TRY(expr)        \
   do {                      \

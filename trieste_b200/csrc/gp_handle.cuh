@@ -1,6 +1,7 @@
 // The model handle: device-resident posterior cache + scratch, and its once-per-step precompute.
 #pragma once
-#include "kernels_f64.cuh"
+#include "common.cuh"
+#include "../../include/trieste_b200.h"
 #include <cublas_v2.h>
 #include <cusolverDn.h>
 #include <vector>
@@ -90,6 +91,13 @@ struct tb_gp {
   bool oz_valid = false;
   int nst = 0, oz_bscale_exp = 0;
   double oz_out_scale = 1.0;
+  // single-pass digit engine (ozaki5.cuh): tight row scales + row sums + S-digit tiles of Linv; mode = digits per operand
+  // (5: fp64 handles, 15 products; 3: fp32 handles, 6 products; 0: not eligible -> the 6-digit / 21-product kernels)
+  tb::DevBuf dAS5, dRowScale5, dRowSum5;
+  bool oz5_valid = false;
+  bool oz_full = false;  // tb_gp_set_engine(2): always the 6-digit / 21-product kernels
+  int oz5_mode = 0;
+  double oz5_est = 0.0;  // a-priori estimate of max |Δvar| / σ_f² in the chosen mode
   tb::DevBuf dWork, dInfo;      // cusolver workspace / info flag
   tb::DevBuf dDinv;             // inverses of the diagonal blocks of L (hand-written factorisation)
   bool factor_own = true;       // false (TB_FACTOR=cusolver): cuSOLVER / cuBLAS cross-check path

@@ -5,6 +5,7 @@
 //   - top-k (bitonic sort of (value, index) pairs)
 #pragma once
 #include "gp_handle.cuh"
+#include "kernels_f64.cuh"
 
 namespace tb {
 

@@ -8,37 +8,10 @@
 #pragma once
 #include "common.cuh"
 #include "../../include/trieste_b200.h"
+#include "kernel_fn.cuh"
 #include <cfloat>
 
 namespace tb {
-
-// ------------------------------------------------------------------------------------------------
-// stationary kernels on the scaled squared distance (GPflow kernels/stationaries.py semantics,
-// SURVEY.md Appendix A1; r = sqrt(max(r2, 1e-36)) for the Matern family)
-// ------------------------------------------------------------------------------------------------
-template <int KIND>
-__device__ __forceinline__ double kernel_from_r2(double r2, double variance) {
-  if (KIND == TB_RBF) return variance * exp(-0.5 * r2);
-  double r = sqrt(fmax(r2, 1e-36));
-  if (KIND == TB_MATERN12) return variance * exp(-r);
-  if (KIND == TB_MATERN32) {
-    double s = 1.7320508075688772 * r;
-    return variance * (1.0 + s) * exp(-s);
-  }
-  double s = 2.23606797749979 * r;
-  return variance * (1.0 + s + (5.0 / 3.0) * r * r) * exp(-s);
-}
-
-// dk/d(r2) (for gradients w.r.t. x*: dk/dx*_d = dk/dr2 * 2 (x*_d - x_d) / l_d^2)
-template <int KIND>
-__device__ __forceinline__ double kernel_dr2(double r2, double variance) {
-  if (KIND == TB_RBF) return -0.5 * variance * exp(-0.5 * r2);
-  double r = sqrt(fmax(r2, 1e-36));
-  if (KIND == TB_MATERN12) return -variance * exp(-r) / (2.0 * r);
-  if (KIND == TB_MATERN32) return -1.5 * variance * exp(-1.7320508075688772 * r);
-  double s = 2.23606797749979 * r;
-  return -(5.0 / 6.0) * variance * (1.0 + s) * exp(-s);
-}
 
 // ------------------------------------------------------------------------------------------------
 // K1a: cross-covariance panels.  grid.x = candidate tiles of the chunk; 512 threads = 16 warps,
@@ -112,11 +85,6 @@ constexpr size_t TG_SMEM = (size_t)TG_STAGES * 2 * PANEL * sizeof(double) + 2 * 
 
 enum { EPI_SUMSQ = 0, EPI_SUMSQ_PACKED = 1, EPI_PLAIN = 2, EPI_SUMSQ_PLAIN = 3 };
 
-__device__ __forceinline__ int serpentine_rowblock(int i, int g, int G) {
-  // i-th row-block of group g (increasing in i); balances the triangular cost across groups
-  int base = (i >> 1) * 2 * G;
-  return (i & 1) ? base + 2 * G - 1 - g : base + g;
-}
 
 // panel range [k0, k1) and storage offset of row-block I
 template <bool UPPER>

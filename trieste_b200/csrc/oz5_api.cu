@@ -1,0 +1,132 @@
+// Host side of the single-pass digit engine (ozaki5.cuh): mode selection from an a-priori error bound, digit tiles of Linv,
+// launches of the centred K* digit generation and of the digit GEMM.  Called from tb_api.cu (run_eval_oz).
+#include "gp_handle.cuh"
+#include "ozaki5.cuh"
+#include "oz5_api.h"
+
+namespace tb {
+
+int oz5_init() {
+  TB_CUDA(cudaFuncSetAttribute(oz5::trigemm_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz5::smem_bytes<5>()));
+  TB_CUDA(cudaFuncSetAttribute(oz5::trigemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz5::smem_bytes<3>()));
+  return 0;
+}
+
+int oz5_tile_width(const tb_gp* gp) { return gp->oz5_mode == 5 ? oz5::Geo<5>::NT : oz5::Geo<3>::NT; }
+size_t oz5_tile_bytes(const tb_gp* gp) {
+  return (size_t)gp->nst * (gp->oz5_mode == 5 ? 5 * oz5::btile<5>() : 3 * oz5::btile<3>());
+}
+
+// Calibrated a-priori estimate of max |Δvar| / σ_f² when the levels r > S+1 are dropped: per element of A the dropped
+// level r = S+2 contributes ~ rowscale·sB·sqrt(6 K)·E[d²]·2^(-8(S+2)) (E[d²] = 256²/12 for uniform balanced digits, K <= N
+// terms with independent signs), and Δvar = 2 Σ_n A_n δ_n with Σ A_n² <= σ_f².  The constant (8/5) was calibrated on the
+// emulated engine over the benchmark configurations (oracle-side study in DESIGN.md §4c): estimate / measured max = 1.1 .. 5.
+static double oz5_estimate(double variance, double max_rowscale, int64_t N, int S) {
+  const double sB = 0.5 * variance / oz5::FILL;
+  return 1.6 * std::sqrt(variance) * max_rowscale * sB * std::sqrt(6.0 * (double)N) * (65536.0 / 12.0) * std::ldexp(1.0, -8 * (S + 2)) / variance;
+}
+
+template <int S>
+static int build_digits(tb_gp* gp, cudaStream_t st) {
+  const int64_t nstages = oz::a_stage_offset(gp->NB);
+  const size_t bytes = (size_t)nstages * S * oz5::ATILE;
+  TB_TRY(gp->dAS5.reserve(bytes));
+  TB_CUDA(cudaMemsetAsync(gp->dAS5.p, 0, bytes, st));
+  oz5::linv_digits_kernel<S><<<dim3(2 * gp->NB, gp->NB), 256, 0, st>>>(gp->dLinv.as<double>(), gp->N, gp->dRowScale5.as<double>(),
+                                                                      gp->dAS5.as<int8_t>());
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int oz5_ensure(tb_gp* gp) {
+  if (gp->oz5_valid) return 0;
+  gp->oz5_mode = 0;
+  gp->oz5_est = 0.0;
+  int force = -1;  // TB_OZ_FAST=0: never; =1: always (experiments / tests of the fallback)
+  if (const char* e = std::getenv("TB_OZ_FAST")) force = std::atoi(e);
+  if (force == 0 || gp->oz_full || gp->N > 16384) {
+    gp->oz5_valid = true;
+    return 0;
+  }
+  cudaStream_t st = gp->stream;
+  const int64_t rows = (int64_t)gp->NB * BM;
+  gp->nst = (int)((gp->N + oz::KST - 1) / oz::KST);
+  TB_TRY(gp->dRowScale5.reserve(sizeof(double) * rows));
+  TB_TRY(gp->dRowSum5.reserve(sizeof(double) * rows));
+  oz5::linv_rowstats_kernel<<<(unsigned)rows, 256, 0, st>>>(gp->dLinv.as<double>(), gp->N, rows, gp->dRowScale5.as<double>(),
+                                                           gp->dRowSum5.as<double>());
+  TB_LAUNCHED();
+  std::vector<double> h((size_t)gp->N);
+  TB_CUDA(cudaMemcpyAsync(h.data(), gp->dRowScale5.p, sizeof(double) * (size_t)gp->N, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  double mx = 0.0;
+  for (double v : h) mx = std::max(mx, v);
+  // fp64 handles: 5 digits / 15 products if the estimate clears 3e-10 (bar: 1e-9); fp32 handles: 3 digits / 6 products if it
+  // clears 3e-5 (bar: 1e-4), else the 5-digit mode, else the 6-digit kernels
+  int mode = 0;
+  if (gp->dtype == TB_F32 && (force == 1 || oz5_estimate(gp->variance, mx, gp->N, 3) <= 3e-5)) mode = 3;
+  if (mode == 0 && (force == 1 || oz5_estimate(gp->variance, mx, gp->N, 5) <= (gp->dtype == TB_F32 ? 3e-5 : 3e-10))) mode = 5;
+  if (mode == 5) TB_TRY(build_digits<5>(gp, st));
+  if (mode == 3) TB_TRY(build_digits<3>(gp, st));
+  if (mode) gp->oz5_est = oz5_estimate(gp->variance, mx, gp->N, mode);
+  gp->oz5_mode = mode;
+  gp->oz5_valid = true;
+  return 0;
+}
+
+template <int S>
+static int launch_kstar_s(tb_gp* gp, cudaStream_t st, const double* Xc_dev, int64_t mc, int tiles, int8_t* BS, double* mean) {
+  const double* Xs = gp->dXs.as<double>();
+  const double* al = gp->dAlpha.as<double>();
+  const double* il = gp->dInvLs.as<double>();
+  const int N = (int)gp->N, nst = gp->nst, D = gp->D;
+  const double var = gp->variance, mc0 = gp->mean_const;
+  const double inv_b = oz5::two_pow_8S<S>() * oz5::FILL / (0.5 * var);
+  constexpr int TH = oz5::Geo<S>::NT * 4;
+#define TB_KD(KIND, DPV) \
+  oz5::kstar_digits_kernel<KIND, DPV, S><<<tiles, TH, 0, st>>>(Xs, al, Xc_dev, il, N, nst, D, mc, var, inv_b, mc0, BS, mean)
+#define TB_KD_DP(KIND)                 \
+  switch (gp->DP) {                    \
+    case 2: TB_KD(KIND, 2); break;     \
+    case 4: TB_KD(KIND, 4); break;     \
+    case 6: TB_KD(KIND, 6); break;     \
+    case 8: TB_KD(KIND, 8); break;     \
+    case 10: TB_KD(KIND, 10); break;   \
+    case 12: TB_KD(KIND, 12); break;   \
+    case 16: TB_KD(KIND, 16); break;   \
+    case 20: TB_KD(KIND, 20); break;   \
+    case 24: TB_KD(KIND, 24); break;   \
+    default: TB_KD(KIND, 32); break;   \
+  }
+  switch (gp->kernel) {
+    case TB_RBF: TB_KD_DP(TB_RBF); break;
+    case TB_MATERN12: TB_KD_DP(TB_MATERN12); break;
+    case TB_MATERN32: TB_KD_DP(TB_MATERN32); break;
+    default: TB_KD_DP(TB_MATERN52); break;
+  }
+#undef TB_KD_DP
+#undef TB_KD
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int oz5_launch_kstar(tb_gp* gp, cudaStream_t st, const double* Xc_dev, int64_t mc, int tiles, int8_t* BS, double* mean) {
+  return gp->oz5_mode == 5 ? launch_kstar_s<5>(gp, st, Xc_dev, mc, tiles, BS, mean) : launch_kstar_s<3>(gp, st, Xc_dev, mc, tiles, BS, mean);
+}
+
+int oz5_launch_gemm(tb_gp* gp, cudaStream_t st, const int8_t* BS, int tiles, int G, int64_t McPad, double* partial) {
+  const double h = 0.5 * gp->variance, sB = h / oz5::FILL;
+  if (gp->oz5_mode == 5)
+    oz5::trigemm_kernel<5><<<dim3(G, tiles), (oz5::EW + 2) * 32, oz5::smem_bytes<5>(), st>>>(
+        gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, McPad, sB, h, partial);
+  else
+    oz5::trigemm_kernel<3><<<dim3(G, tiles), (oz5::EW + 2) * 32, oz5::smem_bytes<3>(), st>>>(
+        gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, McPad, sB, h, partial);
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tb

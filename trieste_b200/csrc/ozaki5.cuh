@@ -1,0 +1,421 @@
+// Single-pass digit GEMM of the INT8 engine (round 2): fewer digit products, one pass, L2-lean tiles.
+//
+// Same error-free splitting as ozaki.cuh, re-budgeted against the 1e-9·σ_f² variance bar (ncu of the round-1 kernel showed it
+// bound by L2 -> SM operand traffic, 59 B/clk/SM demanded against a ~43 B/clk/SM chip-wide cap, not by the tensor pipe):
+//   * operands are scaled TIGHTLY (|x̂| <= 0.4975, arbitrary fp64 scale per row of Linv instead of a power of two with two
+//     spare bits) and K* is CENTRED: K* = h + K̃ with h = σ_f²/2, |K̃| <= h, so the sign bit of the top digit carries
+//     information;  A = Linv·K̃ + h·rowsum(Linv), the second term is a per-row constant added in the epilogue;
+//   * with those 3-4 extra bits, S = 5 balanced base-256 digits and the pairs p + q <= S + 1 (15 products instead of 21)
+//     keep max |Δvar| at ~1e-10·σ_f² (emulated and measured; the host picks this mode from an a-priori bound computed
+//     from the row scales and falls back to the 6-digit / 21-product kernel otherwise);
+//   * S levels r = 2..S+1 of NT columns each fit TMEM at once for NT = 96 (480 of 512 columns): ONE pass per row-block,
+//     every digit tile is loaded once, one epilogue per row-block, no stage-geometry switches;
+//   * fp32 models use S = 3 (6 products, NT = 128): ~5e-6·σ_f² against the 1e-4·σ_f² fp32 bar.
+// Per stage (64 k-columns): S·(8 KB + NT·64 B) of 1-D bulk-TMA copies, S(S+1)/2 products x 2 MMAs (K = 32 each).
+#pragma once
+#include "kernel_fn.cuh"
+#include "umma.cuh"
+
+namespace tb {
+namespace oz5 {
+
+using oz::KST;
+using oz::LBO;
+using oz::SBO;
+constexpr int ATILE = 128 * KST;  // one digit tile of the left factor: 128 rows x 64 k-bytes = 8 KB
+constexpr double FILL = 0.4975;   // |x̂| bound: the largest 5-digit balanced value is 0.49804
+constexpr int STAGES = 3;
+constexpr int EW = 8;  // epilogue warps
+
+template <int S> struct Geo;
+template <> struct Geo<5> { static constexpr int NT = 96; };
+template <> struct Geo<3> { static constexpr int NT = 128; };
+
+template <int S> __host__ __device__ constexpr int btile() { return Geo<S>::NT * KST; }
+template <int S> __host__ __device__ constexpr int stage_bytes() { return S * (ATILE + btile<S>()); }
+template <int S> __host__ __device__ constexpr size_t smem_bytes() { return (size_t)STAGES * stage_bytes<S>() + 256; }
+template <int S> __host__ __device__ constexpr double two_pow_8S() { return S == 5 ? 1099511627776.0 : 16777216.0; }  // 2^40 / 2^24
+
+// v = Σ_{p=1..S} d_p 256^(S-p), d_p in [-128,127]: the int8 digits are the bytes of (v + 0x80..80) ^ 0x80..80 (no carry chain);
+// byte 0 = least significant digit d_S
+template <int S>
+__device__ __forceinline__ void digit_bytes(long long v, uint32_t& lo, uint32_t& hi) {
+  constexpr unsigned long long K = S == 5 ? 0x0000008080808080ULL : 0x0000000000808080ULL;
+  const unsigned long long w = ((unsigned long long)v + K) ^ K;
+  lo = (uint32_t)w;
+  hi = (uint32_t)(w >> 32);
+}
+// element JJ (0..15) of the lane's 16-byte rows: plane p (0 = most significant digit) takes byte S-1-p of the word
+template <int S, int JJ>
+__device__ __forceinline__ void scatter(uint32_t (&pk)[S][4], uint32_t lo, uint32_t hi) {
+#pragma unroll
+  for (int p = 0; p < S; ++p) {
+    const int b = S - 1 - p;
+    if (b >= 4) {
+      if (b == 4) pk[p][JJ >> 2] = oz::put_byte<JJ & 3, 0>(pk[p][JJ >> 2], hi);
+    } else if (b == 3) {
+      pk[p][JJ >> 2] = oz::put_byte<JJ & 3, 3>(pk[p][JJ >> 2], lo);
+    } else if (b == 2) {
+      pk[p][JJ >> 2] = oz::put_byte<JJ & 3, 2>(pk[p][JJ >> 2], lo);
+    } else if (b == 1) {
+      pk[p][JJ >> 2] = oz::put_byte<JJ & 3, 1>(pk[p][JJ >> 2], lo);
+    } else {
+      pk[p][JJ >> 2] = oz::put_byte<JJ & 3, 0>(pk[p][JJ >> 2], lo);
+    }
+  }
+}
+template <int S>
+__device__ __forceinline__ void scatter_rt(uint32_t (&pk)[S][4], int jj, uint32_t lo, uint32_t hi) {
+  switch (jj) {  // jj is a compile-time constant after unrolling
+    case 0: scatter<S, 0>(pk, lo, hi); break;
+    case 1: scatter<S, 1>(pk, lo, hi); break;
+    case 2: scatter<S, 2>(pk, lo, hi); break;
+    case 3: scatter<S, 3>(pk, lo, hi); break;
+    case 4: scatter<S, 4>(pk, lo, hi); break;
+    case 5: scatter<S, 5>(pk, lo, hi); break;
+    case 6: scatter<S, 6>(pk, lo, hi); break;
+    case 7: scatter<S, 7>(pk, lo, hi); break;
+    case 8: scatter<S, 8>(pk, lo, hi); break;
+    case 9: scatter<S, 9>(pk, lo, hi); break;
+    case 10: scatter<S, 10>(pk, lo, hi); break;
+    case 11: scatter<S, 11>(pk, lo, hi); break;
+    case 12: scatter<S, 12>(pk, lo, hi); break;
+    case 13: scatter<S, 13>(pk, lo, hi); break;
+    case 14: scatter<S, 14>(pk, lo, hi); break;
+    default: scatter<S, 15>(pk, lo, hi); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// once per BO step: tight row scales, row sums and digit tiles of Linv
+//   rowscale[n] = max_k |Linv[n,k]| / FILL   (1 for empty / padded rows),   rowsum[n] = Σ_k Linv[n,k]
+// ------------------------------------------------------------------------------------------------
+__global__ void linv_rowstats_kernel(const double* __restrict__ Linv, int64_t N, int64_t rows, double* __restrict__ rowscale,
+                                     double* __restrict__ rowsum) {
+  const int64_t n = blockIdx.x;
+  double mx = 0.0, sm = 0.0;
+  if (n < N)
+    for (int64_t k = threadIdx.x; k <= n; k += blockDim.x) {
+      const double v = Linv[n + k * N];
+      mx = fmax(mx, fabs(v));
+      sm += v;
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    sm += __shfl_xor_sync(0xffffffffu, sm, o);
+  }
+  __shared__ double smx[8], ssm[8];
+  if ((threadIdx.x & 31) == 0) {
+    smx[threadIdx.x >> 5] = mx;
+    ssm[threadIdx.x >> 5] = sm;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      mx = fmax(mx, smx[w]);
+      sm += ssm[w];
+    }
+    if (n < rows) {
+      rowscale[n] = mx > 0.0 ? mx / FILL : 1.0;
+      rowsum[n] = sm;
+    }
+  }
+}
+
+template <int S>
+__global__ void linv_digits_kernel(const double* __restrict__ Linv, int64_t N, const double* __restrict__ rowscale,
+                                   int8_t* __restrict__ AS) {
+  const int I = blockIdx.y, kc = blockIdx.x;
+  if (kc >= 2 * (I + 1)) return;
+  int8_t* dst = AS + (oz::a_stage_offset(I) + kc) * (int64_t)(S * ATILE);
+  for (int e = threadIdx.x; e < 128 * KST; e += blockDim.x) {
+    const int r = e % 128, kin = e / 128;  // r fastest: column-major source is contiguous in n
+    const int64_t n = (int64_t)I * 128 + r, k = (int64_t)kc * KST + kin;
+    long long v = 0;
+    if (n < N && k <= n) v = __double2ll_rn(Linv[n + k * N] / rowscale[n] * two_pow_8S<S>());
+    uint32_t lo, hi;
+    digit_bytes<S>(v, lo, hi);
+    const unsigned long long w = ((unsigned long long)hi << 32) | lo;
+    const int off = (r >> 3) * SBO + (kin >> 4) * LBO + (r & 7) * 16 + (kin & 15);
+#pragma unroll
+    for (int p = 0; p < S; ++p) dst[p * ATILE + off] = (int8_t)((w >> (8 * (S - 1 - p))) & 0xff);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// centred K* digit tiles + posterior mean.  One CTA per candidate tile of NT candidates, NT/8 warps: warp w owns candidates
+// [8w, 8w+8); lane l <-> (candidate l % 8, 16-wide k chunk l / 8): every digit store of a warp is 512 contiguous bytes.
+//   inv_bscale_2p = 2^(8S) / sB,  sB = h / FILL,  h = variance / 2
+// ------------------------------------------------------------------------------------------------
+template <int KIND, int DP, int S>
+__global__ void __launch_bounds__(Geo<S>::NT * 4, 2)
+kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha, const double* __restrict__ Xc,
+                    const double* __restrict__ inv_ls, int N, int nst, int D, int64_t M, double variance, double inv_bscale_2p,
+                    double mean_const, int8_t* __restrict__ BS, double* __restrict__ mean_out) {
+  constexpr int NT = Geo<S>::NT, BTILE = NT * KST;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t tile_id = blockIdx.x;
+  const int cl = lane & 7, ch = lane >> 3;
+  const int t_local = w * 8 + cl;
+  const int64_t t = tile_id * NT + t_local;
+  const bool valid = t < M;
+  const double half_var = 0.5 * variance;
+  double xc[DP];
+#pragma unroll
+  for (int d = 0; d < DP; ++d) xc[d] = (valid && d < D) ? Xc[t * D + d] * inv_ls[d] : 0.0;
+  int8_t* tile = BS + tile_id * (int64_t)nst * (S * BTILE) + w * SBO + ch * LBO + cl * 16;
+  __shared__ __align__(16) double xs_s[2][KST * DP];
+  __shared__ __align__(16) double al_s[2][KST];
+  auto stage_load = [&](int kc, int buf) {
+    const double* src = Xs + (int64_t)kc * KST * DP;
+    for (int e = threadIdx.x; e < KST * DP / 2; e += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&xs_s[buf][2 * e])), "l"(src + 2 * e) : "memory");
+    for (int e = threadIdx.x; e < KST / 2; e += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&al_s[buf][2 * e])), "l"(alpha + (int64_t)kc * KST + 2 * e)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_load(0, 0);
+  double macc = 0.0;
+  for (int kc = 0; kc < nst; ++kc) {
+    const int buf = kc & 1;
+    if (kc + 1 < nst) {
+      stage_load(kc + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t pk[S][4];
+#pragma unroll
+    for (int p = 0; p < S; ++p) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int kl = ch * 16 + j, k = kc * KST + kl;
+      const double* xr = &xs_s[buf][kl * DP];
+      double r2 = 0.0;
+#pragma unroll
+      for (int d = 0; d < DP; d += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(xr + d);
+        double d0 = xc[d] - v.x, d1 = xc[d + 1] - v.y;
+        r2 = fma(d0, d0, r2);
+        r2 = fma(d1, d1, r2);
+      }
+      const bool live = valid && k < N;
+      const double kval = live ? kernel_from_r2<KIND>(r2, variance) : 0.0;
+      macc = fma(kval, al_s[buf][kl], macc);
+      uint32_t wl, wh;
+      digit_bytes<S>(live ? __double2ll_rn((kval - half_var) * inv_bscale_2p) : 0ll, wl, wh);
+      scatter_rt<S>(pk, j, wl, wh);
+    }
+#pragma unroll
+    for (int p = 0; p < S; ++p)
+      *reinterpret_cast<uint4*>(tile + (int64_t)kc * (S * BTILE) + p * BTILE) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+    __syncthreads();
+  }
+  macc += __shfl_xor_sync(0xffffffffu, macc, 8);
+  macc += __shfl_xor_sync(0xffffffffu, macc, 16);
+  if (ch == 0) mean_out[tile_id * NT + t_local] = macc + mean_const;
+}
+
+// all MMAs of one pipeline stage: S(S+1)/2 digit products x (KST / 32) k-steps, descriptors by two 32-bit adds each
+template <int S>
+__device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t stage_base, uint32_t not_first_kc) {
+  constexpr int NT = Geo<S>::NT, BTILE = NT * KST;
+  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t HI = ((SBO >> 4) & 0x3FFF) | (1u << 14);
+  const uint32_t a0 = ((stage_base >> 4) & 0x3FFF) | (((LBO >> 4) & 0x3FFF) << 16);
+  const uint32_t b0 = a0 + ((S * ATILE) >> 4);
+#pragma unroll
+  for (int p = 1; p <= S; ++p)
+#pragma unroll
+    for (int q = 1; q <= S; ++q) {
+      const int r = p + q;
+      if (r > S + 1) continue;
+      const uint32_t acc = tmem + (uint32_t)(r - 2) * NT;
+      const bool first_pair = (p == 1);
+#pragma unroll
+      for (int kk = 0; kk < KST / 32; ++kk) {
+        const uint32_t flag = (first_pair && kk == 0) ? not_first_kc : 1u;
+        const uint32_t a_lo = a0 + (((p - 1) * ATILE + kk * 2 * (int)LBO) >> 4), b_lo = b0 + (((q - 1) * BTILE + kk * 2 * (int)LBO) >> 4);
+        asm volatile(
+            "{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\nsetp.ne.b32 p, %5, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n}\n" ::"r"(acc),
+            "r"(a_lo), "r"(b_lo), "r"(HI), "r"(IDESC), "r"(flag)
+            : "memory");
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the GEMM: grid = (G row-block groups, candidate tiles); partial[g][t] = Σ_{rows n of group g} A[n,t]^2,
+//   A[n,t] = rowscale[n]·out_scale · Σ_{r=2..S+1} 2^(-8r) T_r[n,t]  +  half_var·rowsum[n]
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__((EW + 2) * 32, 1)
+trigemm_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, const double* __restrict__ rowscale,
+               const double* __restrict__ rowsum, int NB, int nst, int G, int64_t McPad, double out_scale, double half_var,
+               double* __restrict__ partial) {
+  constexpr int NT = Geo<S>::NT, BTILE = NT * KST, STAGE = S * (ATILE + BTILE);
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;      // MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * STAGES + 1; // epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x, tile = blockIdx.y;  // g fastest: co-resident CTAs share few candidate tiles -> K* digits stay in L2
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, EW);
+    fence_barrier_init();
+  }
+  if (warp == EW) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const int8_t* bTile = BS + (int64_t)tile * nst * (S * BTILE);
+
+  if (warp == EW) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int i = 0;; ++i) {
+        const int I = serpentine_rowblock(i, g, G);
+        if (I >= NB) break;
+        const int nk = min(2 * (I + 1), nst);
+        const int8_t* aRow = AS + oz::a_stage_offset(I) * (int64_t)(S * ATILE);
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&empty[st], ph ^ 1);
+          unsigned char* dst = smem + (size_t)st * STAGE;
+          mbar_expect_tx(&full[st], STAGE);
+          bulk_g2s(dst, aRow + (int64_t)kc * (S * ATILE), S * ATILE, &full[st]);
+          bulk_g2s(dst + S * ATILE, bTile + (int64_t)kc * (S * BTILE), S * BTILE, &full[st]);
+          if (++st == STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == EW + 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int st = 0, n = 0;
+      uint32_t ph = 0;
+      for (int i = 0;; ++i, ++n) {
+        const int I = serpentine_rowblock(i, g, G);
+        if (I >= NB) break;
+        const int nk = min(2 * (I + 1), nst);
+        if (n > 0) {  // accumulators must have been read out by the epilogue warps
+          mbar_wait(acc_empty, (uint32_t)((n - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&full[st], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          issue_stage<S>(tmem, smem_u32(smem + (size_t)st * STAGE), kc != 0 ? 1u : 0u);
+          oz::umma_commit(&empty[st]);
+          if (++st == STAGES) { st = 0; ph ^= 1; }
+        }
+        oz::umma_commit(acc_full);
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    // warp w reads TMEM lanes [32 (w%4), +32) (rows) and columns [NT/2 (w/4), +NT/2) of every level
+    const int lq = warp & 3, ch = warp >> 2;
+    constexpr int CW = NT / 2;  // 48 (S = 5) or 64 (S = 3) columns per warp
+    const uint32_t lane_base = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * CW);
+    double vacc[CW];
+    double colsum[CW / 16];
+#pragma unroll
+    for (int h = 0; h < CW / 16; ++h) colsum[h] = 0.0;
+    int n = 0;
+    for (int i = 0;; ++i, ++n) {
+      const int I = serpentine_rowblock(i, g, G);
+      if (I >= NB) break;
+      const int64_t nrow = (int64_t)I * 128 + lq * 32 + lane;
+      const double rs = rowscale[nrow] * out_scale;
+      const double rc = rowsum[nrow] * half_var;
+      mbar_wait(acc_full, (uint32_t)(n & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int h = 0; h < CW / 16; ++h) {
+        // Horner over the levels, least significant first: v = ((T_{S+1} 2^-8 + T_S) 2^-8 + ...) ; final factor 2^-16 for r = 2
+        uint32_t t[16];
+        oz::tmem_ld16(lane_base + (uint32_t)((S - 1) * NT) + h * 16, t);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) vacc[h * 16 + c] = (double)(int)t[c];
+#pragma unroll
+        for (int l = S - 2; l >= 0; --l) {
+          oz::tmem_ld16(lane_base + (uint32_t)(l * NT) + h * 16, t);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) vacc[h * 16 + c] = fma(vacc[h * 16 + c], 0x1p-8, (double)(int)t[c]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);  // accumulators are free again: the next row-block's MMAs start now
+      // A = rs 2^-16 v + rc; column sums of A^2 over the warp's 32 rows by recursive halving
+      const double rs16 = rs * 0x1p-16;
+#pragma unroll
+      for (int h = 0; h < CW / 16; ++h) {
+        double a[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const double v = fma(vacc[h * 16 + c], rs16, rc);
+          a[c] = v * v;
+        }
+        double b8[8], b4[4], b2[2];
+        bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const double mine = up ? a[8 + c] : a[c], theirs = up ? a[c] : a[8 + c];
+          b8[c] = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
+        }
+        up = (lane & 8) != 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double mine = up ? b8[4 + c] : b8[c], theirs = up ? b8[c] : b8[4 + c];
+          b4[c] = mine + __shfl_xor_sync(0xffffffffu, theirs, 8);
+        }
+        up = (lane & 4) != 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const double mine = up ? b4[2 + c] : b4[c], theirs = up ? b4[c] : b4[2 + c];
+          b2[c] = mine + __shfl_xor_sync(0xffffffffu, theirs, 4);
+        }
+        up = (lane & 2) != 0;
+        double e = (up ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, up ? b2[0] : b2[1], 2);
+        e += __shfl_xor_sync(0xffffffffu, e, 1);
+        colsum[h] += e;  // lane holds column h*16 + (lane >> 1) (both lanes of a pair hold the same sum)
+      }
+    }
+    // combine the four row-quarters (warps lq = 0..3 of the same column half) through shared memory
+    // (every MMA has retired and every stage has been consumed, so the stage buffers are free)
+    double (*redbuf)[CW] = reinterpret_cast<double (*)[CW]>(smem);
+    if ((lane & 1) == 0) {
+#pragma unroll
+      for (int h = 0; h < CW / 16; ++h) redbuf[warp][h * 16 + (lane >> 1)] = colsum[h];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EW * 32));
+    for (int col = threadIdx.x; col < NT; col += EW * 32) {
+      const int cg = col / CW, cc = col % CW, wb = cg * 4;
+      partial[(int64_t)g * McPad + (int64_t)tile * NT + col] = redbuf[wb][cc] + redbuf[wb + 1][cc] + redbuf[wb + 2][cc] + redbuf[wb + 3][cc];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == EW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+}  // namespace oz5
+}  // namespace tb

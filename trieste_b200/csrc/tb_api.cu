@@ -3,6 +3,7 @@
 #include "gp_handle.cuh"
 #include "kernels_extra.cuh"
 #include "ozaki.cuh"
+#include "oz5_api.h"
 #include "factor.cuh"
 #include "lbfgs.cuh"
 
@@ -223,13 +224,13 @@ __global__ void colmajor_lower_to_rowmajor_kernel(const double* __restrict__ A, 
   do {                                                                                             \
     cusolverStatus_t _s = (expr);                                                                  \
     if (_s != CUSOLVER_STATUS_SUCCESS) return tb::fail(std::string(#expr) + ": cusolver status " + \
-                                                       std::to_string((int)_s));                   \
+                                                       std::to_string((int)_s), tb::ERR_RUNTIME);  \
   } while (0)
 #define TB_CUBLAS(expr)                                                                        \
   do {                                                                                         \
     cublasStatus_t _s = (expr);                                                                \
     if (_s != CUBLAS_STATUS_SUCCESS) return tb::fail(std::string(#expr) + ": cublas status " + \
-                                                     std::to_string((int)_s));                 \
+                                                     std::to_string((int)_s), tb::ERR_RUNTIME);\
   } while (0)
 
 static const char* kVersion = "trieste_b200 0.1 (sm_100a; fp64 DMMA triangular GEMM)";
@@ -244,7 +245,7 @@ int tb_device_count(int* count) {
   if (e != cudaSuccess) {
     *count = 0;
     cudaGetLastError();
-    return tb::fail(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return tb::fail(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e), tb::ERR_RUNTIME);
   }
   return 0;
 }
@@ -256,7 +257,7 @@ int tb_gp_create(tb_gp** out, int device, int dtype) {
   TB_CHECK(dtype == TB_F64 || dtype == TB_F32, "tb_gp_create: dtype must be TB_F64 or TB_F32");
   int n = 0;
   TB_TRY(tb_device_count(&n));
-  TB_CHECK(n > 0, "tb_gp_create: no CUDA device visible (this library has no CPU fallback)");
+  TB_CHECK_CODE(n > 0, "tb_gp_create: no CUDA device visible (this library has no CPU fallback)", tb::ERR_RUNTIME);
   TB_CHECK(device >= 0 && device < n, "tb_gp_create: device index out of range");
   TB_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -413,6 +414,7 @@ static int finish_cache(tb_gp* gp) {
   gp->cache_valid = true;
   gp->upper_valid = false;
   gp->oz_valid = false;
+  gp->oz5_valid = false;
   gp->kinv_valid = false;
   return 0;
 }
@@ -468,8 +470,8 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
     TB_CUDA(cudaMemcpyAsync(&info, gp->dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     TB_CUDA(cudaStreamSynchronize(st));
     TB_CUDA(cudaGetLastError());
-    TB_CHECK(info == 0, "tb_gp_update_posterior_cache: Cholesky decomposition was not successful "
-                        "(K + noise*I not positive definite at leading minor " + std::to_string(info) + ")");
+    TB_CHECK_CODE(info == 0, "tb_gp_update_posterior_cache: Cholesky decomposition was not successful "
+                        "(K + noise*I not positive definite at leading minor " + std::to_string(info) + ")", tb::ERR_NUMERIC);
     {
       dim3 grid((unsigned)((N + 127) / 128), (unsigned)N);
       zero_upper_kernel<<<grid, 128, 0, st>>>(N, A);
@@ -503,8 +505,8 @@ int tb_gp_update_posterior_cache(tb_gp* gp) {
     int info = 0;
     TB_CUDA(cudaMemcpyAsync(&info, gp->dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     TB_CUDA(cudaStreamSynchronize(st));
-    TB_CHECK(info == 0, "tb_gp_update_posterior_cache: Cholesky decomposition was not successful "
-                        "(K + noise*I not positive definite at leading minor " + std::to_string(info) + ")");
+    TB_CHECK_CODE(info == 0, "tb_gp_update_posterior_cache: Cholesky decomposition was not successful "
+                        "(K + noise*I not positive definite at leading minor " + std::to_string(info) + ")", tb::ERR_NUMERIC);
     {
       dim3 grid((unsigned)((N + 127) / 128), (unsigned)N);
       zero_upper_kernel<<<grid, 128, 0, st>>>(N, gp->dL.as<double>());
@@ -605,8 +607,8 @@ static int tb_gp_append_data_f64(tb_gp* gp, const double* Xnew, const double* yn
   TB_CUDA(cudaMemcpyAsync(&info, gp->dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
   TB_CUDA(cudaGetLastError());
-  TB_CHECK(info == 0, "tb_gp_append_data: Cholesky decomposition was not successful "
-                      "(K + noise*I not positive definite at leading minor " + std::to_string(info) + ")");
+  TB_CHECK_CODE(info == 0, "tb_gp_append_data: Cholesky decomposition was not successful "
+                      "(K + noise*I not positive definite at leading minor " + std::to_string(info) + ")", tb::ERR_NUMERIC);
   TB_TRY(alpha_from_linv(gp));
   return finish_cache(gp);
 }
@@ -707,6 +709,7 @@ int kernels_init() {
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_lowreg_kernel<oz::OZ_SUMSQ, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
   TB_CUDA(cudaFuncSetAttribute(oz::trigemm_i8_kernel<oz::OZ_STORE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
+  TB_TRY(oz5_init());
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_SUMSQ_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
   TB_CUDA(cudaFuncSetAttribute(trigemm_kernel<false, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
@@ -943,23 +946,27 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
     TB_CUDA(cudaMemcpyAsync((char*)gp->sRun.p + 8, &init_i, 8, cudaMemcpyHostToDevice, sa));
   }
   if (rq.M == 0) return 0;
-  TB_TRY(ensure_ozaki(gp));
+  // single-pass engine (15 / 6 digit products) when its a-priori error estimate clears the bar, else the 6-digit kernels
+  TB_TRY(oz5_ensure(gp));
+  const bool fast = gp->oz5_mode != 0;
+  if (!fast) TB_TRY(ensure_ozaki(gp));
   TB_CUDA(cudaStreamSynchronize(sa));  // digit tiles of Linv are built on stream A; stream B reads model state too
+  const int nt = fast ? oz5_tile_width(gp) : BT;  // candidates per tile
 
   const bool xc_dev = is_device_ptr(rq.Xc);
   const bool vals_dev = is_device_ptr(rq.out_vals), mean_dev = is_device_ptr(rq.out_mean), var_dev = is_device_ptr(rq.out_var);
   // half the usual scratch budget per slot (two slots are live)
-  const size_t per_tile = (size_t)gp->nst * oz::S * oz::TILE;
+  const size_t per_tile = fast ? oz5_tile_bytes(gp) : (size_t)gp->nst * oz::S * oz::TILE;
   int64_t max_tiles = std::max<int64_t>(1, (int64_t)(((size_t)1024 << 20) / per_tile));
   if (max_tiles >= 148) max_tiles = (max_tiles / 148) * 148;
   max_tiles = std::min<int64_t>(max_tiles, 148 * 8);
-  const int64_t chunk_cap = std::min<int64_t>(max_tiles * BT, ((rq.M + BT - 1) / BT) * BT);
-  const int64_t tiles_cap = chunk_cap / BT;
+  const int64_t chunk_cap = std::min<int64_t>(max_tiles * nt, ((rq.M + nt - 1) / nt) * nt);
+  const int64_t tiles_cap = chunk_cap / nt;
   // row-block groups per candidate tile: ~4 row-blocks per CTA amortise the CTA prologue while the co-resident CTAs still
   // share few enough candidate tiles for the K* digits to live in L2; small batches get more groups to fill the GPU
   int G = std::max(1, (gp->NB + 3) / 4);
   {
-    const int64_t tiles_all = std::min<int64_t>(tiles_cap, (rq.M + BT - 1) / BT);
+    const int64_t tiles_all = std::min<int64_t>(tiles_cap, (rq.M + nt - 1) / nt);
     if (tiles_all * G < 2 * 148) G = (int)std::min<int64_t>(gp->NB, (2 * 148 + tiles_all - 1) / tiles_all);
   }
   if (const char* e = std::getenv("TB_OZ_G")) G = std::max(1, std::min(std::atoi(e), gp->NB));  // experiment knob
@@ -985,8 +992,8 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
   for (int64_t c0 = 0; c0 < rq.M; c0 += chunk_cap, ++c) {
     const int slot = (int)(c & 1);
     const int64_t mc = std::min<int64_t>(chunk_cap, rq.M - c0);
-    const int tiles = (int)((mc + BT - 1) / BT);
-    const int64_t McPad = (int64_t)tiles * BT;
+    const int tiles = (int)((mc + nt - 1) / nt);
+    const int64_t McPad = (int64_t)tiles * nt;
     // ---- stream B: candidates in, K* digits + mean out ----
     if (c >= 2) TB_CUDA(cudaStreamWaitEvent(sb, gp->evDone[slot], 0));
     const double* xc_chunk;
@@ -996,7 +1003,9 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
       TB_CUDA(cudaMemcpyAsync(gp->sXc.p, rq.Xc + c0 * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, sb));
       xc_chunk = gp->sXc.as<double>();
     }
-    {
+    if (fast) {
+      TB_TRY(oz5_launch_kstar(gp, sb, xc_chunk, mc, tiles, ks[slot]->as<int8_t>(), mean[slot]->as<double>()));
+    } else {
       cudaStream_t keep = gp->stream;
       gp->stream = sb;  // launch_kstar_digits launches on gp->stream
       int rc = launch_kstar_digits(gp, xc_chunk, mc, tiles, ks[slot]->as<int8_t>(), mean[slot]->as<double>());
@@ -1012,7 +1021,9 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
       TB_CUDA(cudaEventCreate(&e1));
       TB_CUDA(cudaEventRecord(e0, sa));
     }
-    if (sb != sa)  // overlapped K* generation: register-capped GEMM so that generation CTAs fit beside it
+    if (fast)
+      TB_TRY(oz5_launch_gemm(gp, sa, ks[slot]->as<int8_t>(), tiles, G, McPad, part[slot]->as<double>()));
+    else if (sb != sa)  // overlapped K* generation: register-capped GEMM so that generation CTAs fit beside it
       oz::trigemm_i8_lowreg_kernel<oz::OZ_SUMSQ, 8><<<dim3(G, tiles), 10 * 32, oz::SMEM_BYTES, sa>>>(
           gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
           oz_npass(gp), 0, part[slot]->as<double>(), nullptr, 0);
@@ -1020,7 +1031,7 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
       oz::trigemm_i8_kernel<oz::OZ_SUMSQ, 8><<<dim3(G, tiles), 10 * 32, oz::SMEM_BYTES, sa>>>(
           gp->dAS.as<int8_t>(), ks[slot]->as<int8_t>(), gp->dRowScale.as<double>(), gp->NB, gp->nst, G, McPad, gp->oz_out_scale,
           oz_npass(gp), 0, part[slot]->as<double>(), nullptr, 0);
-    TB_LAUNCHED();
+    if (!fast) TB_LAUNCHED();
     if (gp->profile) {
       TB_CUDA(cudaEventRecord(e1, sa));
       gp->prof_events.emplace_back(e0, e1);
@@ -1301,8 +1312,27 @@ int tb_gp_profile(tb_gp* gp, int enable) {
 }
 int tb_gp_set_engine(tb_gp* gp, int engine) {
   TB_CHECK(gp, "tb_gp_set_engine: null handle");
-  TB_CHECK(engine == 0 || engine == 1, "tb_gp_set_engine: engine must be 0 (fp64 DMMA) or 1 (int8 Ozaki)");
-  gp->engine = engine;
+  TB_CHECK(engine >= 0 && engine <= 2, "tb_gp_set_engine: engine must be 0 (fp64 DMMA), 1 (int8 Ozaki) or 2 (int8, full 21 products)");
+  gp->engine = engine == 0 ? 0 : 1;
+  if (gp->oz_full != (engine == 2)) gp->oz5_valid = false;
+  gp->oz_full = engine == 2;
+  return 0;
+}
+int tb_gp_engine_info(tb_gp* gp, int* digit_products, double* error_estimate) {
+  TB_CHECK(gp, "tb_gp_engine_info: null handle");
+  TB_CHECK(gp->cache_valid, "tb_gp_engine_info: posterior cache is not built");
+  int products = 0;
+  double est = 0.0;
+  if (gp->engine == 1 && gp->N <= 16384) {
+    TB_CUDA(cudaSetDevice(gp->device));
+    TB_TRY(oz5_ensure(gp));
+    if (gp->oz5_mode == 5) products = 15;
+    else if (gp->oz5_mode == 3) products = 6;
+    else products = gp->dtype == TB_F32 ? 10 : 21;
+    est = gp->oz5_est;
+  }
+  if (digit_products) *digit_products = products;
+  if (error_estimate) *error_estimate = est;
   return 0;
 }
 int tb_gp_kinv_apply(tb_gp* gp, const double* B, int nrhs, double* out) {
@@ -1490,8 +1520,8 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
   TB_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
   TB_CUDA(cudaGetLastError());
-  TB_CHECK(herr == 0, "Cholesky decomposition was not successful. The input might not be valid "
-                      "(covariance + jitter*I of a query batch is not positive definite)");
+  TB_CHECK_CODE(herr == 0, "Cholesky decomposition was not successful. The input might not be valid "
+                      "(covariance + jitter*I of a query batch is not positive definite)", tb::ERR_NUMERIC);
   return 0;
 }
 
@@ -1700,8 +1730,8 @@ static int run_sample_joint(tb_gp* gp, const double* Xc, int64_t M, const double
   TB_CUDA(cudaMemcpyAsync(&info, gp->dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
   TB_CUDA(cudaGetLastError());
-  TB_CHECK(info == 0, "Cholesky decomposition was not successful. The input might not be valid "
-                      "(joint covariance + jitter*I is not positive definite at leading minor " + std::to_string(info) + ")");
+  TB_CHECK_CODE(info == 0, "Cholesky decomposition was not successful. The input might not be valid "
+                      "(joint covariance + jitter*I is not positive definite at leading minor " + std::to_string(info) + ")", tb::ERR_NUMERIC);
   // samples = mean + L z
   const double* zd = z;
   if (!is_device_ptr(z)) {
@@ -1890,8 +1920,8 @@ static int run_qei_grad(tb_gp* gp, const double* Xc, int64_t B, int q, const dou
   TB_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
   TB_CUDA(cudaGetLastError());
-  TB_CHECK(herr == 0, "Cholesky decomposition was not successful. The input might not be valid "
-                      "(covariance + jitter*I of a query batch is not positive definite)");
+  TB_CHECK_CODE(herr == 0, "Cholesky decomposition was not successful. The input might not be valid "
+                      "(covariance + jitter*I of a query batch is not positive definite)", tb::ERR_NUMERIC);
   return 0;
 }
 
@@ -2014,7 +2044,7 @@ int tb_rff_create(tb_rff** out, int device) {
   TB_CHECK(out, "tb_rff_create: null output");
   int n = 0;
   TB_TRY(tb_device_count(&n));
-  TB_CHECK(n > 0, "tb_rff_create: no CUDA device visible (this library has no CPU fallback)");
+  TB_CHECK_CODE(n > 0, "tb_rff_create: no CUDA device visible (this library has no CPU fallback)", tb::ERR_RUNTIME);
   TB_CHECK(device >= 0 && device < n, "tb_rff_create: device index out of range");
   TB_CUDA(cudaSetDevice(device));
   tb_rff* r = new tb_rff();

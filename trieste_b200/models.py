@@ -158,14 +158,23 @@ class GaussianProcessRegression:
     def set_engine(self, engine: str) -> None:
         """Engine of the variance GEMM (predict / EI / LCB / log-EI / argmax): ``"fp64"`` = native DMMA,
         ``"int8"`` = fp64-accurate Ozaki splitting on the INT8 tensor cores (same stated tolerances)."""
-        if engine not in ("fp64", "int8"):
-            raise ValueError(f"engine must be 'fp64' or 'int8', got {engine!r}")
-        _lib.check(_lib.lib().tb_gp_set_engine(self._h, 1 if engine == "int8" else 0))
+        if engine not in ("fp64", "int8", "int8x21"):
+            raise ValueError(f"engine must be 'fp64', 'int8' or 'int8x21', got {engine!r}")
+        # "int8" picks the number of digit products (15 or 21; fp32 models 6 or 10) from the a-priori error estimate of the
+        # cache; "int8x21" pins the full 21-product kernels
+        _lib.check(_lib.lib().tb_gp_set_engine(self._h, {"fp64": 0, "int8": 1, "int8x21": 2}[engine]))
         self._engine = engine
 
     @property
     def engine(self) -> str:
         return getattr(self, "_engine", "int8" if os.environ.get("TB_ENGINE", "int8") != "fp64" else "fp64")
+
+    def engine_info(self) -> Tuple[int, float]:
+        """(int8 digit products per k-step of the variance GEMM — 15 / 21, fp32 models 6 / 10, 0 = native fp64 engine —,
+        a-priori estimate of max |Δvar| / σ_f² of a reduced mode)."""
+        n, est = C.c_int(0), C.c_double(0.0)
+        _lib.check(_lib.lib().tb_gp_engine_info(self._h, C.byref(n), C.byref(est)))
+        return n.value, est.value
 
     def update_posterior_cache(self) -> None:
         """interface.py:108-112 — must follow any change of data or hyper-parameters."""

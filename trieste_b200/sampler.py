@@ -446,6 +446,7 @@ class DecoupledTrajectorySampler:
         u = torch.as_tensor(resid[:, 0][None, :] + math.sqrt(self._model.get_observation_noise()) * np.asarray(eps), device=dev)
         diff = (u - torch.as_tensor(np.asarray(prior_w), device=dev) @ phi_Z.T).contiguous()  # [B, N]
         out = torch.empty_like(diff)
+        _lib.sync_torch_stream(diff)  # diff was produced on torch's stream; the library reads it on the handle's stream
         _lib.check(_lib.lib().tb_gp_kinv_apply(self._model.handle, diff.data_ptr(), diff.shape[0], out.data_ptr()))
         return out.cpu().numpy()
 
