@@ -320,6 +320,23 @@ def log_expected_improvement(mean, var, eta):
     return out + np.log(sigma)
 
 
+def log_ei_gradient(m: GPRModel, Xq: np.ndarray, eta: float):
+    """Value and gradient of :func:`log_expected_improvement` (ours; parity unpinned like the value).  With EI = sigma h(z),
+    h = z Phi + phi:  d log EI / d mean = -(Phi / h) / sigma,  d log EI / d var = (phi / h) / (2 var); the two ratios are
+    formed in log space so they stay finite where EI underflows."""
+    mean, var = predict(m, Xq)
+    dmean, dvar = posterior_gradients(m, Xq)
+    sigma = np.sqrt(var)
+    z = (eta - mean) / sigma
+    val = log_expected_improvement(mean, var, eta)
+    log_h = val - np.log(sigma)
+    Phi_over_h = np.exp(ssp.log_ndtr(z) - log_h)
+    phi_over_h = np.exp(-0.5 * z * z - 0.5 * math.log(2.0 * math.pi) - log_h)
+    clipped = var <= VAR_CLIP
+    g = -(Phi_over_h / sigma) * dmean + np.where(clipped, 0.0, phi_over_h / (2.0 * var)) * dvar
+    return val, g
+
+
 def ei_gradient(m: GPRModel, Xq: np.ndarray, eta: float):
     """Value and d EI / d x*: dEI/dmean = -Phi(z), dEI/dvar = phi(z) / (2 sigma)."""
     mean, var = predict(m, Xq)
@@ -599,3 +616,64 @@ def decoupled_trajectory(m: GPRModel, Xq, W, b, prior_w, v, chunk: int = 32768):
 def probability_below_threshold(mean, var, threshold):
     """trieste/acquisition/function/function.py:507-509: Normal(mean, sqrt(var)).cdf(threshold)."""
     return ndtr((threshold - mean) / np.sqrt(var))
+
+
+# --------------------------------------------------------------------------------------------
+# multiple_optimism_lower_confidence_bound — trieste/acquisition/function/function.py:1857-1911
+# --------------------------------------------------------------------------------------------
+def molcb_betas(batch_size: int, search_space_dim: int) -> np.ndarray:
+    """:1898-1905: spread = 0.5 + 0.5 * (1..B) / (B + 1); betas = 5 * d * Normal(0,1).quantile(spread)."""
+    spread = 0.5 + 0.5 * np.arange(1, batch_size + 1, dtype=np.float64) / (batch_size + 1.0)
+    return 5.0 * search_space_dim * ssp.ndtri(spread)
+
+
+def multiple_optimism_lower_confidence_bound(m: GPRModel, Xb: np.ndarray, search_space_dim: int) -> np.ndarray:
+    """:1907-1911: x [..., B, D] -> -mean + sqrt(var) * betas, shape [..., B]."""
+    Xb = np.asarray(Xb, dtype=np.float64)
+    B, D = Xb.shape[-2], Xb.shape[-1]
+    mean, var = predict(m, Xb.reshape(-1, D))
+    mean, var = mean.reshape(Xb.shape[:-1]), var.reshape(Xb.shape[:-1])
+    return -mean + np.sqrt(var) * molcb_betas(B, search_space_dim)
+
+
+# --------------------------------------------------------------------------------------------
+# conditional predictions (FastUpdateModel) — trieste/models/gpflow/models.py:355-425 (Chevalier et al. 2014,
+# eqs. 8-10), the posterior the reference's Fantasizer evaluates through _fantasized_model
+# (acquisition/function/greedy_batch.py:630-770)
+# --------------------------------------------------------------------------------------------
+def conditional_predict_f(m: GPRModel, Xq: np.ndarray, X_add: np.ndarray, y_add: np.ndarray):
+    """models.py:383-425 written out: mean_add / cov_add at the additional points (:383-385), cross covariance
+    (:386-390), L = chol(cov_add + noise I) (:392-397), A = L^-1 cov_cross, mean_new = mean_qp + A^T L^-1 (y_add - mean_add),
+    var_new = var_qp - sum A^2 (:399-420).  Xq [M, D], X_add [N2, D], y_add [N2, 1]."""
+    mean_add, cov_add = predict_f(m, X_add, full_cov=True)
+    cov_cross = covariance_between_points(m, X_add, Xq)[0]  # [1, N2, M] -> [N2, M]
+    L = sla.cholesky(cov_add + m.noise * np.eye(X_add.shape[0]), lower=True)
+    A = sla.solve_triangular(L, cov_cross, lower=True)
+    AM = sla.solve_triangular(L, np.asarray(y_add, dtype=np.float64) - mean_add, lower=True)
+    mean_qp, var_qp = predict_f(m, Xq)
+    return mean_qp + A.T @ AM, var_qp - np.sum(A * A, axis=0)[:, None]
+
+
+# --------------------------------------------------------------------------------------------
+# the reference's continuous optimiser engine — trieste/acquisition/optimizer.py:566-745: one
+# scipy.optimize.minimize(method="l-bfgs-b", jac=True, bounds=...) per start on the NEGATED function (:721-738),
+# default options (:719: none beyond SciPy's own), best run = argmax over the runs' values (:556-559)
+# --------------------------------------------------------------------------------------------
+def scipy_lbfgsb_multistart(value_and_gradient, starts: np.ndarray, lower, upper, options=None):
+    """``value_and_gradient(x [n, D]) -> (f [n], g [n, D])`` of the function to MAXIMISE.  Returns
+    (success [P] bool, fun [P] maximised values, x [P, D], nfev [P])."""
+    from scipy import optimize as spo
+
+    starts = np.asarray(starts, dtype=np.float64)
+    P, D = starts.shape
+    bounds = spo.Bounds(np.broadcast_to(np.asarray(lower, dtype=np.float64), (D,)), np.broadcast_to(np.asarray(upper, dtype=np.float64), (D,)))
+    ok, fun, xs, nfev = np.zeros(P, bool), np.zeros(P), np.zeros((P, D)), np.zeros(P, np.int64)
+
+    def neg(x):
+        f, g = value_and_gradient(x[None, :])
+        return -float(np.asarray(f).reshape(-1)[0]), -np.asarray(g, dtype=np.float64).reshape(-1)
+
+    for p in range(P):
+        res = spo.minimize(neg, starts[p], jac=True, bounds=bounds, method="l-bfgs-b", options=dict(options or {}))
+        ok[p], fun[p], xs[p], nfev[p] = res.success, -res.fun, res.x, res.nfev
+    return ok, fun, xs, nfev

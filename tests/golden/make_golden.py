@@ -21,6 +21,11 @@ CASES = [
     ("hartmann6_n200_matern52", o.hartmann_6, 200, 6, "matern52", None),
     ("hartmann6_n200_rbf", o.hartmann_6, 200, 6, "rbf", None),
     ("ackley10_n300_matern32", o.ackley, 300, 10, "matern32", None),
+    # round 2: the non-differentiable Matern12, and the benchmark sizes (training data regenerated from the seed by the test:
+    # the fixture stores the generator's name instead of X, y)
+    ("hartmann6_n300_matern12", o.hartmann_6, 300, 6, "matern12", None),
+    ("hartmann6_n1024_matern52", o.hartmann_6, 1024, 6, "matern52", None),
+    ("ackley10_n4096_matern52", o.ackley, 4096, 10, "matern52", None),
 ]
 
 
@@ -36,9 +41,10 @@ def main():
         g = GaussianProcessRegressor(k, alpha=om.noise, optimizer=None, normalize_y=False).fit(om.X, om.y - om.mean_const)
         Xq = np.random.default_rng(11).uniform(size=(64, D))
         mu, cov = g.predict(Xq, return_cov=True)
+        data = dict(X=om.X, y=om.y) if N <= 300 else dict(generator=obj.__name__, N=N, D=D, seed=0)
         np.savez_compressed(
             os.path.join(HERE, f"gpr_sklearn_{name}.npz"),
-            X=om.X, y=om.y, kind=kind, variance=om.variance, lengthscales=om.lengthscales, noise=om.noise,
+            **data, kind=kind, variance=om.variance, lengthscales=om.lengthscales, noise=om.noise,
             mean_const=om.mean_const, Xq=Xq, mean=mu.reshape(-1) + om.mean_const, var=np.diag(cov).copy(), cov=cov,
         )
         print(name, "ok")

@@ -36,7 +36,9 @@ def test_device_lbfgs_reaches_first_order_points_and_matches_host(which, monkeyp
     assert ok.shape == (200,) and x.shape == (200, 6) and (x >= 0).all() and (x <= 1).all()
     assert ok.mean() > 0.9
     f0 = fn(x0[:, None, :])[:, 0]
-    assert np.all(val >= f0 - 1e-9 * np.abs(f0).max())  # never worse than the start
+    # never worse than the start (the start values come from the value-only kernels, the optimiser's from the
+    # value+gradient kernels: tail quantities such as MES agree to ~1e-8 relative between the two digit engines)
+    assert np.all(val >= f0 - 1e-6 * np.abs(f0) - 1e-9 * np.abs(f0).max())
     np.testing.assert_allclose(val, fn(x[:, None, :])[:, 0], rtol=1e-6, atol=1e-9 * np.abs(val).max())
     if which != "ei":  # plain EI is flat (~0, gradient ~0) far from the data: gtol is met immediately there
         pg = _proj_grad(fn, x[ok], lower, upper)

@@ -6,6 +6,8 @@ from .function import (  # noqa: F401
     LogExpectedImprovement,
     MinValueEntropySearch,
     MonteCarloExpectedImprovement,
+    MultipleOptimismNegativeLowerConfidenceBound,
+    multiple_optimism_lower_confidence_bound,
     monte_carlo_expected_improvement,
     min_value_entropy_search,
     NegativeLowerConfidenceBound,
@@ -17,4 +19,13 @@ from .function import (  # noqa: F401
     lower_confidence_bound,
     probability_below_threshold,
 )
-from .interface import AcquisitionFunctionBuilder, SingleModelAcquisitionBuilder  # noqa: F401
+from .greedy_batch import Fantasizer  # noqa: F401
+from .interface import (  # noqa: F401
+    AcquisitionFunctionBuilder,
+    GreedyAcquisitionFunctionBuilder,
+    SingleModelAcquisitionBuilder,
+    SingleModelGreedyAcquisitionBuilder,
+    SingleModelVectorizedAcquisitionBuilder,
+    VectorizedAcquisitionFunctionBuilder,
+)
+from .utils import split_acquisition_function, split_acquisition_function_calls  # noqa: F401

@@ -15,7 +15,7 @@ import numpy as np
 from .. import _lib
 from ..data import Dataset
 from ..models import GaussianProcessRegression, _flatten_leading, _ptr
-from .interface import AcquisitionFunctionClass, SingleModelAcquisitionBuilder
+from .interface import AcquisitionFunctionClass, SingleModelAcquisitionBuilder, SingleModelVectorizedAcquisitionBuilder
 
 JITTER = 1e-6  # trieste/utils/misc.py:183
 
@@ -200,8 +200,15 @@ def lower_confidence_bound(model, beta: float):
 
 
 def _eta_from_model(model, dataset: Dataset, search_space=None) -> float:
-    """function.py:133-149: eta = min over the (feasible) training inputs of the posterior mean."""
+    """function.py:133-149: eta = min over the FEASIBLE training inputs of the posterior mean; with a constrained search
+    space only the query points that satisfy the constraints count, and if none does eta = max of the mean."""
     mean, _ = model.predict(np.asarray(dataset.query_points))
+    mean = np.asarray(_to_host(mean))
+    if search_space is not None and getattr(search_space, "has_constraints", False):
+        feasible = np.asarray(search_space.is_feasible(np.asarray(dataset.query_points)), dtype=bool).reshape(-1)
+        if not feasible.any():
+            return float(np.max(mean, axis=0)[0])
+        mean = mean[feasible]
     return float(np.min(mean, axis=0)[0])
 
 
@@ -305,6 +312,7 @@ class MinValueEntropySearch(SingleModelAcquisitionBuilder):
                     "however the passed sampler has sample_min_value=False."
                 )
         self._seed = seed
+        self._draws = 0
         self._min_value_sampler = min_value_sampler  # None: chosen per draw (see _draw)
         self._search_space = search_space
         self._num_samples = num_samples
@@ -320,15 +328,17 @@ class MinValueEntropySearch(SingleModelAcquisitionBuilder):
         grid = np.asarray(self._search_space.sample(self._grid_size))
         query_points = np.concatenate([np.asarray(dataset.query_points, dtype=grid.dtype), grid], axis=0)
         sampler = self._min_value_sampler
+        # a seeded builder is reproducible: draw k of the builder uses seed + k for the samplers that take a per-call seed
+        draw_seed = None if self._seed is None else int(self._seed) + self._draws
+        self._draws += 1
         if sampler is None:
             # entropy.py:111: the reference default is ExactThompsonSampler(sample_min_value=True) — joint samples over the
             # data and the grid; beyond the device path's point limit the Gumbel sampler (marginals only) takes over
             from .sampler import ExactThompsonSampler, GumbelSampler
 
             if query_points.shape[0] <= self.MAX_EXACT_POINTS:
-                sampler = ExactThompsonSampler(sample_min_value=True)
-            else:
-                sampler = GumbelSampler(sample_min_value=True, seed=self._seed)
+                return ExactThompsonSampler(sample_min_value=True).sample(model, self._num_samples, query_points, seed=draw_seed)
+            sampler = GumbelSampler(sample_min_value=True, seed=draw_seed)
         return sampler.sample(model, self._num_samples, query_points)
 
     def prepare_acquisition_function(self, model, dataset: Optional[Dataset] = None):
@@ -371,6 +381,81 @@ class NegativeLowerConfidenceBound(SingleModelAcquisitionBuilder):
 
     def update_acquisition_function(self, function, model, dataset: Optional[Dataset] = None):
         return function  # no dependence on data (function.py:361-372)
+
+
+class multiple_optimism_lower_confidence_bound(AcquisitionFunctionClass):
+    """function.py:1857-1911 (MOLCB, Torossian et al. 2020): a VECTORISED function ``[..., B, D] -> [..., B]``; column b is
+    the negated lower confidence bound ``-mean + beta_b sqrt(var)`` with ``beta_b = 5 d Phi^-1(0.5 + 0.5 b / (B + 1))``, b = 1..B,
+    fixed at the first call (a later call with another batch size is an error, as in the reference).  Each column runs the
+    fused predict + NegLCB kernels with its own beta (value and gradient), so ``batchify_vectorize`` optimises the B
+    columns independently."""
+
+    def __init__(self, model, search_space_dim: int):
+        if search_space_dim <= 0:
+            raise ValueError(f"search_space_dim must be positive, got {search_space_dim}")
+        self._model = _require_native(model)
+        self._search_space_dim = int(search_space_dim)
+        self._betas: Optional[np.ndarray] = None  # [B], lazily initialised
+        self._columns = []
+
+    @property
+    def betas(self) -> Optional[np.ndarray]:
+        return self._betas
+
+    def _prepare(self, x):
+        if len(x.shape) < 2:
+            raise ValueError(f"expected [..., B, D] query batches, got shape {tuple(x.shape)}")
+        B = int(x.shape[-2])
+        if B <= 0:
+            raise ValueError("batch size must be positive")
+        if self._betas is None:
+            from statistics import NormalDist
+
+            spread = 0.5 + 0.5 * np.arange(1, B + 1, dtype=np.float64) / (B + 1.0)
+            self._betas = 5.0 * self._search_space_dim * np.array([NormalDist().inv_cdf(p) for p in spread])
+            self._columns = [_lcb(self._model, float(b), negate=True) for b in self._betas]
+        elif B != self._betas.shape[0]:
+            raise ValueError(
+                f"{type(self).__name__} requires a fixed batch size. Got batch size {B} but previous batch size was "
+                f"{self._betas.shape[0]}."
+            )
+        return B
+
+    def __call__(self, x):
+        x = x if hasattr(x, "shape") else np.asarray(x)
+        B = self._prepare(x)
+        cols = [_to_host(self._columns[b](x[..., b : b + 1, :])) for b in range(B)]  # each [..., 1]
+        return np.concatenate(cols, axis=-1)
+
+    def value_and_gradient(self, x):
+        """[..., B, D] -> (values [..., B], gradients [..., B, D]); column b only depends on x[..., b, :]."""
+        x = x if hasattr(x, "shape") else np.asarray(x)
+        B = self._prepare(x)
+        vals, grads = [], []
+        for b in range(B):
+            v, g = self._columns[b].value_and_gradient(x[..., b : b + 1, :])
+            vals.append(_to_host(v))
+            grads.append(_to_host(g))
+        return np.concatenate(vals, axis=-1), np.concatenate(grads, axis=-2)
+
+
+class MultipleOptimismNegativeLowerConfidenceBound(SingleModelVectorizedAcquisitionBuilder):
+    """function.py:1808-1854: builder of :class:`multiple_optimism_lower_confidence_bound`; nothing to update between
+    steps."""
+
+    def __init__(self, search_space):
+        self._search_space = search_space
+
+    def __repr__(self) -> str:
+        return f"MultipleOptimismNegativeLowerConfidenceBound({self._search_space!r})"
+
+    def prepare_acquisition_function(self, model, dataset: Optional[Dataset] = None):
+        return multiple_optimism_lower_confidence_bound(model, self._search_space.dimension)
+
+    def update_acquisition_function(self, function, model, dataset: Optional[Dataset] = None):
+        if not isinstance(function, multiple_optimism_lower_confidence_bound):
+            raise ValueError(f"expected a multiple_optimism_lower_confidence_bound function, got {function!r}")
+        return function  # nothing to update
 
 
 class batch_monte_carlo_expected_improvement(AcquisitionFunctionClass):

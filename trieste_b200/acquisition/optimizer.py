@@ -154,14 +154,16 @@ def generate_initial_points(num_initial_points: int, initial_sampler, space: Sea
 # vectorised projected L-BFGS (replaces greenlets + SciPy L-BFGS-B, optimizer.py:566-745)
 # ---------------------------------------------------------------------------------------------------
 def _value_and_gradient(fn, x: np.ndarray):
-    """x [R, V, D] -> (values [R, V], grads [R, V, D]) of the function to MAXIMISE."""
+    """x [R, V, D] -> (values [R, V], grads [R, V, D]) of the function to MAXIMISE.  V = 1: an ordinary function
+    ``[..., 1, D] -> [..., 1]``; V > 1: a vectorised one, ``[..., V, D] -> [..., V]`` (column v may be a different function,
+    e.g. the per-column beta of the multiple-optimism LCB)."""
     if not hasattr(fn, "value_and_gradient"):
         raise NotImplementedError(
             "generate_continuous_optimizer needs an acquisition function with a value_and_gradient method "
             "(the reference differentiates through TensorFlow, optimizer.py:621-629)"
         )
     R, V, D = x.shape
-    vals, grads = fn.value_and_gradient(x.reshape(R * V, 1, D))
+    vals, grads = fn.value_and_gradient(x)
     return _to_numpy(vals).reshape(R, V), _to_numpy(grads).reshape(R, V, D)
 
 
@@ -176,7 +178,7 @@ def _perform_parallel_continuous_optimization(fn, lower, upper, starting_points:
 
     R, V, D = starting_points.shape
     P = R * V
-    if hasattr(fn, "maximize_from") and os.environ.get("TB_LBFGS", "device") != "host" and m <= 16:
+    if V == 1 and hasattr(fn, "maximize_from") and os.environ.get("TB_LBFGS", "device") != "host" and m <= 16:
         # fused single-model acquisition functions: the whole multi-start loop runs on the device (tb_acq_maximize)
         ok, fun, xs, nf = fn.maximize_from(starting_points.reshape(P, D), lower, upper, maxcor=m, maxiter=maxiter, maxls=maxls,
                                            gtol=gtol, ftol=ftol)
@@ -184,8 +186,17 @@ def _perform_parallel_continuous_optimization(fn, lower, upper, starting_points:
     x = np.clip(starting_points.reshape(P, D).astype(np.float64), lower, upper)
 
     def evaluate(idx, pts):
-        v, g = _value_and_gradient(fn, pts.reshape(-1, 1, D))
-        return -v.reshape(-1), -g.reshape(-1, D)  # minimise the negation
+        """trial points ``pts`` [n, D] of the problems ``idx`` (flat (run, column) indices) -> (f [n], g [n, D]) of the
+        NEGATED function (this routine minimises)"""
+        if V == 1:
+            v, g = _value_and_gradient(fn, pts.reshape(-1, 1, D))
+            return -v.reshape(-1), -g.reshape(-1, D)
+        # vectorised function: column v of the input selects the function, so evaluate the full [R, V, D] block with the
+        # other problems held at their current iterates and read out the requested entries
+        full = x.copy()
+        full[idx] = pts
+        v, g = _value_and_gradient(fn, full.reshape(R, V, D))
+        return -v.reshape(-1)[idx], -g.reshape(-1, D)[idx]
 
     f, g = evaluate(np.arange(P), x)
     nfev = np.ones(P, dtype=np.int64)
@@ -330,12 +341,18 @@ def generate_continuous_optimizer(num_initial_samples: int = NUM_SAMPLES_MIN, nu
             raise FailedOptimizationError(
                 f"Acquisition function optimization failed, even after {num_recovery_runs + num_optimization_runs} restarts."
             )
-        masked = np.where(success, fun, -np.inf)
-        best = np.argmax(masked, axis=0)  # [V]  (optimizer.py:556-559)
-        optimize_continuous.last_stats = {
-            "spo_af_evaluations": total_nfev,
-            "spo_improvement_on_initial_samples": float(np.max(masked) - np.max(_to_numpy(fn(initial.reshape(-1, 1, initial.shape[-1]))))),
-        }
+        # optimizer.py:556-559: argmax over the values of ALL runs (``successes`` only decides recovery / failure above);
+        # non-finite values never win
+        finite = np.where(np.isfinite(fun), fun, -np.inf)
+        best = np.argmax(finite, axis=0)  # [V]
+
+        def improvement():
+            """optimizer.py:546-549 (evaluated only when asked for: the reference computes it under a summary writer)"""
+            init = _to_numpy(fn(initial if V > 1 else initial.reshape(-1, 1, initial.shape[-1]))).reshape(-1, V)
+            imp = np.max(finite, axis=0) - np.max(init, axis=0)
+            return float(imp[0]) if V == 1 else imp
+
+        optimize_continuous.last_stats = {"spo_af_evaluations": total_nfev, "spo_improvement_on_initial_samples": improvement}
         return np.stack([xs[best[v], v, :] for v in range(V)], axis=0)
 
     return optimize_continuous
@@ -371,6 +388,20 @@ def batchify_joint(batch_size_one_optimizer, batch_size: int):
         target_on_expanded = _Expanded()
         vectorized_points = batch_size_one_optimizer(expanded, target_on_expanded)  # [1, q*D]
         return vectorized_points.reshape(batch_size, -1)
+
+    return optimizer
+
+
+def batchify_vectorize(batch_size_one_optimizer, batch_size: int):
+    """optimizer.py:939-970: for functions whose batch elements can be optimised independently (vectorised functions,
+    ``[..., B, D] -> [..., B]``): the batch-size-one optimiser is asked for ``batch_size`` independent maximisers."""
+    if batch_size <= 0:
+        raise ValueError(f"batch_size must be positive, got {batch_size}")
+
+    def optimizer(space: SearchSpace, f: TargetFunc) -> np.ndarray:
+        if isinstance(f, tuple):
+            raise ValueError("batchify_vectorize cannot be applied to an already vectorized acquisition function")
+        return batch_size_one_optimizer(space, (f, batch_size))
 
     return optimizer
 

@@ -418,7 +418,7 @@ tail_kernel(const double* __restrict__ partial, int G, int64_t McPad, const doub
             const double* __restrict__ samp, int nsamp, double* __restrict__ out_vals, double* __restrict__ out_mean, double* __restrict__ out_var,
             double* __restrict__ blk_best, int64_t* __restrict__ blk_idx) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  double bv = -DBL_MAX;
+  double bv = -INFINITY;
   int64_t bi = INT64_MAX;
   if (t < Mc) {
     double ss = 0.0;
@@ -458,7 +458,7 @@ tail_kernel(const double* __restrict__ partial, int G, int64_t McPad, const doub
 __global__ void __launch_bounds__(256)
 argmax_fold_kernel(const double* __restrict__ blk_best, const int64_t* __restrict__ blk_idx, int nblk,
                    double* __restrict__ run_best, int64_t* __restrict__ run_idx) {
-  double bv = -DBL_MAX;
+  double bv = -INFINITY;
   int64_t bi = INT64_MAX;
   for (int i = threadIdx.x; i < nblk; i += blockDim.x) best_merge(bv, bi, blk_best[i], blk_idx[i]);
 #pragma unroll

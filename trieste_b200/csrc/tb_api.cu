@@ -940,7 +940,7 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
   if (rq.want_argmax) {
     TB_CHECK(rq.M > 0, "argmax over an empty candidate set");
     TB_TRY(gp->sRun.reserve(16));
-    double init_v = -DBL_MAX;
+    double init_v = -INFINITY;  // a candidate worth -inf still beats "nothing seen" through the lower-index tie rule
     int64_t init_i = INT64_MAX;
     TB_CUDA(cudaMemcpyAsync(gp->sRun.p, &init_v, 8, cudaMemcpyHostToDevice, sa));
     TB_CUDA(cudaMemcpyAsync((char*)gp->sRun.p + 8, &init_i, 8, cudaMemcpyHostToDevice, sa));
@@ -1096,7 +1096,7 @@ static int run_eval(tb_gp* gp, EvalRequest& rq) {
   if (rq.want_argmax) {
     TB_CHECK(rq.M > 0, "argmax over an empty candidate set");
     TB_TRY(gp->sRun.reserve(16));
-    double init_v = -DBL_MAX;
+    double init_v = -INFINITY;  // a candidate worth -inf still beats "nothing seen" through the lower-index tie rule
     int64_t init_i = INT64_MAX;
     TB_CUDA(cudaMemcpyAsync(gp->sRun.p, &init_v, 8, cudaMemcpyHostToDevice, st));
     TB_CUDA(cudaMemcpyAsync((char*)gp->sRun.p + 8, &init_i, 8, cudaMemcpyHostToDevice, st));
@@ -1286,6 +1286,10 @@ static int tb_acq_argmax_f64(tb_gp* gp, int acq, double param, const void* Xc, i
   rq.out_vals = (double*)out;
   rq.want_argmax = true;
   TB_TRY(tb::run_eval(gp, rq));
+  if (rq.best_index == INT64_MAX) {  // every value was NaN: tf.math.argmax still returns a valid index (optimizer.py:149)
+    rq.best_index = 0;
+    rq.best_value = std::nan("");
+  }
   *(double*)best_value = rq.best_value;
   *best_index = rq.best_index;
   return 0;

@@ -288,6 +288,21 @@ class GaussianProcessRegression:
         M = xq.shape[0]
         return (mean_new.reshape(lead + (M, 1)).astype(self._dtype), cov_new.reshape(lead + (1, M, M)).astype(self._dtype))
 
+    def conditional_predict_f_sample(self, query_points, additional_data: Dataset, num_samples: int, seed: Optional[int] = None):
+        """models.py:490-509: ``num_samples`` joint samples at ``query_points`` [M, D] conditioned on ``additional_data``
+        — gpflow ``sample_mvn`` on :meth:`conditional_predict_joint` (full covariance + jitter 1e-6, Cholesky,
+        mean + L z).  Returns [..., num_samples, M, 1]."""
+        if num_samples <= 0:
+            raise ValueError(f"num_samples must be positive, got {num_samples}")
+        mean, cov = self.conditional_predict_joint(query_points, additional_data)  # [..., M, 1], [..., 1, M, M]
+        mean = np.asarray(mean, dtype=np.float64)[..., 0]  # [..., M]
+        cov = np.asarray(cov, dtype=np.float64)[..., 0, :, :]  # [..., M, M]
+        M = mean.shape[-1]
+        L = np.linalg.cholesky(cov + 1e-6 * np.eye(M))
+        z = np.random.default_rng(seed).standard_normal(mean.shape[:-1] + (num_samples, M))
+        samples = mean[..., None, :] + np.einsum("...ij,...sj->...si", L, z)  # [..., S, M]
+        return samples[..., None].astype(self._dtype)
+
     def conditional_predict_y(self, query_points, additional_data: Dataset):
         """models.py:502-525: :meth:`conditional_predict_f` plus the observation noise."""
         mean, var = self.conditional_predict_f(query_points, additional_data)

@@ -8,8 +8,15 @@ from typing import Mapping, Optional
 import numpy as np
 
 from .acquisition.function import ExpectedImprovement
-from .acquisition.interface import OBJECTIVE, AcquisitionFunctionBuilder, SingleModelAcquisitionBuilder
-from .acquisition.optimizer import automatic_optimizer_selector, batchify_joint
+from .acquisition.interface import (
+    OBJECTIVE,
+    AcquisitionFunctionBuilder,
+    GreedyAcquisitionFunctionBuilder,
+    SingleModelAcquisitionBuilder,
+    SingleModelGreedyAcquisitionBuilder,
+    VectorizedAcquisitionFunctionBuilder,
+)
+from .acquisition.optimizer import automatic_optimizer_selector, batchify_joint, batchify_vectorize
 from .acquisition.sampler import ExactThompsonSampler, ThompsonSamplerFromTrajectory  # noqa: F401
 from .data import Dataset
 from .space import SearchSpace
@@ -27,11 +34,15 @@ class EfficientGlobalOptimization:
             builder = ExpectedImprovement()
         if optimizer is None:
             optimizer = automatic_optimizer_selector
-        if isinstance(builder, SingleModelAcquisitionBuilder):
+        if isinstance(builder, (SingleModelAcquisitionBuilder, SingleModelGreedyAcquisitionBuilder)):
             builder = builder.using(OBJECTIVE)
-        if num_query_points > 1:
-            optimizer = batchify_joint(optimizer, num_query_points)  # rule.py:291-297
-        self._builder: AcquisitionFunctionBuilder = builder
+        if num_query_points > 1:  # rule.py:291-301
+            if isinstance(builder, VectorizedAcquisitionFunctionBuilder):
+                optimizer = batchify_vectorize(optimizer, num_query_points)  # batch elements optimised independently
+            elif isinstance(builder, AcquisitionFunctionBuilder):
+                optimizer = batchify_joint(optimizer, num_query_points)  # ... jointly over space ** q
+            # a GreedyAcquisitionFunctionBuilder collects the batch sequentially in acquire()
+        self._builder = builder
         self._optimizer = optimizer
         self._num_query_points = num_query_points
         self._acquisition_function = None
@@ -51,7 +62,15 @@ class EfficientGlobalOptimization:
             self._acquisition_function = self._builder.update_acquisition_function(
                 self._acquisition_function, models, datasets=datasets
             )
-        return self._optimizer(search_space, self._acquisition_function)
+        points = self._optimizer(search_space, self._acquisition_function)
+        if isinstance(self._builder, GreedyAcquisitionFunctionBuilder):
+            for _ in range(self._num_query_points - 1):  # rule.py:371-385: greedily allocate the remaining batch elements
+                self._acquisition_function = self._builder.update_acquisition_function(
+                    self._acquisition_function, models, datasets=datasets, pending_points=points, new_optimization_step=False
+                )
+                chosen_point = self._optimizer(search_space, self._acquisition_function)
+                points = np.concatenate([points, chosen_point], axis=0)
+        return points
 
     def acquire_single(self, search_space, model, dataset=None):
         return self.acquire(search_space, {OBJECTIVE: model}, None if dataset is None else {OBJECTIVE: dataset})

@@ -235,8 +235,8 @@ class feature_decomposition_trajectory:
         th = np.ascontiguousarray(self._weights_sample, dtype=np.float64)
         _lib.check(_lib.lib().tb_rff_set_theta(self._h, th.ctypes.data_as(C.POINTER(C.c_double)), th.shape[0]))
 
-    def __call__(self, inputs):
-        x, _ = _lib.as_f64_contiguous(inputs)
+    def __call__(self, x):
+        x, _ = _lib.as_f64_contiguous(x)
         if x.ndim != 3:
             raise ValueError(f"trajectory inputs must be [N, B, D], got shape {tuple(x.shape)}")
         N, B, D = x.shape
