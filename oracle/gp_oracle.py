@@ -57,8 +57,25 @@ def kernel_from_r2(kind: str, r2: np.ndarray, variance: float) -> np.ndarray:
     raise ValueError(f"unknown kernel kind {kind!r}")
 
 
+KERNEL_WORKERS = 1  # > 1: evaluate kernel matrices in column slabs on a thread pool (bench.py's CPU baseline; NumPy's
+# elementwise loops release the GIL, so the Matern evaluation no longer runs on one core beside a multi-threaded dtrsm)
+
+
 def kernel_matrix(kind, X1, X2, variance, lengthscales) -> np.ndarray:
     ls = np.broadcast_to(np.asarray(lengthscales, dtype=X1.dtype), (X1.shape[-1],))
+    if KERNEL_WORKERS > 1 and X2.ndim == 2 and X2.shape[0] >= 4 * KERNEL_WORKERS:
+        from concurrent.futures import ThreadPoolExecutor
+
+        bounds = np.linspace(0, X2.shape[0], KERNEL_WORKERS + 1).astype(int)
+        out = np.empty((X1.shape[0], X2.shape[0]), dtype=np.result_type(X1.dtype, X2.dtype))
+
+        def slab(i):
+            lo, hi = bounds[i], bounds[i + 1]
+            out[:, lo:hi] = kernel_from_r2(kind, scaled_square_dist(X1, X2[lo:hi], ls), variance)
+
+        with ThreadPoolExecutor(max_workers=KERNEL_WORKERS) as pool:
+            list(pool.map(slab, range(KERNEL_WORKERS)))
+        return out
     return kernel_from_r2(kind, scaled_square_dist(X1, X2, ls), variance)
 
 

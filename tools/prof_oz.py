@@ -7,7 +7,7 @@ g.build()
 import trieste_b200 as tb
 from trieste_b200.acquisition import expected_improvement
 from trieste_b200.objectives import ackley
-N, D, M = 4096, 10, 42624  # one chunk of the single-pass engine: 444 tiles x 96 candidates
+N, D, M = 4096, 10, 56832  # one chunk of the single-pass engine: 592 tiles x 96 candidates
 rng = np.random.default_rng(0)
 X = rng.uniform(size=(N, D)); y = ackley(X)
 model = tb.GaussianProcessRegression(tb.build_gpr(tb.Dataset(X, y), tb.Box([0.0] * D, [1.0] * D)))

@@ -93,7 +93,7 @@ struct tb_gp {
   double oz_out_scale = 1.0;
   // single-pass digit engine (ozaki5.cuh): tight row scales + row sums + S-digit tiles of Linv; mode = digits per operand
   // (5: fp64 handles, 15 products; 3: fp32 handles, 6 products; 0: not eligible -> the 6-digit / 21-product kernels)
-  tb::DevBuf dAS5, dRowScale5, dRowSum5;
+  tb::DevBuf dAS5, dRowScale5, dRowSum5, dX2;
   bool oz5_valid = false;
   bool oz_full = false;  // tb_gp_set_engine(2): always the 6-digit / 21-product kernels
   int oz5_mode = 0;

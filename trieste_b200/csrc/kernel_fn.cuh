@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "../../include/trieste_b200.h"
+#include "fastmath.cuh"
 
 namespace tb {
 
@@ -21,6 +22,22 @@ __device__ __forceinline__ double kernel_from_r2(double r2, double variance) {
   }
   double s = 2.23606797749979 * r;
   return variance * (1.0 + s + (5.0 / 3.0) * r * r) * exp(-s);
+}
+
+// The same kernels on the branch-free exp / sqrt of fastmath.cuh (T = the 64-entry 2^(j/64) table in shared memory).  r2 may come
+// from the expansion form |a|^2 + |b|^2 - 2 a.b and be slightly negative, exactly as in GPflow's square_distance.
+template <int KIND>
+__device__ __forceinline__ double kernel_from_r2_fast(double r2, double variance, const double* T, const fm::Consts& c) {
+  if (KIND == TB_RBF) return variance * fm::exp_neg(0.5 * fm::clamp_below(r2, 0.0), T, c);
+  const double q = fm::clamp_below(r2, 1e-36);
+  if (KIND == TB_MATERN12) return variance * fm::exp_neg(fm::sqrt_pos(q), T, c);
+  if (KIND == TB_MATERN32) {
+    const double s = fm::sqrt_pos(3.0 * q);
+    return variance * (1.0 + s) * fm::exp_neg(s, T, c);
+  }
+  const double s2 = 5.0 * q;
+  const double s = fm::sqrt_pos(s2);
+  return variance * fma(s2, c.third, 1.0 + s) * fm::exp_neg(s, T, c);
 }
 
 // dk/d(r2) (for gradients w.r.t. x*: dk/dx*_d = dk/dr2 * 2 (x*_d - x_d) / l_d^2)

@@ -52,6 +52,13 @@ int oz5_ensure(tb_gp* gp) {
   cudaStream_t st = gp->stream;
   const int64_t rows = (int64_t)gp->NB * BM;
   gp->nst = (int)((gp->N + oz::KST - 1) / oz::KST);
+  {  // squared row norms of the scaled training inputs (expansion-form distances of the K* generation kernel)
+    const int64_t xrows = (int64_t)gp->nst * oz::KST;
+    TB_TRY(gp->dX2.reserve(sizeof(double) * xrows));
+    oz5::row_norms_kernel<<<(unsigned)((xrows + 255) / 256), 256, 0, st>>>(gp->dXs.as<double>(), (int64_t)gp->NB * BM, gp->DP, xrows,
+                                                                         gp->dX2.as<double>());
+    TB_LAUNCHED();
+  }
   TB_TRY(gp->dRowScale5.reserve(sizeof(double) * rows));
   TB_TRY(gp->dRowSum5.reserve(sizeof(double) * rows));
   oz5::linv_rowstats_kernel<<<(unsigned)rows, 256, 0, st>>>(gp->dLinv.as<double>(), gp->N, rows, gp->dRowScale5.as<double>(),
@@ -75,6 +82,13 @@ int oz5_ensure(tb_gp* gp) {
   return 0;
 }
 
+// the centre of K* in digit units: the integer nearest to h * inv_b = FILL * 2^(8S); the centre actually subtracted is
+// h_eff = centre / inv_b = h * centre / (FILL 2^(8S)), used consistently by the generation kernel and the GEMM epilogue
+template <int S>
+static double oz5_centre_int() { return std::nearbyint(oz5::FILL * oz5::two_pow_8S<S>()); }
+template <int S>
+static double oz5_h_eff(double variance) { return 0.5 * variance * oz5_centre_int<S>() / (oz5::FILL * oz5::two_pow_8S<S>()); }
+
 template <int S>
 static int launch_kstar_s(tb_gp* gp, cudaStream_t st, const double* Xc_dev, int64_t mc, int tiles, int8_t* BS, double* mean) {
   const double* Xs = gp->dXs.as<double>();
@@ -83,9 +97,11 @@ static int launch_kstar_s(tb_gp* gp, cudaStream_t st, const double* Xc_dev, int6
   const int N = (int)gp->N, nst = gp->nst, D = gp->D;
   const double var = gp->variance, mc0 = gp->mean_const;
   const double inv_b = oz5::two_pow_8S<S>() * oz5::FILL / (0.5 * var);
+  const double dig_c = fm::MAGIC + oz5::dig_koff<S>() - oz5_centre_int<S>();
+  const double* X2 = gp->dX2.as<double>();
   constexpr int TH = oz5::Geo<S>::NT * 4;
 #define TB_KD(KIND, DPV) \
-  oz5::kstar_digits_kernel<KIND, DPV, S><<<tiles, TH, 0, st>>>(Xs, al, Xc_dev, il, N, nst, D, mc, var, inv_b, mc0, BS, mean)
+  oz5::kstar_digits_kernel<KIND, DPV, S><<<tiles, TH, 0, st>>>(Xs, X2, al, Xc_dev, il, N, nst, D, mc, var, inv_b, dig_c, mc0, fm::Consts(), BS, mean)
 #define TB_KD_DP(KIND)                 \
   switch (gp->DP) {                    \
     case 2: TB_KD(KIND, 2); break;     \
@@ -117,13 +133,15 @@ int oz5_launch_kstar(tb_gp* gp, cudaStream_t st, const double* Xc_dev, int64_t m
 }
 
 int oz5_launch_gemm(tb_gp* gp, cudaStream_t st, const int8_t* BS, int tiles, int G, int64_t McPad, double* partial) {
-  const double h = 0.5 * gp->variance, sB = h / oz5::FILL;
+  const double sB = 0.5 * gp->variance / oz5::FILL;
   if (gp->oz5_mode == 5)
     oz5::trigemm_kernel<5><<<dim3(G, tiles), (oz5::EW + 2) * 32, oz5::smem_bytes<5>(), st>>>(
-        gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, McPad, sB, h, partial);
+        gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, McPad, sB,
+        oz5_h_eff<5>(gp->variance), partial);
   else
     oz5::trigemm_kernel<3><<<dim3(G, tiles), (oz5::EW + 2) * 32, oz5::smem_bytes<3>(), st>>>(
-        gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, McPad, sB, h, partial);
+        gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, McPad, sB,
+        oz5_h_eff<3>(gp->variance), partial);
   TB_LAUNCHED();
   TB_CUDA(cudaGetLastError());
   return 0;

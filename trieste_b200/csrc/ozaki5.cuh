@@ -45,6 +45,7 @@ __device__ __forceinline__ void digit_bytes(long long v, uint32_t& lo, uint32_t&
   lo = (uint32_t)w;
   hi = (uint32_t)(w >> 32);
 }
+template <int S> __host__ __device__ constexpr double dig_koff() { return S == 5 ? 551911719040.0 : 8421504.0; }  // 0x8080808080 / 0x808080
 // element JJ (0..15) of the lane's 16-byte rows: plane p (0 = most significant digit) takes byte S-1-p of the word
 template <int S, int JJ>
 __device__ __forceinline__ void scatter(uint32_t (&pk)[S][4], uint32_t lo, uint32_t hi) {
@@ -123,6 +124,16 @@ __global__ void linv_rowstats_kernel(const double* __restrict__ Linv, int64_t N,
   }
 }
 
+// X2[k] = |Xs[k]|^2 for the rows that exist (Xs is [rows_have][DP], zero padded), 0 beyond
+__global__ void row_norms_kernel(const double* __restrict__ Xs, int64_t rows_have, int DP, int64_t rows, double* __restrict__ X2) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= rows) return;
+  double s = 0.0;
+  if (k < rows_have)
+    for (int d = 0; d < DP; ++d) s = fma(Xs[k * DP + d], Xs[k * DP + d], s);
+  X2[k] = s;
+}
+
 template <int S>
 __global__ void linv_digits_kernel(const double* __restrict__ Linv, int64_t N, const double* __restrict__ rowscale,
                                    int8_t* __restrict__ AS) {
@@ -149,34 +160,66 @@ __global__ void linv_digits_kernel(const double* __restrict__ Linv, int64_t N, c
 //   inv_bscale_2p = 2^(8S) / sB,  sB = h / FILL,  h = variance / 2
 // ------------------------------------------------------------------------------------------------
 template <int KIND, int DP, int S>
-__global__ void __launch_bounds__(Geo<S>::NT * 4, 2)
-kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha, const double* __restrict__ Xc,
-                    const double* __restrict__ inv_ls, int N, int nst, int D, int64_t M, double variance, double inv_bscale_2p,
-                    double mean_const, int8_t* __restrict__ BS, double* __restrict__ mean_out) {
-  constexpr int NT = Geo<S>::NT, BTILE = NT * KST;
+__global__ void __launch_bounds__(Geo<S>::NT * 4, Geo<S>::NT * 4 <= 384 ? 2 : 1)
+kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ X2, const double* __restrict__ alpha,
+                    const double* __restrict__ Xc, const double* __restrict__ inv_ls, int N, int nst, int D, int64_t M, double variance,
+                    double inv_bscale_2p, double dig_c, double mean_const, const __grid_constant__ fm::Consts fc,
+                    int8_t* __restrict__ BS, double* __restrict__ mean_out) {
+  constexpr int NT = Geo<S>::NT, BTILE = NT * KST, TH = NT * 4;
+  // No masking of k >= N or of candidates t >= M is needed: training rows beyond N are zero-padded (their kernel values are
+  // finite), alpha is zero there and so are all digits of Linv's columns k >= N, so those K* digits never reach a result;
+  // padded candidates produce values nobody reads.
+  // squared distances: the exact difference form for Matern12 (exp(-r) is not differentiable at r = 0, so the O(1e-16)
+  // cancellation noise of the expansion form would show at 1e-8), the expansion |a|^2 + |b|^2 - 2 a.b (GPflow's
+  // square_distance; D FMAs instead of 2 D operations per element) for the smooth kernels
+  constexpr bool EXPAND = KIND != TB_MATERN12;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t tile_id = blockIdx.x;
   const int cl = lane & 7, ch = lane >> 3;
   const int t_local = w * 8 + cl;
   const int64_t t = tile_id * NT + t_local;
   const bool valid = t < M;
-  const double half_var = 0.5 * variance;
   double xc[DP];
+  double xc2 = 0.0;
 #pragma unroll
-  for (int d = 0; d < DP; ++d) xc[d] = (valid && d < D) ? Xc[t * D + d] * inv_ls[d] : 0.0;
+  for (int d = 0; d < DP; ++d) {
+    xc[d] = (valid && d < D) ? Xc[t * D + d] * inv_ls[d] : 0.0;
+    xc2 = fma(xc[d], xc[d], xc2);
+  }
   int8_t* tile = BS + tile_id * (int64_t)nst * (S * BTILE) + w * SBO + ch * LBO + cl * 16;
-  __shared__ __align__(16) double xs_s[2][KST * DP];
-  __shared__ __align__(16) double al_s[2][KST];
+  // lanes with different ch read rows 16 apart: 16 rows are a multiple of 128 bytes, i.e. the same banks (ncu: 4-way conflicts
+  // on every operand load) — every 16-row block is skewed by 16 bytes
+  constexpr int XROW = KST * DP + 2 * (KST / 16), VROW = KST + 2 * (KST / 16);
+  __shared__ __align__(16) double xs_s[2][XROW];
+  __shared__ __align__(16) double al_s[2][VROW];
+  __shared__ __align__(16) double x2_s[2][VROW];
+  __shared__ __align__(16) double exp_tab[64];
+  if (threadIdx.x < 64) exp_tab[threadIdx.x] = fm::EXP2_TABLE_DEV[threadIdx.x];
   auto stage_load = [&](int kc, int buf) {
     const double* src = Xs + (int64_t)kc * KST * DP;
-    for (int e = threadIdx.x; e < KST * DP / 2; e += blockDim.x)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&xs_s[buf][2 * e])), "l"(src + 2 * e) : "memory");
-    for (int e = threadIdx.x; e < KST / 2; e += blockDim.x)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&al_s[buf][2 * e])), "l"(alpha + (int64_t)kc * KST + 2 * e)
+    constexpr int CH = KST * DP / 2;  // 16-byte chunks of the stage's training rows
+#pragma unroll
+    for (int i = 0; i < (CH + TH - 1) / TH; ++i) {
+      const int e = i * TH + (int)threadIdx.x;
+      const int blk = (2 * e) / (16 * DP);  // 16-row block of this chunk (DP is even: a chunk never straddles rows)
+      if (e < CH) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&xs_s[buf][2 * e + 2 * blk])), "l"(src + 2 * e) : "memory");
+    }
+    if (threadIdx.x < KST / 2) {
+      const int e = threadIdx.x;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&al_s[buf][2 * e + 2 * (e / 8)])), "l"(alpha + (int64_t)kc * KST + 2 * e)
                    : "memory");
+    } else if (EXPAND && threadIdx.x < KST) {
+      const int e = threadIdx.x - KST / 2;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&x2_s[buf][2 * e + 2 * (e / 8)])), "l"(X2 + (int64_t)kc * KST + 2 * e)
+                   : "memory");
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   stage_load(0, 0);
+  // digit extraction without a conversion: v = rint(k inv) - c rides in the low mantissa bits of
+  //   fma(k, inv, dig_c),  dig_c = 1.5 2^52 + 0x80..80 - c,  c = the INTEGER nearest to h inv (host: the centre actually
+  //   subtracted is h_eff = c / inv, and the epilogue's row constant uses the same h_eff, so no bias is introduced);
+  // the int8 digits are the low S bytes XOR 0x80 (digit_bytes, folded)
   double macc = 0.0;
   for (int kc = 0; kc < nst; ++kc) {
     const int buf = kc & 1;
@@ -192,21 +235,32 @@ kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ al
     for (int p = 0; p < S; ++p) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int kl = ch * 16 + j, k = kc * KST + kl;
-      const double* xr = &xs_s[buf][kl * DP];
-      double r2 = 0.0;
+      const int kl = ch * 16 + j, kv = kl + 2 * ch;  // kv: index into the skewed per-row vectors
+      const double* xr = &xs_s[buf][kl * DP + 2 * ch];
+      double r2;
+      if (EXPAND) {
+        double dot = 0.0;
 #pragma unroll
-      for (int d = 0; d < DP; d += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(xr + d);
-        double d0 = xc[d] - v.x, d1 = xc[d + 1] - v.y;
-        r2 = fma(d0, d0, r2);
-        r2 = fma(d1, d1, r2);
+        for (int d = 0; d < DP; d += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(xr + d);
+          dot = fma(xc[d], v.x, dot);
+          dot = fma(xc[d + 1], v.y, dot);
+        }
+        r2 = fma(-2.0, dot, xc2 + x2_s[buf][kv]);
+      } else {
+        r2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < DP; d += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(xr + d);
+          double d0 = xc[d] - v.x, d1 = xc[d + 1] - v.y;
+          r2 = fma(d0, d0, r2);
+          r2 = fma(d1, d1, r2);
+        }
       }
-      const bool live = valid && k < N;
-      const double kval = live ? kernel_from_r2<KIND>(r2, variance) : 0.0;
-      macc = fma(kval, al_s[buf][kl], macc);
-      uint32_t wl, wh;
-      digit_bytes<S>(live ? __double2ll_rn((kval - half_var) * inv_bscale_2p) : 0ll, wl, wh);
+      const double kval = kernel_from_r2_fast<KIND>(r2, variance, exp_tab, fc);
+      macc = fma(kval, al_s[buf][kv], macc);
+      const double tb = fma(kval, inv_bscale_2p, dig_c);
+      const uint32_t wl = (uint32_t)__double2loint(tb) ^ 0x80808080u, wh = (uint32_t)__double2hiint(tb) ^ 0x80u;
       scatter_rt<S>(pk, j, wl, wh);
     }
 #pragma unroll

@@ -957,9 +957,12 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
   const bool vals_dev = is_device_ptr(rq.out_vals), mean_dev = is_device_ptr(rq.out_mean), var_dev = is_device_ptr(rq.out_var);
   // half the usual scratch budget per slot (two slots are live)
   const size_t per_tile = fast ? oz5_tile_bytes(gp) : (size_t)gp->nst * oz::S * oz::TILE;
-  int64_t max_tiles = std::max<int64_t>(1, (int64_t)(((size_t)1024 << 20) / per_tile));
-  if (max_tiles >= 148) max_tiles = (max_tiles / 148) * 148;
-  max_tiles = std::min<int64_t>(max_tiles, 148 * 8);
+  int64_t max_tiles = std::max<int64_t>(1, (int64_t)(((size_t)1280 << 20) / per_tile));
+  // whole waves for both kernels of a chunk: the generation kernel runs 2 CTAs per SM (one per tile), the GEMM one CTA per SM
+  // and G per tile (ncu: 444 tiles left the generation kernel with a half-empty second wave)
+  if (max_tiles >= 296) max_tiles = (max_tiles / 296) * 296;
+  else if (max_tiles >= 148) max_tiles = 148;
+  max_tiles = std::min<int64_t>(max_tiles, 296 * 4);
   const int64_t chunk_cap = std::min<int64_t>(max_tiles * nt, ((rq.M + nt - 1) / nt) * nt);
   const int64_t tiles_cap = chunk_cap / nt;
   // row-block groups per candidate tile: ~4 row-blocks per CTA amortise the CTA prologue while the co-resident CTAs still

@@ -36,100 +36,122 @@ def merge_best(pairs) -> Tuple[float, int]:
     return bv, bi
 
 
-def allgather_best(value: float, global_index: int, point: Optional[np.ndarray] = None, group=None, device=None):
-    """The path's single collective.  Returns (best_value, best_global_index, best_point or None),
-    identical on every rank."""
+def _to_host(x) -> np.ndarray:
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
+
+
+def allgather_best(value, global_index, point: Optional[np.ndarray] = None, group=None, device=None):
+    """The path's single collective.  ``value`` / ``global_index`` may be scalars (one winner) or arrays of length B
+    (B independent winners — the q trajectories of a Thompson batch travel in ONE all-gather); ``point`` is [D] or [B, D].
+    Returns (best_value, best_global_index, best_point or None) with the same leading shape, identical on every rank:
+    larger value wins, ties -> lower global index (first-max, optimizer.py:149); NaN and empty shards (index -1) never win."""
     import torch
     import torch.distributed as dist
 
+    scalar = np.ndim(value) == 0
+    vals = np.atleast_1d(np.asarray(value, dtype=np.float64))
+    idxs = np.atleast_1d(np.asarray(global_index, dtype=np.int64))
+    B = vals.shape[0]
+    pts = None if point is None else np.asarray(_to_host(point), dtype=np.float64).reshape(B, -1)
+    D = 0 if pts is None else pts.shape[1]
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return float(value), int(global_index), None if point is None else np.asarray(point, dtype=np.float64)
-    world = dist.get_world_size(group)
-    D = 0 if point is None else int(np.asarray(point).shape[-1])
-    if device is None:
-        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    payload = torch.zeros(2 + D, dtype=torch.float64, device=device)
-    payload[0] = float(value) if value == value else float("-inf")
-    payload[1] = float(global_index)  # exact for indices < 2^53
-    if D:
-        payload[2:] = torch.as_tensor(np.asarray(point, dtype=np.float64).reshape(-1), device=device)
-    gathered = [torch.empty_like(payload) for _ in range(world)]
-    dist.all_gather(gathered, payload, group=group)
-    rows = [g.cpu().numpy() for g in gathered]
-    bv, bi = merge_best([(r[0], int(r[1])) for r in rows])
-    bp = None
-    if D:
-        for r in rows:
-            if int(r[1]) == bi:
-                bp = r[2:].copy()
-                break
+        bv, bi, bp = vals.copy(), idxs.copy(), None if pts is None else pts.copy()
+    else:
+        world = dist.get_world_size(group)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        payload = np.zeros((B, 2 + D))
+        payload[:, 0] = np.where(vals == vals, vals, -np.inf)
+        payload[:, 1] = idxs  # exact for indices < 2^53
+        if D:
+            payload[:, 2:] = pts
+        mine = torch.as_tensor(payload, device=device)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=group)
+        rows = np.stack([g.cpu().numpy() for g in gathered])  # [world, B, 2 + D]
+        bv, bi = np.empty(B), np.empty(B, dtype=np.int64)
+        bp = None if not D else np.empty((B, D))
+        for b in range(B):
+            v, i = merge_best([(rows[r, b, 0], int(rows[r, b, 1])) for r in range(world)])
+            bv[b], bi[b] = v, i
+            if D:
+                src = [r for r in range(world) if int(rows[r, b, 1]) == i]
+                bp[b] = rows[src[0], b, 2:] if src else np.nan
+    if scalar:
+        return float(bv[0]), int(bi[0]), None if bp is None else bp[0]
     return bv, bi, bp
 
 
-def sharded_argmax(fn, points: np.ndarray, group=None):
-    """``_get_max_discrete_points`` over candidates sharded across the ranks of ``group``:
-    each rank evaluates its slice with the fused argmax kernels and one all-gather picks the winner.
-    ``points`` [M, D] must be identical on every rank.  Returns (point [1, D], value, global index)."""
+def _world_rank(group):
     import torch.distributed as dist
 
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank(group) if world > 1 else 0
-    lo, hi = shard_bounds(points.shape[0], rank, world)
-    if hi > lo:
-        idx, val = fn.fused_argmax(points[lo:hi])
-        gidx = lo + idx
-        pt = points[gidx]
+    return world, (dist.get_rank(group) if world > 1 else 0)
+
+
+def sharded_argmax_local(fn, local_points, global_offset: int, group=None):
+    """The rank's own shard of the candidates is already in place (``local_points`` [m, D], NumPy or torch.cuda; global
+    indices ``global_offset + i``): fused evaluation + argmax over the shard, then the single all-gather.
+    Returns (point [1, D], value, global index), identical on every rank."""
+    if local_points.shape[0] > 0:
+        idx, val = fn.fused_argmax(local_points)
+        gidx, pt = global_offset + idx, _to_host(local_points[idx])
     else:
-        gidx, val, pt = -1, float("-inf"), np.zeros(points.shape[1])
+        gidx, val, pt = -1, float("-inf"), np.zeros(local_points.shape[1])
     bv, bi, bp = allgather_best(val, gidx, pt, group=group)
     return bp[None, :], bv, bi
 
 
-def sharded_thompson_argmin(trajectory, points: np.ndarray, group=None):
-    """BASELINE config 4: batch Thompson sampling over candidates sharded across the ranks.  Every rank holds the same
-    trajectory (same W, b, theta — broadcast or seeded identically) and evaluates its slice with the fused eval+argmin
-    kernel; one all-gather per trajectory of (-value, global index) picks the minimiser.  Returns (points [B, D],
-    values [B], global indices [B])."""
-    import torch.distributed as dist
-
-    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank(group) if world > 1 else 0
+def sharded_argmax(fn, points, group=None):
+    """``_get_max_discrete_points`` over candidates sharded across the ranks of ``group``:
+    each rank evaluates its slice with the fused argmax kernels and one all-gather picks the winner.
+    ``points`` [M, D] must be identical on every rank.  Returns (point [1, D], value, global index)."""
+    world, rank = _world_rank(group)
     lo, hi = shard_bounds(points.shape[0], rank, world)
-    if hi > lo:
-        mv, mi = trajectory.argmin_over(points[lo:hi])
+    return sharded_argmax_local(fn, points[lo:hi], lo, group=group)
+
+
+def sharded_thompson_argmin_local(trajectory, local_points, global_offset: int, group=None):
+    """BASELINE config 4 on the rank's own shard: every rank holds the same trajectories (same W, b, theta) and evaluates
+    its candidates with the fused eval+argmin kernel; the B (value, index, point) triples of the batch travel in ONE
+    all-gather.  Returns (points [B, D], values [B], global indices [B])."""
+    D = local_points.shape[1]
+    if local_points.shape[0] > 0:
+        mv, mi = trajectory.argmin_over(local_points)
+        B = len(mv)
+        vals, gidx = -np.asarray(mv, dtype=np.float64), global_offset + np.asarray(mi, dtype=np.int64)
+        pts = np.stack([_to_host(local_points[int(i)]) for i in mi])
     else:
-        mv, mi = None, None
-    B = len(mv) if mv is not None else int(getattr(trajectory, "_batch_size", 1) or 1)
-    out_p, out_v, out_i = [], [], []
-    for b in range(B):
-        if mv is not None:
-            val, gidx = -float(mv[b]), lo + int(mi[b])
-            pt = points[gidx]
-        else:
-            val, gidx, pt = float("-inf"), -1, np.zeros(points.shape[1])
-        bv, bi, bp = allgather_best(val, gidx, pt, group=group)
-        out_p.append(bp if bp is not None else pt)
-        out_v.append(-bv)
-        out_i.append(bi)
-    return np.stack(out_p), np.asarray(out_v), np.asarray(out_i)
+        B = int(getattr(trajectory, "_batch_size", 1) or 1)
+        vals, gidx, pts = np.full(B, -np.inf), np.full(B, -1, dtype=np.int64), np.zeros((B, D))
+    bv, bi, bp = allgather_best(vals, gidx, pts, group=group)
+    return bp, -bv, bi
 
 
-def sharded_multistart(optimize_starts, starts: np.ndarray, group=None):
-    """BASELINE config 5: the R multi-starts of ``generate_continuous_optimizer`` sharded across the ranks — each rank
-    runs its slice of starts to convergence with no communication (``optimize_starts(starts_slice) -> (x [r, D],
-    values [r])``), then one all-gather of (best value, global start index, x) picks the winner
-    (optimizer.py:556-559)."""
-    import torch.distributed as dist
+def sharded_thompson_argmin(trajectory, points, group=None):
+    """As above with ``points`` [M, D] identical on every rank (sliced here)."""
+    world, rank = _world_rank(group)
+    lo, hi = shard_bounds(points.shape[0], rank, world)
+    return sharded_thompson_argmin_local(trajectory, points[lo:hi], lo, group=group)
 
-    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank(group) if world > 1 else 0
-    lo, hi = shard_bounds(starts.shape[0], rank, world)
-    if hi > lo:
-        xs, vals = optimize_starts(starts[lo:hi])
-        vals = np.asarray(vals, dtype=np.float64).reshape(-1)
+
+def sharded_multistart_local(optimize_starts, local_starts, global_offset: int, group=None):
+    """BASELINE config 5 on the rank's own shard of the multi-starts: ``optimize_starts(starts) -> (x [r, D], values [r])``
+    runs them to convergence with no communication, then one all-gather of (best value, global start index, x) picks the
+    winner (optimizer.py:556-559)."""
+    if local_starts.shape[0] > 0:
+        xs, vals = optimize_starts(local_starts)
+        vals = np.asarray(_to_host(vals), dtype=np.float64).reshape(-1)
         j = int(np.argmax(np.where(np.isfinite(vals), vals, -np.inf)))
-        val, gidx, pt = float(vals[j]), lo + j, np.asarray(xs)[j]
+        val, gidx, pt = float(vals[j]), global_offset + j, _to_host(xs)[j]
     else:
-        val, gidx, pt = float("-inf"), -1, np.zeros(starts.shape[1])
+        val, gidx, pt = float("-inf"), -1, np.zeros(local_starts.shape[1])
     bv, bi, bp = allgather_best(val, gidx, pt, group=group)
-    return (bp if bp is not None else pt)[None, :], bv, bi
+    return bp[None, :], bv, bi
+
+
+def sharded_multistart(optimize_starts, starts, group=None):
+    """As above with ``starts`` [R, D] identical on every rank (sliced here)."""
+    world, rank = _world_rank(group)
+    lo, hi = shard_bounds(starts.shape[0], rank, world)
+    return sharded_multistart_local(optimize_starts, starts[lo:hi], lo, group=group)
