@@ -57,6 +57,29 @@ def test_repeated_single_appends_track_the_oracle_and_gradients_follow():
     np.testing.assert_allclose(cj, ocj, rtol=0, atol=1e-9 * full.variance)
 
 
+@pytest.mark.parametrize("engine", ["int8", "fp64"])
+def test_gradients_between_appends_use_the_rank_m_update_of_the_inverse(engine):
+    """A BO loop with a gradient-based optimiser asks for gradients after EVERY append: the dense K^-1 behind the int8
+    engine's gradient GEMM is grown by rank m with the factor (O(m N^2)) instead of being rebuilt (O(N^3))."""
+    import trieste_b200 as tb
+    from trieste_b200.acquisition import expected_improvement
+
+    head, full = _grown(o.hartmann_6, 250, 12, 6)
+    nm = native_from_oracle(head)
+    nm.set_engine(engine)
+    Xq = candidates(200, 6)
+    for k in (0, 1, 4, 12):  # gradients first (builds K^-1), then appends of 1, 3 and 8 rows with gradients in between
+        if k:
+            nm.update(tb.Dataset(full.X[: 250 + k], full.y[: 250 + k]))
+            assert nm.last_update_appended
+        ref = o.build_model(full.kind, full.X[: 250 + k], full.y[: 250 + k], full.variance, full.lengthscales, full.noise, full.mean_const)
+        eta = o.ei_eta(ref)
+        val, grad = expected_improvement(nm, eta).value_and_gradient(Xq[:, None, :])
+        oval, ograd = o.ei_gradient(ref, Xq, eta)
+        np.testing.assert_allclose(val.reshape(-1), oval.reshape(-1), rtol=1e-6, atol=1e-15)
+        np.testing.assert_allclose(grad.reshape(-1, 6), ograd, rtol=1e-6, atol=1e-12)
+
+
 def test_update_falls_back_to_a_full_refresh_when_it_is_not_an_append():
     import trieste_b200 as tb
 

@@ -235,6 +235,18 @@ kinv_kernel(const double* __restrict__ Linv, double* __restrict__ Kinv, int64_t 
   });
 }
 
+// ---- rank-m growth of K^-1 = Linv^T Linv after m rows were appended to the factor (N0 -> N): K^-1[i,j] = Σ_{n >= max(i,j)}
+// Linv[n,i] Linv[n,j], so the old block gains only the m new rows' contribution and the new rows are sums over <= m terms:
+// O(m N^2) instead of the O(N^3) rebuild.  Lower triangle (i >= j), column-major, old ld = N0, new ld = N.
+__global__ void kinv_grow_kernel(const double* __restrict__ Kold, int64_t N0, const double* __restrict__ Linv, int64_t N,
+                                 double* __restrict__ Knew) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= N || j > i) return;
+  double s = (i < N0) ? Kold[i + j * N0] : 0.0;
+  for (int64_t n = (i > N0 ? i : N0); n < N; ++n) s = fma(Linv[n + i * N], Linv[n + j * N], s);
+  Knew[i + j * N] = s;
+}
+
 // ---- alpha = Linv^T (Linv r): two triangular mat-vecs, one warp per output element ----
 __global__ void trmv_lower_kernel(const double* __restrict__ Linv, int64_t N, const double* __restrict__ x, double* __restrict__ y) {
   const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

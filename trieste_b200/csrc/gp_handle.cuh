@@ -84,7 +84,10 @@ struct tb_gp {
   int engine = 1;  // 0 = fp64 DMMA, 1 = int8 tensor cores (default; same stated tolerances, ~3x faster)
   tb::DevBuf dAS, dRowScale;
   tb::DevBuf dKinv, dKinvS, dKinvScale;  // gradient path of the int8 engine: digit tiles of K^-1 (full rows)
-  bool kinv_valid = false;
+  bool kinv_valid = false;       // digit tiles of K^-1 current
+  bool kinv_dense_valid = false; // dense K^-1 (dKinv, lower triangle, ld = kinv_dense_N) current: kept so that an append can
+  int64_t kinv_dense_N = 0;      // update it by rank m (tb_gp_append_data) instead of rebuilding it in O(N^3)
+  tb::DevBuf dKinvSpare;
   tb::DevBuf sKs2, sMean2, sPartial2;  // second scratch slot of the pipelined driver
   cudaStream_t stream2 = nullptr;      // K* digit generation stream (overlaps the digit GEMM)
   cudaEvent_t evK[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr};

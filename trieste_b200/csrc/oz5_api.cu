@@ -134,13 +134,21 @@ int oz5_launch_kstar(tb_gp* gp, cudaStream_t st, const double* Xc_dev, int64_t m
 
 int oz5_launch_gemm(tb_gp* gp, cudaStream_t st, const int8_t* BS, int tiles, int G, int64_t McPad, double* partial) {
   const double sB = 0.5 * gp->variance / oz5::FILL;
+  // persistent grid: one CTA per SM (fewer when there are fewer work items)
+  static int sms = 0;
+  if (sms == 0) {
+    cudaDeviceProp prop;
+    TB_CUDA(cudaGetDeviceProperties(&prop, gp->device));
+    sms = prop.multiProcessorCount;
+  }
+  const int grid = std::min(sms, tiles * G);
   if (gp->oz5_mode == 5)
-    oz5::trigemm_kernel<5><<<dim3(G, tiles), (oz5::EW + 2) * 32, oz5::smem_bytes<5>(), st>>>(
-        gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, McPad, sB,
+    oz5::trigemm_kernel<5><<<grid, (oz5::EW + 2) * 32, oz5::smem_bytes<5>(), st>>>(
+        gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, tiles, McPad, sB,
         oz5_h_eff<5>(gp->variance), partial);
   else
-    oz5::trigemm_kernel<3><<<dim3(G, tiles), (oz5::EW + 2) * 32, oz5::smem_bytes<3>(), st>>>(
-        gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, McPad, sB,
+    oz5::trigemm_kernel<3><<<grid, (oz5::EW + 2) * 32, oz5::smem_bytes<3>(), st>>>(
+        gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, tiles, McPad, sB,
         oz5_h_eff<3>(gp->variance), partial);
   TB_LAUNCHED();
   TB_CUDA(cudaGetLastError());

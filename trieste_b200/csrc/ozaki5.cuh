@@ -33,7 +33,9 @@ template <> struct Geo<3> { static constexpr int NT = 128; };
 
 template <int S> __host__ __device__ constexpr int btile() { return Geo<S>::NT * KST; }
 template <int S> __host__ __device__ constexpr int stage_bytes() { return S * (ATILE + btile<S>()); }
-template <int S> __host__ __device__ constexpr size_t smem_bytes() { return (size_t)STAGES * stage_bytes<S>() + 256; }
+template <int S> __host__ __device__ constexpr size_t smem_bytes() {  // stages + barriers + the epilogue's column-sum exchange buffer
+  return (size_t)STAGES * stage_bytes<S>() + 256 + (size_t)EW * (Geo<S>::NT / 2) * sizeof(double);
+}
 template <int S> __host__ __device__ constexpr double two_pow_8S() { return S == 5 ? 1099511627776.0 : 16777216.0; }  // 2^40 / 2^24
 
 // v = Σ_{p=1..S} d_p 256^(S-p), d_p in [-128,127]: the int8 digits are the bytes of (v + 0x80..80) ^ 0x80..80 (no carry chain);
@@ -273,6 +275,16 @@ kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ X2
   if (ch == 0) mean_out[tile_id * NT + t_local] = macc + mean_const;
 }
 
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+// exact int32 -> fp64 on the ALU + fp64 pipes: bits(2^52 + 2^31 + t) = {0x43300000, t ^ 0x80000000}
+__device__ __forceinline__ double int_to_double(uint32_t t) {
+  return __hiloint2double(0x43300000, (int)(t ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
+}
+
 // all MMAs of one pipeline stage: S(S+1)/2 digit products x (KST / 32) k-steps, descriptors by two 32-bit adds each
 template <int S>
 __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t stage_base, uint32_t not_first_kc) {
@@ -303,15 +315,21 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t stage_base, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// the GEMM: grid = (G row-block groups, candidate tiles); partial[g][t] = Σ_{rows n of group g} A[n,t]^2,
+// the GEMM: PERSISTENT, one CTA per SM; work item = (candidate tile, row-block group g), item = tile * G + g, CTA c takes
+// items c, c + gridDim.x, ... (co-running CTAs share ~gridDim.x / G candidate tiles -> the K* digits stay in L2; the
+// serpentine row-block assignment gives every item the same cost).  The TMA ring, the mbarrier phases and the TMEM
+// allocation live across items, so the producer prefetches the next item's first stages while the epilogue of the current one
+// still runs and the per-CTA prologue (barrier init, TMEM allocation, pipeline fill) is paid once per SM instead of per item.
+//   partial[g][t] = Σ_{rows n of group g} A[n,t]^2,
 //   A[n,t] = rowscale[n]·out_scale · Σ_{r=2..S+1} 2^(-8r) T_r[n,t]  +  half_var·rowsum[n]
 // ------------------------------------------------------------------------------------------------
 template <int S>
 __global__ void __launch_bounds__((EW + 2) * 32, 1)
 trigemm_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, const double* __restrict__ rowscale,
-               const double* __restrict__ rowsum, int NB, int nst, int G, int64_t McPad, double out_scale, double half_var,
+               const double* __restrict__ rowsum, int NB, int nst, int G, int tiles, int64_t McPad, double out_scale, double half_var,
                double* __restrict__ partial) {
   constexpr int NT = Geo<S>::NT, BTILE = NT * KST, STAGE = S * (ATILE + BTILE);
+  constexpr int CW = NT / 2;  // accumulator columns per epilogue warp: 48 (S = 5) or 64 (S = 3)
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE);
   uint64_t* full = bars;                 // [STAGES]
@@ -319,9 +337,10 @@ trigemm_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, con
   uint64_t* acc_full = bars + 2 * STAGES;      // MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * STAGES + 1; // epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+  double (*redbuf)[CW] = reinterpret_cast<double (*)[CW]>(smem + (size_t)STAGES * STAGE + 256);  // [EW][CW] column-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x, tile = blockIdx.y;  // g fastest: co-resident CTAs share few candidate tiles -> K* digits stay in L2
+  const int nitems = tiles * G;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -337,25 +356,28 @@ trigemm_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  const int8_t* bTile = BS + (int64_t)tile * nst * (S * BTILE);
 
   if (warp == EW) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
-      for (int i = 0;; ++i) {
-        const int I = serpentine_rowblock(i, g, G);
-        if (I >= NB) break;
-        const int nk = min(2 * (I + 1), nst);
-        const int8_t* aRow = AS + oz::a_stage_offset(I) * (int64_t)(S * ATILE);
-        for (int kc = 0; kc < nk; ++kc) {
-          mbar_wait(&empty[st], ph ^ 1);
-          unsigned char* dst = smem + (size_t)st * STAGE;
-          mbar_expect_tx(&full[st], STAGE);
-          bulk_g2s(dst, aRow + (int64_t)kc * (S * ATILE), S * ATILE, &full[st]);
-          bulk_g2s(dst + S * ATILE, bTile + (int64_t)kc * (S * BTILE), S * BTILE, &full[st]);
-          if (++st == STAGES) { st = 0; ph ^= 1; }
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int g = item % G, tile = item / G;
+        const int8_t* bTile = BS + (int64_t)tile * nst * (S * BTILE);
+        for (int i = 0;; ++i) {
+          const int I = serpentine_rowblock(i, g, G);
+          if (I >= NB) break;
+          const int nk = min(2 * (I + 1), nst);
+          const int8_t* aRow = AS + oz::a_stage_offset(I) * (int64_t)(S * ATILE);
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(&empty[st], ph ^ 1);
+            unsigned char* dst = smem + (size_t)st * STAGE;
+            mbar_expect_tx(&full[st], STAGE);
+            bulk_g2s(dst, aRow + (int64_t)kc * (S * ATILE), S * ATILE, &full[st]);
+            bulk_g2s(dst + S * ATILE, bTile + (int64_t)kc * (S * BTILE), S * BTILE, &full[st]);
+            if (++st == STAGES) { st = 0; ph ^= 1; }
+          }
         }
       }
     }
@@ -364,106 +386,122 @@ trigemm_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, con
     if (lane == 0) {
       int st = 0, n = 0;
       uint32_t ph = 0;
-      for (int i = 0;; ++i, ++n) {
-        const int I = serpentine_rowblock(i, g, G);
-        if (I >= NB) break;
-        const int nk = min(2 * (I + 1), nst);
-        if (n > 0) {  // accumulators must have been read out by the epilogue warps
-          mbar_wait(acc_empty, (uint32_t)((n - 1) & 1));
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int g = item % G;
+        for (int i = 0;; ++i, ++n) {
+          const int I = serpentine_rowblock(i, g, G);
+          if (I >= NB) break;
+          const int nk = min(2 * (I + 1), nst);
+          if (n > 0) {  // accumulators must have been read out by the epilogue warps
+            mbar_wait(acc_empty, (uint32_t)((n - 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(&full[st], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            issue_stage<S>(tmem, smem_u32(smem + (size_t)st * STAGE), kc != 0 ? 1u : 0u);
+            oz::umma_commit(&empty[st]);
+            if (++st == STAGES) { st = 0; ph ^= 1; }
+          }
+          oz::umma_commit(acc_full);
         }
-        for (int kc = 0; kc < nk; ++kc) {
-          mbar_wait(&full[st], ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          issue_stage<S>(tmem, smem_u32(smem + (size_t)st * STAGE), kc != 0 ? 1u : 0u);
-          oz::umma_commit(&empty[st]);
-          if (++st == STAGES) { st = 0; ph ^= 1; }
-        }
-        oz::umma_commit(acc_full);
       }
     }
   } else {
     // ===================== epilogue warps =====================
     // warp w reads TMEM lanes [32 (w%4), +32) (rows) and columns [NT/2 (w/4), +NT/2) of every level
     const int lq = warp & 3, ch = warp >> 2;
-    constexpr int CW = NT / 2;  // 48 (S = 5) or 64 (S = 3) columns per warp
     const uint32_t lane_base = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * CW);
     double vacc[CW];
     double colsum[CW / 16];
-#pragma unroll
-    for (int h = 0; h < CW / 16; ++h) colsum[h] = 0.0;
     int n = 0;
-    for (int i = 0;; ++i, ++n) {
-      const int I = serpentine_rowblock(i, g, G);
-      if (I >= NB) break;
-      const int64_t nrow = (int64_t)I * 128 + lq * 32 + lane;
-      const double rs = rowscale[nrow] * out_scale;
-      const double rc = rowsum[nrow] * half_var;
-      mbar_wait(acc_full, (uint32_t)(n & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int g = item % G, tile = item / G;
 #pragma unroll
-      for (int h = 0; h < CW / 16; ++h) {
-        // Horner over the levels, least significant first: v = ((T_{S+1} 2^-8 + T_S) 2^-8 + ...) ; final factor 2^-16 for r = 2
-        uint32_t t[16];
-        oz::tmem_ld16(lane_base + (uint32_t)((S - 1) * NT) + h * 16, t);
+      for (int h = 0; h < CW / 16; ++h) colsum[h] = 0.0;
+      for (int i = 0;; ++i, ++n) {
+        const int I = serpentine_rowblock(i, g, G);
+        if (I >= NB) break;
+        const int64_t nrow = (int64_t)I * 128 + lq * 32 + lane;
+        const double rs = rowscale[nrow] * out_scale;
+        const double rc = rowsum[nrow] * half_var;
+        mbar_wait(acc_full, (uint32_t)(n & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // TMEM -> fp64 as fast as possible (the tensor pipe waits for this read-out: ncu put it at ~10 % of the kernel when
+        // every 16-column load was followed by its own wait and 240 I2F.F64 conversions per thread):
+        //   * all S levels of an 8-column group are loaded back to back and waited for once;
+        //   * int32 -> fp64 without the conversion unit (int_to_double: one LOP3 + one DADD instead of a quarter-rate I2F);
+        //   * Horner over the levels, least significant first: v = ((T_{S+1} 2^-8 + T_S) 2^-8 + ...); 2^-16 applied below
 #pragma unroll
-        for (int c = 0; c < 16; ++c) vacc[h * 16 + c] = (double)(int)t[c];
+        for (int h = 0; h < CW / 8; ++h) {
+          uint32_t t[S][8];
 #pragma unroll
-        for (int l = S - 2; l >= 0; --l) {
-          oz::tmem_ld16(lane_base + (uint32_t)(l * NT) + h * 16, t);
+          for (int l = 0; l < S; ++l) tmem_ld8_nowait(lane_base + (uint32_t)(l * NT) + h * 8, t[l]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          // zero-instruction fences: volatile asms keep their order, so every use of a loaded register below is tied to a
+          // definition placed after the wait (plain arithmetic is not ordered against an asm by its memory clobber alone)
 #pragma unroll
-          for (int c = 0; c < 16; ++c) vacc[h * 16 + c] = fma(vacc[h * 16 + c], 0x1p-8, (double)(int)t[c]);
+          for (int l = 0; l < S; ++l)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) asm volatile("" : "+r"(t[l][c]));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            double v = int_to_double(t[S - 1][c]);
+#pragma unroll
+            for (int l = S - 2; l >= 0; --l) v = fma(v, 0x1p-8, int_to_double(t[l][c]));
+            vacc[h * 8 + c] = v;
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);  // accumulators are free again: the next row-block's MMAs start now
+        // A = rs 2^-16 v + rc; column sums of A^2 over the warp's 32 rows by recursive halving
+        const double rs16 = rs * 0x1p-16;
+#pragma unroll
+        for (int h = 0; h < CW / 16; ++h) {
+          double a[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const double v = fma(vacc[h * 16 + c], rs16, rc);
+            a[c] = v * v;
+          }
+          double b8[8], b4[4], b2[2];
+          bool up = (lane & 16) != 0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const double mine = up ? a[8 + c] : a[c], theirs = up ? a[c] : a[8 + c];
+            b8[c] = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
+          }
+          up = (lane & 8) != 0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double mine = up ? b8[4 + c] : b8[c], theirs = up ? b8[c] : b8[4 + c];
+            b4[c] = mine + __shfl_xor_sync(0xffffffffu, theirs, 8);
+          }
+          up = (lane & 4) != 0;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const double mine = up ? b4[2 + c] : b4[c], theirs = up ? b4[c] : b4[2 + c];
+            b2[c] = mine + __shfl_xor_sync(0xffffffffu, theirs, 4);
+          }
+          up = (lane & 2) != 0;
+          double e = (up ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, up ? b2[0] : b2[1], 2);
+          e += __shfl_xor_sync(0xffffffffu, e, 1);
+          colsum[h] += e;  // lane holds column h*16 + (lane >> 1) (both lanes of a pair hold the same sum)
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);  // accumulators are free again: the next row-block's MMAs start now
-      // A = rs 2^-16 v + rc; column sums of A^2 over the warp's 32 rows by recursive halving
-      const double rs16 = rs * 0x1p-16;
+      // end of the item: combine the four row-quarters (warps lq = 0..3 of the same column half) through the dedicated
+      // exchange buffer (the stage buffers already receive the next item's tiles)
+      if ((lane & 1) == 0) {
 #pragma unroll
-      for (int h = 0; h < CW / 16; ++h) {
-        double a[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const double v = fma(vacc[h * 16 + c], rs16, rc);
-          a[c] = v * v;
-        }
-        double b8[8], b4[4], b2[2];
-        bool up = (lane & 16) != 0;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const double mine = up ? a[8 + c] : a[c], theirs = up ? a[c] : a[8 + c];
-          b8[c] = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
-        }
-        up = (lane & 8) != 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double mine = up ? b8[4 + c] : b8[c], theirs = up ? b8[c] : b8[4 + c];
-          b4[c] = mine + __shfl_xor_sync(0xffffffffu, theirs, 8);
-        }
-        up = (lane & 4) != 0;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const double mine = up ? b4[2 + c] : b4[c], theirs = up ? b4[c] : b4[2 + c];
-          b2[c] = mine + __shfl_xor_sync(0xffffffffu, theirs, 4);
-        }
-        up = (lane & 2) != 0;
-        double e = (up ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, up ? b2[0] : b2[1], 2);
-        e += __shfl_xor_sync(0xffffffffu, e, 1);
-        colsum[h] += e;  // lane holds column h*16 + (lane >> 1) (both lanes of a pair hold the same sum)
+        for (int h = 0; h < CW / 16; ++h) redbuf[warp][h * 16 + (lane >> 1)] = colsum[h];
       }
-    }
-    // combine the four row-quarters (warps lq = 0..3 of the same column half) through shared memory
-    // (every MMA has retired and every stage has been consumed, so the stage buffers are free)
-    double (*redbuf)[CW] = reinterpret_cast<double (*)[CW]>(smem);
-    if ((lane & 1) == 0) {
-#pragma unroll
-      for (int h = 0; h < CW / 16; ++h) redbuf[warp][h * 16 + (lane >> 1)] = colsum[h];
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(EW * 32));
-    for (int col = threadIdx.x; col < NT; col += EW * 32) {
-      const int cg = col / CW, cc = col % CW, wb = cg * 4;
-      partial[(int64_t)g * McPad + (int64_t)tile * NT + col] = redbuf[wb][cc] + redbuf[wb + 1][cc] + redbuf[wb + 2][cc] + redbuf[wb + 3][cc];
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32));
+      for (int col = threadIdx.x; col < NT; col += EW * 32) {
+        const int cg = col / CW, cc = col % CW, wb = cg * 4;
+        partial[(int64_t)g * McPad + (int64_t)tile * NT + col] = redbuf[wb][cc] + redbuf[wb + 1][cc] + redbuf[wb + 2][cc] + redbuf[wb + 3][cc];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32));  // redbuf is reused by the next item
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -400,7 +400,9 @@ static int alpha_from_linv(tb_gp* gp) {
 }
 
 // pack the lower triangle of Linv into DMMA-fragment-ordered panels and mark the derived operand sets stale
-static int finish_cache(tb_gp* gp) {
+// appended_from > 0: the cache was extended from that many rows by tb_gp_append_data (the dense K^-1, when it exists, is grown
+// by the same rank instead of being invalidated)
+static int finish_cache(tb_gp* gp, int64_t appended_from = 0) {
   const int64_t N = gp->N;
   cudaStream_t st = gp->stream;
   int64_t npanels = rowblock_panel_offset(gp->NB);
@@ -416,6 +418,18 @@ static int finish_cache(tb_gp* gp) {
   gp->oz_valid = false;
   gp->oz5_valid = false;
   gp->kinv_valid = false;
+  if (appended_from > 0 && gp->kinv_dense_valid && gp->kinv_dense_N == appended_from) {
+    TB_TRY(gp->dKinvSpare.reserve(sizeof(double) * N * N));
+    fac::kinv_grow_kernel<<<dim3((unsigned)((N + 127) / 128), (unsigned)N), 128, 0, st>>>(gp->dKinv.as<double>(), appended_from,
+                                                                                       gp->dLinv.as<double>(), N, gp->dKinvSpare.as<double>());
+    TB_LAUNCHED();
+    TB_CUDA(cudaStreamSynchronize(st));
+    TB_CUDA(cudaGetLastError());
+    std::swap(gp->dKinv, gp->dKinvSpare);
+    gp->kinv_dense_N = N;
+  } else {
+    gp->kinv_dense_valid = false;
+  }
   return 0;
 }
 
@@ -610,7 +624,7 @@ static int tb_gp_append_data_f64(tb_gp* gp, const double* Xnew, const double* yn
   TB_CHECK_CODE(info == 0, "tb_gp_append_data: Cholesky decomposition was not successful "
                       "(K + noise*I not positive definite at leading minor " + std::to_string(info) + ")", tb::ERR_NUMERIC);
   TB_TRY(alpha_from_linv(gp));
-  return finish_cache(gp);
+  return finish_cache(gp, N0);
 }
 
 static int tb_gp_get_cholesky_f64(tb_gp* gp, void* L_out) {
@@ -824,21 +838,27 @@ static int ensure_kinv_digits(tb_gp* gp) {
   TB_TRY(ensure_ozaki(gp));
   cudaStream_t st = gp->stream;
   const int64_t N = gp->N, rows = (int64_t)gp->NB * BM;
-  TB_TRY(gp->dKinv.reserve(sizeof(double) * N * N));
-  if (gp->factor_own) {
-    const unsigned t = (unsigned)((N + fac::FB - 1) / fac::FB);
-    fac::kinv_kernel<<<dim3(t, t), fac::THREADS, fac::GEMM_SMEM, st>>>(gp->dLinv.as<double>(), gp->dKinv.as<double>(), N);
-    TB_LAUNCHED();
-  } else {
-  TB_TRY(ensure_library_handles(gp));
-  TB_CUDA(cudaMemcpyAsync(gp->dKinv.p, gp->dL.p, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, st));
-  int lwork = 0;
-  cusolverStatus_t cs = cusolverDnDpotri_bufferSize(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, &lwork);
-  TB_CHECK(cs == CUSOLVER_STATUS_SUCCESS, "cusolverDnDpotri_bufferSize failed");
-  TB_TRY(gp->dWork.reserve(sizeof(double) * (size_t)std::max(lwork, 1)));
-  cs = cusolverDnDpotri(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, gp->dWork.as<double>(), lwork,
-                        gp->dInfo.as<int>());
-  TB_CHECK(cs == CUSOLVER_STATUS_SUCCESS, "cusolverDnDpotri failed");
+  if (!(gp->kinv_dense_valid && gp->kinv_dense_N == N)) {
+    // dense K^-1 = Linv^T Linv (lower triangle), O(N^3) on the DMMA pipe: once per full cache refresh; appends grow it in
+    // O(m N^2) (finish_cache / fac::kinv_grow_kernel)
+    TB_TRY(gp->dKinv.reserve(sizeof(double) * N * N));
+    if (gp->factor_own) {
+      const unsigned t = (unsigned)((N + fac::FB - 1) / fac::FB);
+      fac::kinv_kernel<<<dim3(t, t), fac::THREADS, fac::GEMM_SMEM, st>>>(gp->dLinv.as<double>(), gp->dKinv.as<double>(), N);
+      TB_LAUNCHED();
+    } else {
+      TB_TRY(ensure_library_handles(gp));
+      TB_CUDA(cudaMemcpyAsync(gp->dKinv.p, gp->dL.p, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, st));
+      int lwork = 0;
+      cusolverStatus_t cs = cusolverDnDpotri_bufferSize(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, &lwork);
+      TB_CHECK_CODE(cs == CUSOLVER_STATUS_SUCCESS, "cusolverDnDpotri_bufferSize failed", tb::ERR_RUNTIME);
+      TB_TRY(gp->dWork.reserve(sizeof(double) * (size_t)std::max(lwork, 1)));
+      cs = cusolverDnDpotri(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, gp->dWork.as<double>(), lwork,
+                            gp->dInfo.as<int>());
+      TB_CHECK_CODE(cs == CUSOLVER_STATUS_SUCCESS, "cusolverDnDpotri failed", tb::ERR_RUNTIME);
+    }
+    gp->kinv_dense_valid = true;
+    gp->kinv_dense_N = N;
   }
   TB_TRY(gp->dKinvScale.reserve(sizeof(double) * rows));
   oz::sym_rowscale_kernel<<<(unsigned)rows, 256, 0, st>>>(gp->dKinv.as<double>(), N, rows, gp->dKinvScale.as<double>());
@@ -850,7 +870,6 @@ static int ensure_kinv_digits(tb_gp* gp) {
   TB_LAUNCHED();
   TB_CUDA(cudaStreamSynchronize(st));
   TB_CUDA(cudaGetLastError());
-  gp->dKinv.release();  // the dense copy is only needed to cut the digits
   gp->kinv_valid = true;
   return 0;
 }
