@@ -100,7 +100,11 @@ struct tb_gp {
   bool oz5_valid = false;
   bool oz_full = false;  // tb_gp_set_engine(2): always the 6-digit / 21-product kernels
   int oz5_mode = 0;
+  int oz5_planes = 0;    // digit planes stored per operand stage (5: fp64 handles; 4: fp32 handles, whose variance GEMM computes
+                         // with the 3 leading planes and whose store-A / V GEMMs use all 4)
   double oz5_est = 0.0;  // a-priori estimate of max |Δvar| / σ_f² in the chosen mode
+  tb::DevBuf dKinvS5, dKinvScale5, dKinvSum5;  // tight digit tiles / row scales / row sums of the dense K^-1 (gradient path)
+  bool kinv5_valid = false, kinv5_ok = false;  // kinv5_ok: the V GEMM's own error estimate admits the single-pass engine
   tb::DevBuf dWork, dInfo;      // cusolver workspace / info flag
   tb::DevBuf dDinv;             // inverses of the diagonal blocks of L (hand-written factorisation)
   bool factor_own = true;       // false (TB_FACTOR=cusolver): cuSOLVER / cuBLAS cross-check path

@@ -7,14 +7,20 @@
 namespace tb {
 
 int oz5_init() {
-  TB_CUDA(cudaFuncSetAttribute(oz5::trigemm_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz5::smem_bytes<5>()));
-  TB_CUDA(cudaFuncSetAttribute(oz5::trigemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz5::smem_bytes<3>()));
+#define TB_ATTR(SV, EPI) \
+  TB_CUDA(cudaFuncSetAttribute(oz5::trigemm_kernel<SV, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz5::smem_bytes<SV>()))
+  TB_ATTR(5, oz5::EPI_SUMSQ);
+  TB_ATTR(5, oz5::EPI_STORE);
+  TB_ATTR(4, oz5::EPI_SUMSQ);
+  TB_ATTR(4, oz5::EPI_STORE);
+  TB_ATTR(3, oz5::EPI_SUMSQ);
+#undef TB_ATTR
   return 0;
 }
 
-int oz5_tile_width(const tb_gp* gp) { return gp->oz5_mode == 5 ? oz5::Geo<5>::NT : oz5::Geo<3>::NT; }
+int oz5_tile_width(const tb_gp* gp) { return gp->oz5_planes == 5 ? oz5::Geo<5>::NT : oz5::Geo<4>::NT; }
 size_t oz5_tile_bytes(const tb_gp* gp) {
-  return (size_t)gp->nst * (gp->oz5_mode == 5 ? 5 * oz5::btile<5>() : 3 * oz5::btile<3>());
+  return (size_t)gp->nst * (gp->oz5_planes == 5 ? 5 * oz5::btile<5>() : 4 * oz5::btile<4>());
 }
 
 // Calibrated a-priori estimate of max |Δvar| / σ_f² when the levels r > S+1 are dropped: per element of A the dropped
@@ -69,16 +75,68 @@ int oz5_ensure(tb_gp* gp) {
   TB_CUDA(cudaStreamSynchronize(st));
   double mx = 0.0;
   for (double v : h) mx = std::max(mx, v);
-  // fp64 handles: 5 digits / 15 products if the estimate clears 3e-10 (bar: 1e-9); fp32 handles: 3 digits / 6 products if it
-  // clears 3e-5 (bar: 1e-4), else the 5-digit mode, else the 6-digit kernels
-  int mode = 0;
-  if (gp->dtype == TB_F32 && (force == 1 || oz5_estimate(gp->variance, mx, gp->N, 3) <= 3e-5)) mode = 3;
-  if (mode == 0 && (force == 1 || oz5_estimate(gp->variance, mx, gp->N, 5) <= (gp->dtype == TB_F32 ? 3e-5 : 3e-10))) mode = 5;
-  if (mode == 5) TB_TRY(build_digits<5>(gp, st));
-  if (mode == 3) TB_TRY(build_digits<3>(gp, st));
+  // fp64 handles: 5 digits / 15 products if the estimate clears 3e-10 (bar: 1e-9).  fp32 handles (bar: 1e-4): 4 planes are
+  // stored; the variance GEMM computes with 3 digits / 6 products if that clears 3e-5, else with all 4 (10 products, one pass);
+  // if even 4 digits do not clear it the handle is treated like an fp64 one.  Otherwise: the 6-digit two-pass kernels.
+  int mode = 0, planes = 0;
+  if (gp->dtype == TB_F32) {
+    if (force == 1 || oz5_estimate(gp->variance, mx, gp->N, 3) <= 3e-5) mode = 3, planes = 4;
+    else if (oz5_estimate(gp->variance, mx, gp->N, 4) <= 3e-5) mode = 4, planes = 4;
+  }
+  if (mode == 0 && (force == 1 || oz5_estimate(gp->variance, mx, gp->N, 5) <= (gp->dtype == TB_F32 ? 3e-5 : 3e-10))) mode = 5, planes = 5;
+  if (planes == 5) TB_TRY(build_digits<5>(gp, st));
+  if (planes == 4) TB_TRY(build_digits<4>(gp, st));
   if (mode) gp->oz5_est = oz5_estimate(gp->variance, mx, gp->N, mode);
   gp->oz5_mode = mode;
+  gp->oz5_planes = planes;
+  gp->kinv5_valid = false;
   gp->oz5_valid = true;
+  return 0;
+}
+
+// Tight digit tiles of the dense K^-1 (gp->dKinv, lower triangle, ld = N; kept current by ensure_kinv_dense / the rank-m
+// growth on append).  The V GEMM has its own admission test: the element error of V = K^-1 k* is
+// ~ rowscale(K^-1) sB sqrt(6 N) E[d^2] 2^(-8(S+2)); gradients are held to rtol 1e-6 (fp64) / 1e-3 (fp32) and V enters them
+// through sums of ~N terms with |V| ~ 0.1 .. 1, so the element error must stay below ~1e-7 / ~1e-4.
+int oz5_ensure_kinv(tb_gp* gp) {
+  if (gp->kinv5_valid) return 0;
+  gp->kinv5_ok = false;
+  if (gp->oz5_planes == 0) {
+    gp->kinv5_valid = true;
+    return 0;
+  }
+  cudaStream_t st = gp->stream;
+  const int64_t N = gp->N, rows = (int64_t)gp->NB * BM;
+  TB_TRY(gp->dKinvScale5.reserve(sizeof(double) * rows));
+  TB_TRY(gp->dKinvSum5.reserve(sizeof(double) * rows));
+  oz5::sym_rowstats_kernel<<<(unsigned)rows, 256, 0, st>>>(gp->dKinv.as<double>(), N, rows, gp->dKinvScale5.as<double>(),
+                                                          gp->dKinvSum5.as<double>());
+  TB_LAUNCHED();
+  std::vector<double> h((size_t)N);
+  TB_CUDA(cudaMemcpyAsync(h.data(), gp->dKinvScale5.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  double mx = 0.0;
+  for (double v : h) mx = std::max(mx, v);
+  const int S = gp->oz5_planes;
+  const double sB = 0.5 * gp->variance / oz5::FILL;
+  const double eps_v = mx * sB * std::sqrt(6.0 * (double)N) * (65536.0 / 12.0) * std::ldexp(1.0, -8 * (S + 2));
+  int force = -1;
+  if (const char* e = std::getenv("TB_OZ_FAST")) force = std::atoi(e);
+  gp->kinv5_ok = force == 1 || eps_v <= (gp->dtype == TB_F32 ? 1e-4 : 1e-7);
+  if (gp->kinv5_ok) {
+    const size_t bytes = (size_t)gp->NB * gp->nst * S * oz5::ATILE;
+    TB_TRY(gp->dKinvS5.reserve(bytes));
+    if (S == 5)
+      oz5::sym_digits_kernel<5><<<dim3(gp->nst, gp->NB), 256, 0, st>>>(gp->dKinv.as<double>(), N, gp->nst, gp->dKinvScale5.as<double>(),
+                                                                      gp->dKinvS5.as<int8_t>());
+    else
+      oz5::sym_digits_kernel<4><<<dim3(gp->nst, gp->NB), 256, 0, st>>>(gp->dKinv.as<double>(), N, gp->nst, gp->dKinvScale5.as<double>(),
+                                                                      gp->dKinvS5.as<int8_t>());
+    TB_LAUNCHED();
+    TB_CUDA(cudaStreamSynchronize(st));
+    TB_CUDA(cudaGetLastError());
+  }
+  gp->kinv5_valid = true;
   return 0;
 }
 
@@ -99,9 +157,11 @@ static int launch_kstar_s(tb_gp* gp, cudaStream_t st, const double* Xc_dev, int6
   const double inv_b = oz5::two_pow_8S<S>() * oz5::FILL / (0.5 * var);
   const double dig_c = fm::MAGIC + oz5::dig_koff<S>() - oz5_centre_int<S>();
   const double* X2 = gp->dX2.as<double>();
-  constexpr int TH = oz5::Geo<S>::NT * 4;
-#define TB_KD(KIND, DPV) \
-  oz5::kstar_digits_kernel<KIND, DPV, S><<<tiles, TH, 0, st>>>(Xs, X2, al, Xc_dev, il, N, nst, D, mc, var, inv_b, dig_c, mc0, fm::Consts(), BS, mean)
+  constexpr int TH = oz5::KGEN_WARPS * 32;
+  const unsigned ctas = (unsigned)(((int64_t)tiles * (oz5::Geo<S>::NT / 8) + oz5::KGEN_WARPS - 1) / oz5::KGEN_WARPS);
+#define TB_KD(KIND, DPV)                                                                                                            \
+  oz5::kstar_digits_kernel<KIND, DPV, S><<<ctas, TH, 0, st>>>(Xs, X2, al, Xc_dev, il, N, nst, D, mc, var, inv_b, dig_c, mc0, fm::Consts(), \
+                                                              tiles, BS, mean)
 #define TB_KD_DP(KIND)                 \
   switch (gp->DP) {                    \
     case 2: TB_KD(KIND, 2); break;     \
@@ -129,27 +189,60 @@ static int launch_kstar_s(tb_gp* gp, cudaStream_t st, const double* Xc_dev, int6
 }
 
 int oz5_launch_kstar(tb_gp* gp, cudaStream_t st, const double* Xc_dev, int64_t mc, int tiles, int8_t* BS, double* mean) {
-  return gp->oz5_mode == 5 ? launch_kstar_s<5>(gp, st, Xc_dev, mc, tiles, BS, mean) : launch_kstar_s<3>(gp, st, Xc_dev, mc, tiles, BS, mean);
+  return gp->oz5_planes == 5 ? launch_kstar_s<5>(gp, st, Xc_dev, mc, tiles, BS, mean) : launch_kstar_s<4>(gp, st, Xc_dev, mc, tiles, BS, mean);
 }
 
-int oz5_launch_gemm(tb_gp* gp, cudaStream_t st, const int8_t* BS, int tiles, int G, int64_t McPad, double* partial) {
-  const double sB = 0.5 * gp->variance / oz5::FILL;
-  // persistent grid: one CTA per SM (fewer when there are fewer work items)
+static int oz5_grid(tb_gp* gp, int items, int* grid) {  // persistent grid: one CTA per SM (fewer when there are fewer work items)
   static int sms = 0;
   if (sms == 0) {
     cudaDeviceProp prop;
     TB_CUDA(cudaGetDeviceProperties(&prop, gp->device));
     sms = prop.multiProcessorCount;
   }
-  const int grid = std::min(sms, tiles * G);
-  if (gp->oz5_mode == 5)
-    oz5::trigemm_kernel<5><<<grid, (oz5::EW + 2) * 32, oz5::smem_bytes<5>(), st>>>(
-        gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, tiles, McPad, sB,
-        oz5_h_eff<5>(gp->variance), partial);
-  else
-    oz5::trigemm_kernel<3><<<grid, (oz5::EW + 2) * 32, oz5::smem_bytes<3>(), st>>>(
-        gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, tiles, McPad, sB,
-        oz5_h_eff<3>(gp->variance), partial);
+  *grid = std::min(sms, items);
+  return 0;
+}
+
+// The K* digits are cut against sB = h / FILL with 2^(8 planes) steps; a GEMM that computes with S < planes leading digits sees
+// exactly the same scaled operand (the planes are a prefix of the same balanced expansion), so out_scale and h_eff are those
+// of the STORED split.
+template <int PL>
+static double h_eff_planes(double variance) { return oz5_h_eff<PL>(variance); }
+
+int oz5_launch_gemm(tb_gp* gp, cudaStream_t st, const int8_t* BS, int tiles, int G, int64_t McPad, double* partial) {
+  const double sB = 0.5 * gp->variance / oz5::FILL;
+  int grid = 0;
+  TB_TRY(oz5_grid(gp, tiles * G, &grid));
+  const int pl = gp->oz5_planes;
+  const double h = pl == 5 ? h_eff_planes<5>(gp->variance) : h_eff_planes<4>(gp->variance);
+#define TB_GEMM(SV)                                                                                                                  \
+  oz5::trigemm_kernel<SV, oz5::EPI_SUMSQ><<<grid, (oz5::EW + 2) * 32, oz5::smem_bytes<SV>(), st>>>(                                  \
+      gp->dAS5.as<int8_t>(), BS, gp->dRowScale5.as<double>(), gp->dRowSum5.as<double>(), gp->NB, gp->nst, G, tiles, McPad, sB, h, pl, pl, 0, \
+      partial, nullptr, 0)
+  if (gp->oz5_mode == 5) TB_GEMM(5);
+  else if (gp->oz5_mode == 4) TB_GEMM(4);
+  else TB_GEMM(3);
+#undef TB_GEMM
+  TB_LAUNCHED();
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int oz5_launch_gemm_store(tb_gp* gp, cudaStream_t st, int left, const int8_t* BS, int tiles, int G, double* out, int64_t lda) {
+  const double sB = 0.5 * gp->variance / oz5::FILL;
+  int grid = 0;
+  TB_TRY(oz5_grid(gp, tiles * G, &grid));
+  const int pl = gp->oz5_planes;
+  const double h = pl == 5 ? h_eff_planes<5>(gp->variance) : h_eff_planes<4>(gp->variance);
+  const int8_t* AS = left ? gp->dKinvS5.as<int8_t>() : gp->dAS5.as<int8_t>();
+  const double* rs = left ? gp->dKinvScale5.as<double>() : gp->dRowScale5.as<double>();
+  const double* rc = left ? gp->dKinvSum5.as<double>() : gp->dRowSum5.as<double>();
+#define TB_GEMM(SV)                                                                                                          \
+  oz5::trigemm_kernel<SV, oz5::EPI_STORE><<<grid, (oz5::EW + 2) * 32, oz5::smem_bytes<SV>(), st>>>(                           \
+      AS, BS, rs, rc, gp->NB, gp->nst, G, tiles, 0, sB, h, pl, pl, left ? 1 : 0, nullptr, out, lda)
+  if (pl == 5) TB_GEMM(5);
+  else TB_GEMM(4);
+#undef TB_GEMM
   TB_LAUNCHED();
   TB_CUDA(cudaGetLastError());
   return 0;

@@ -29,25 +29,26 @@ constexpr int EW = 8;  // epilogue warps
 
 template <int S> struct Geo;
 template <> struct Geo<5> { static constexpr int NT = 96; };
+template <> struct Geo<4> { static constexpr int NT = 128; };
 template <> struct Geo<3> { static constexpr int NT = 128; };
 
 template <int S> __host__ __device__ constexpr int btile() { return Geo<S>::NT * KST; }
 template <int S> __host__ __device__ constexpr int stage_bytes() { return S * (ATILE + btile<S>()); }
 template <int S> __host__ __device__ constexpr size_t smem_bytes() {  // stages + barriers + the epilogue's column-sum exchange buffer
-  return (size_t)STAGES * stage_bytes<S>() + 256 + (size_t)EW * (Geo<S>::NT / 2) * sizeof(double);
+  return (size_t)STAGES * stage_bytes<S>() + 256 + (size_t)6 * (Geo<S>::NT / 2) * sizeof(double);
 }
-template <int S> __host__ __device__ constexpr double two_pow_8S() { return S == 5 ? 1099511627776.0 : 16777216.0; }  // 2^40 / 2^24
+template <int S> __host__ __device__ constexpr double two_pow_8S() { return S == 5 ? 1099511627776.0 : S == 4 ? 4294967296.0 : 16777216.0; }  // 2^40 / 2^32 / 2^24
 
 // v = Σ_{p=1..S} d_p 256^(S-p), d_p in [-128,127]: the int8 digits are the bytes of (v + 0x80..80) ^ 0x80..80 (no carry chain);
 // byte 0 = least significant digit d_S
 template <int S>
 __device__ __forceinline__ void digit_bytes(long long v, uint32_t& lo, uint32_t& hi) {
-  constexpr unsigned long long K = S == 5 ? 0x0000008080808080ULL : 0x0000000000808080ULL;
+  constexpr unsigned long long K = S == 5 ? 0x0000008080808080ULL : S == 4 ? 0x0000000080808080ULL : 0x0000000000808080ULL;
   const unsigned long long w = ((unsigned long long)v + K) ^ K;
   lo = (uint32_t)w;
   hi = (uint32_t)(w >> 32);
 }
-template <int S> __host__ __device__ constexpr double dig_koff() { return S == 5 ? 551911719040.0 : 8421504.0; }  // 0x8080808080 / 0x808080
+template <int S> __host__ __device__ constexpr double dig_koff() { return S == 5 ? 551911719040.0 : S == 4 ? 2155905152.0 : 8421504.0; }  // 0x8080808080 / 0x80808080 / 0x808080
 // element JJ (0..15) of the lane's 16-byte rows: plane p (0 = most significant digit) takes byte S-1-p of the word
 template <int S, int JJ>
 __device__ __forceinline__ void scatter(uint32_t (&pk)[S][4], uint32_t lo, uint32_t hi) {
@@ -156,18 +157,76 @@ __global__ void linv_digits_kernel(const double* __restrict__ Linv, int64_t N, c
   }
 }
 
+// K^-1 (gradient path): symmetric, given by its lower triangle (column-major, ld = N); full rows, same tight scaling and
+// row sums as for Linv:  V = K^-1 k* = K^-1 K~ + h rowsum(K^-1)
+__device__ __forceinline__ double sym_lower_at(const double* __restrict__ A, int64_t N, int64_t n, int64_t k) {
+  return n >= k ? A[n + k * N] : A[k + n * N];
+}
+__global__ void sym_rowstats_kernel(const double* __restrict__ A, int64_t N, int64_t rows, double* __restrict__ rowscale,
+                                    double* __restrict__ rowsum) {
+  const int64_t n = blockIdx.x;
+  double mx = 0.0, sm = 0.0;
+  if (n < N)
+    for (int64_t k = threadIdx.x; k < N; k += blockDim.x) {
+      const double v = sym_lower_at(A, N, n, k);
+      mx = fmax(mx, fabs(v));
+      sm += v;
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    sm += __shfl_xor_sync(0xffffffffu, sm, o);
+  }
+  __shared__ double smx[8], ssm[8];
+  if ((threadIdx.x & 31) == 0) {
+    smx[threadIdx.x >> 5] = mx;
+    ssm[threadIdx.x >> 5] = sm;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      mx = fmax(mx, smx[w]);
+      sm += ssm[w];
+    }
+    if (n < rows) {
+      rowscale[n] = mx > 0.0 ? mx / FILL : 1.0;
+      rowsum[n] = sm;
+    }
+  }
+}
+template <int S>
+__global__ void sym_digits_kernel(const double* __restrict__ A, int64_t N, int nst, const double* __restrict__ rowscale,
+                                  int8_t* __restrict__ AS) {
+  const int I = blockIdx.y, kc = blockIdx.x;
+  int8_t* dst = AS + ((int64_t)I * nst + kc) * (int64_t)(S * ATILE);
+  for (int e = threadIdx.x; e < 128 * KST; e += blockDim.x) {
+    const int r = e % 128, kin = e / 128;
+    const int64_t n = (int64_t)I * 128 + r, k = (int64_t)kc * KST + kin;
+    long long v = 0;
+    if (n < N && k < N) v = __double2ll_rn(sym_lower_at(A, N, n, k) / rowscale[n] * two_pow_8S<S>());
+    uint32_t lo, hi;
+    digit_bytes<S>(v, lo, hi);
+    const unsigned long long w = ((unsigned long long)hi << 32) | lo;
+    const int off = (r >> 3) * SBO + (kin >> 4) * LBO + (r & 7) * 16 + (kin & 15);
+#pragma unroll
+    for (int p = 0; p < S; ++p) dst[p * ATILE + off] = (int8_t)((w >> (8 * (S - 1 - p))) & 0xff);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
-// centred K* digit tiles + posterior mean.  One CTA per candidate tile of NT candidates, NT/8 warps: warp w owns candidates
-// [8w, 8w+8); lane l <-> (candidate l % 8, 16-wide k chunk l / 8): every digit store of a warp is 512 contiguous bytes.
+// centred K* digit tiles + posterior mean.  CTAs of KGEN_WARPS warps; warp (global index wg) owns the 8 candidates
+// [8 (wg % (NT/8)), +8) of candidate tile wg / (NT/8); lane l <-> (candidate l % 8, 16-wide k chunk l / 8): every digit
+// store of a warp is 512 contiguous bytes.  The training rows of a stage are staged per CTA (they do not depend on the tile).
 //   inv_bscale_2p = 2^(8S) / sB,  sB = h / FILL,  h = variance / 2
 // ------------------------------------------------------------------------------------------------
+constexpr int KGEN_WARPS = 8;
 template <int KIND, int DP, int S>
-__global__ void __launch_bounds__(Geo<S>::NT * 4, Geo<S>::NT * 4 <= 384 ? 2 : 1)
+__global__ void __launch_bounds__(KGEN_WARPS * 32, 4)  // 64 registers (a few bytes of spill), 32 warps per SM
 kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ X2, const double* __restrict__ alpha,
                     const double* __restrict__ Xc, const double* __restrict__ inv_ls, int N, int nst, int D, int64_t M, double variance,
-                    double inv_bscale_2p, double dig_c, double mean_const, const __grid_constant__ fm::Consts fc,
+                    double inv_bscale_2p, double dig_c, double mean_const, const __grid_constant__ fm::Consts fc, int ntiles,
                     int8_t* __restrict__ BS, double* __restrict__ mean_out) {
-  constexpr int NT = Geo<S>::NT, BTILE = NT * KST, TH = NT * 4;
+  constexpr int NT = Geo<S>::NT, BTILE = NT * KST, TH = KGEN_WARPS * 32, WPT = NT / 8;  // WPT: warps per candidate tile
   // No masking of k >= N or of candidates t >= M is needed: training rows beyond N are zero-padded (their kernel values are
   // finite), alpha is zero there and so are all digits of Linv's columns k >= N, so those K* digits never reach a result;
   // padded candidates produce values nobody reads.
@@ -175,12 +234,14 @@ kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ X2
   // cancellation noise of the expansion form would show at 1e-8), the expansion |a|^2 + |b|^2 - 2 a.b (GPflow's
   // square_distance; D FMAs instead of 2 D operations per element) for the smooth kernels
   constexpr bool EXPAND = KIND != TB_MATERN12;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t tile_id = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t wg = (int64_t)blockIdx.x * KGEN_WARPS + (threadIdx.x >> 5);
+  const int64_t tile_id = wg / WPT;
+  const int w = (int)(wg % WPT);
   const int cl = lane & 7, ch = lane >> 3;
   const int t_local = w * 8 + cl;
   const int64_t t = tile_id * NT + t_local;
-  const bool valid = t < M;
+  const bool valid = t < M && tile_id < ntiles;  // warps past the last tile still take part in the staging barriers
   double xc[DP];
   double xc2 = 0.0;
 #pragma unroll
@@ -265,14 +326,16 @@ kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ X2
       const uint32_t wl = (uint32_t)__double2loint(tb) ^ 0x80808080u, wh = (uint32_t)__double2hiint(tb) ^ 0x80u;
       scatter_rt<S>(pk, j, wl, wh);
     }
+    if (tile_id < ntiles) {
 #pragma unroll
-    for (int p = 0; p < S; ++p)
-      *reinterpret_cast<uint4*>(tile + (int64_t)kc * (S * BTILE) + p * BTILE) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+      for (int p = 0; p < S; ++p)
+        *reinterpret_cast<uint4*>(tile + (int64_t)kc * (S * BTILE) + p * BTILE) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+    }
     __syncthreads();
   }
   macc += __shfl_xor_sync(0xffffffffu, macc, 8);
   macc += __shfl_xor_sync(0xffffffffu, macc, 16);
-  if (ch == 0) mean_out[tile_id * NT + t_local] = macc + mean_const;
+  if (ch == 0 && tile_id < ntiles) mean_out[tile_id * NT + t_local] = macc + mean_const;
 }
 
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
@@ -323,11 +386,18 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t stage_base, 
 //   partial[g][t] = Σ_{rows n of group g} A[n,t]^2,
 //   A[n,t] = rowscale[n]·out_scale · Σ_{r=2..S+1} 2^(-8r) T_r[n,t]  +  half_var·rowsum[n]
 // ------------------------------------------------------------------------------------------------
-template <int S>
+// EPI_SUMSQ: partial column sums of A^2 (variance path).  EPI_STORE: A itself, fp64, candidate-major [t][lda] (joint path; with
+// the dense K^-1 as left factor: V = K^-1 k* of the gradient path).
+// a_planes / b_planes: digit planes STORED per stage of the left / right operand (>= S): a kernel computing with S digits reads
+// the S most significant planes of a wider split (fp32 models: 4 planes stored, the variance GEMM uses 3, the V GEMM 4).
+// full_rows = 0: lower-triangular left factor (Linv), row-block I spans stages [0, 2(I+1)), packed triangularly;
+// full_rows = 1: dense square left factor, every row-block spans all nst stages, offset I * nst.
+enum { EPI_SUMSQ = 0, EPI_STORE = 1 };
+template <int S, int EPI>
 __global__ void __launch_bounds__((EW + 2) * 32, 1)
 trigemm_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, const double* __restrict__ rowscale,
                const double* __restrict__ rowsum, int NB, int nst, int G, int tiles, int64_t McPad, double out_scale, double half_var,
-               double* __restrict__ partial) {
+               int a_planes, int b_planes, int full_rows, double* __restrict__ partial, double* __restrict__ Aplain, int64_t lda) {
   constexpr int NT = Geo<S>::NT, BTILE = NT * KST, STAGE = S * (ATILE + BTILE);
   constexpr int CW = NT / 2;  // accumulator columns per epilogue warp: 48 (S = 5) or 64 (S = 3)
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -337,7 +407,7 @@ trigemm_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, con
   uint64_t* acc_full = bars + 2 * STAGES;      // MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * STAGES + 1; // epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
-  double (*redbuf)[CW] = reinterpret_cast<double (*)[CW]>(smem + (size_t)STAGES * STAGE + 256);  // [EW][CW] column-sum exchange
+  double (*redbuf)[CW] = reinterpret_cast<double (*)[CW]>(smem + (size_t)STAGES * STAGE + 256);  // [2 halves x 3 quarters][CW] exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nitems = tiles * G;
@@ -364,18 +434,18 @@ trigemm_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, con
       uint32_t ph = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int g = item % G, tile = item / G;
-        const int8_t* bTile = BS + (int64_t)tile * nst * (S * BTILE);
+        const int8_t* bTile = BS + (int64_t)tile * nst * ((int64_t)b_planes * BTILE);
         for (int i = 0;; ++i) {
           const int I = serpentine_rowblock(i, g, G);
           if (I >= NB) break;
-          const int nk = min(2 * (I + 1), nst);
-          const int8_t* aRow = AS + oz::a_stage_offset(I) * (int64_t)(S * ATILE);
+          const int nk = full_rows ? nst : min(2 * (I + 1), nst);
+          const int8_t* aRow = AS + (full_rows ? (int64_t)I * nst : oz::a_stage_offset(I)) * ((int64_t)a_planes * ATILE);
           for (int kc = 0; kc < nk; ++kc) {
             mbar_wait(&empty[st], ph ^ 1);
             unsigned char* dst = smem + (size_t)st * STAGE;
             mbar_expect_tx(&full[st], STAGE);
-            bulk_g2s(dst, aRow + (int64_t)kc * (S * ATILE), S * ATILE, &full[st]);
-            bulk_g2s(dst + S * ATILE, bTile + (int64_t)kc * (S * BTILE), S * BTILE, &full[st]);
+            bulk_g2s(dst, aRow + (int64_t)kc * ((int64_t)a_planes * ATILE), S * ATILE, &full[st]);  // the S leading planes
+            bulk_g2s(dst + S * ATILE, bTile + (int64_t)kc * ((int64_t)b_planes * BTILE), S * BTILE, &full[st]);
             if (++st == STAGES) { st = 0; ph ^= 1; }
           }
         }
@@ -391,7 +461,7 @@ trigemm_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, con
         for (int i = 0;; ++i, ++n) {
           const int I = serpentine_rowblock(i, g, G);
           if (I >= NB) break;
-          const int nk = min(2 * (I + 1), nst);
+          const int nk = full_rows ? nst : min(2 * (I + 1), nst);
           if (n > 0) {  // accumulators must have been read out by the epilogue warps
             mbar_wait(acc_empty, (uint32_t)((n - 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -455,8 +525,15 @@ trigemm_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, con
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty);  // accumulators are free again: the next row-block's MMAs start now
-        // A = rs 2^-16 v + rc; column sums of A^2 over the warp's 32 rows by recursive halving
         const double rs16 = rs * 0x1p-16;
+        if (EPI == EPI_STORE) {
+          // A[n,t] = rs 2^-16 v + rc, candidate-major: the 32 lanes of a warp write 32 consecutive rows (256 B) per column
+          double* dstA = Aplain + ((int64_t)tile * NT + ch * CW) * lda + nrow;
+#pragma unroll
+          for (int c = 0; c < CW; ++c) dstA[(int64_t)c * lda] = fma(vacc[c], rs16, rc);
+          continue;
+        }
+        // A = rs 2^-16 v + rc; column sums of A^2 over the warp's 32 rows by recursive halving
 #pragma unroll
         for (int h = 0; h < CW / 16; ++h) {
           double a[16];
@@ -490,16 +567,21 @@ trigemm_kernel(const int8_t* __restrict__ AS, const int8_t* __restrict__ BS, con
           colsum[h] += e;  // lane holds column h*16 + (lane >> 1) (both lanes of a pair hold the same sum)
         }
       }
+      if (EPI == EPI_STORE) continue;
       // end of the item: combine the four row-quarters (warps lq = 0..3 of the same column half) through the dedicated
       // exchange buffer (the stage buffers already receive the next item's tiles)
-      if ((lane & 1) == 0) {
+      if (lq != 0 && (lane & 1) == 0) {
 #pragma unroll
-        for (int h = 0; h < CW / 16; ++h) redbuf[warp][h * 16 + (lane >> 1)] = colsum[h];
+        for (int h = 0; h < CW / 16; ++h) redbuf[ch * 3 + lq - 1][h * 16 + (lane >> 1)] = colsum[h];
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32));
-      for (int col = threadIdx.x; col < NT; col += EW * 32) {
-        const int cg = col / CW, cc = col % CW, wb = cg * 4;
-        partial[(int64_t)g * McPad + (int64_t)tile * NT + col] = redbuf[wb][cc] + redbuf[wb + 1][cc] + redbuf[wb + 2][cc] + redbuf[wb + 3][cc];
+      if (lq == 0 && (lane & 1) == 0) {  // the first quarter's warp of each column half adds the other three and writes
+#pragma unroll
+        for (int h = 0; h < CW / 16; ++h) {
+          const int cc = h * 16 + (lane >> 1);
+          partial[(int64_t)g * McPad + (int64_t)tile * NT + ch * CW + cc] =
+              ((colsum[h] + redbuf[ch * 3][cc]) + redbuf[ch * 3 + 1][cc]) + redbuf[ch * 3 + 2][cc];
+        }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32));  // redbuf is reused by the next item
     }

@@ -418,6 +418,7 @@ static int finish_cache(tb_gp* gp, int64_t appended_from = 0) {
   gp->oz_valid = false;
   gp->oz5_valid = false;
   gp->kinv_valid = false;
+  gp->kinv5_valid = false;
   if (appended_from > 0 && gp->kinv_dense_valid && gp->kinv_dense_N == appended_from) {
     TB_TRY(gp->dKinvSpare.reserve(sizeof(double) * N * N));
     fac::kinv_grow_kernel<<<dim3((unsigned)((N + 127) / 128), (unsigned)N), 128, 0, st>>>(gp->dKinv.as<double>(), appended_from,
@@ -833,33 +834,40 @@ static int ensure_ozaki(tb_gp* gp) {
 
 // K^-1 digit tiles for the gradient path of the int8 engine: V = K^-1 k* as one dense digit GEMM (same K* digits as the
 // variance GEMM).  K^-1 from the cached factor with cuSOLVER potri (once per BO step, lazily).
+// dense K^-1 = Linv^T Linv (lower triangle, ld = N), O(N^3) on the DMMA pipe: once per full cache refresh; appends grow it in
+// O(m N^2) (finish_cache / fac::kinv_grow_kernel)
+static int ensure_kinv_dense(tb_gp* gp) {
+  const int64_t N = gp->N;
+  if (gp->kinv_dense_valid && gp->kinv_dense_N == N) return 0;
+  cudaStream_t st = gp->stream;
+  TB_TRY(gp->dKinv.reserve(sizeof(double) * N * N));
+  if (gp->factor_own) {
+    const unsigned t = (unsigned)((N + fac::FB - 1) / fac::FB);
+    fac::kinv_kernel<<<dim3(t, t), fac::THREADS, fac::GEMM_SMEM, st>>>(gp->dLinv.as<double>(), gp->dKinv.as<double>(), N);
+    TB_LAUNCHED();
+  } else {
+    TB_TRY(ensure_library_handles(gp));
+    TB_CUDA(cudaMemcpyAsync(gp->dKinv.p, gp->dL.p, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, st));
+    int lwork = 0;
+    cusolverStatus_t cs = cusolverDnDpotri_bufferSize(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, &lwork);
+    TB_CHECK_CODE(cs == CUSOLVER_STATUS_SUCCESS, "cusolverDnDpotri_bufferSize failed", tb::ERR_RUNTIME);
+    TB_TRY(gp->dWork.reserve(sizeof(double) * (size_t)std::max(lwork, 1)));
+    cs = cusolverDnDpotri(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, gp->dWork.as<double>(), lwork,
+                          gp->dInfo.as<int>());
+    TB_CHECK_CODE(cs == CUSOLVER_STATUS_SUCCESS, "cusolverDnDpotri failed", tb::ERR_RUNTIME);
+  }
+  gp->kinv_dense_valid = true;
+  gp->kinv_dense_N = N;
+  gp->kinv5_valid = false;
+  return 0;
+}
+
 static int ensure_kinv_digits(tb_gp* gp) {
   if (gp->kinv_valid) return 0;
   TB_TRY(ensure_ozaki(gp));
   cudaStream_t st = gp->stream;
   const int64_t N = gp->N, rows = (int64_t)gp->NB * BM;
-  if (!(gp->kinv_dense_valid && gp->kinv_dense_N == N)) {
-    // dense K^-1 = Linv^T Linv (lower triangle), O(N^3) on the DMMA pipe: once per full cache refresh; appends grow it in
-    // O(m N^2) (finish_cache / fac::kinv_grow_kernel)
-    TB_TRY(gp->dKinv.reserve(sizeof(double) * N * N));
-    if (gp->factor_own) {
-      const unsigned t = (unsigned)((N + fac::FB - 1) / fac::FB);
-      fac::kinv_kernel<<<dim3(t, t), fac::THREADS, fac::GEMM_SMEM, st>>>(gp->dLinv.as<double>(), gp->dKinv.as<double>(), N);
-      TB_LAUNCHED();
-    } else {
-      TB_TRY(ensure_library_handles(gp));
-      TB_CUDA(cudaMemcpyAsync(gp->dKinv.p, gp->dL.p, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, st));
-      int lwork = 0;
-      cusolverStatus_t cs = cusolverDnDpotri_bufferSize(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, &lwork);
-      TB_CHECK_CODE(cs == CUSOLVER_STATUS_SUCCESS, "cusolverDnDpotri_bufferSize failed", tb::ERR_RUNTIME);
-      TB_TRY(gp->dWork.reserve(sizeof(double) * (size_t)std::max(lwork, 1)));
-      cs = cusolverDnDpotri(gp->cusolver, CUBLAS_FILL_MODE_LOWER, (int)N, gp->dKinv.as<double>(), (int)N, gp->dWork.as<double>(), lwork,
-                            gp->dInfo.as<int>());
-      TB_CHECK_CODE(cs == CUSOLVER_STATUS_SUCCESS, "cusolverDnDpotri failed", tb::ERR_RUNTIME);
-    }
-    gp->kinv_dense_valid = true;
-    gp->kinv_dense_N = N;
-  }
+  TB_TRY(ensure_kinv_dense(gp));
   TB_TRY(gp->dKinvScale.reserve(sizeof(double) * rows));
   oz::sym_rowscale_kernel<<<(unsigned)rows, 256, 0, st>>>(gp->dKinv.as<double>(), N, rows, gp->dKinvScale.as<double>());
   TB_LAUNCHED();
@@ -1107,11 +1115,137 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
   return 0;
 }
 
+// Can the joint / gradient paths of this handle run on the single-pass engine (ozaki5.cuh)?  Needs an admitted variance mode;
+// the gradient path also needs the V GEMM's own admission (oz5_ensure_kinv).
+static int oz5_store_ready(tb_gp* gp, bool need_kinv, bool* ok) {
+  *ok = false;
+  if (!(gp->engine == 1 && gp->N <= 16384)) return 0;
+  TB_TRY(oz5_ensure(gp));
+  if (gp->oz5_planes == 0) return 0;
+  if (need_kinv) {
+    TB_TRY(ensure_kinv_dense(gp));
+    TB_TRY(oz5_ensure_kinv(gp));
+    if (!gp->kinv5_ok) return 0;
+  }
+  *ok = true;
+  return 0;
+}
+static inline int oz5_groups(const tb_gp* gp, int tiles) {  // row-block groups per candidate tile: >= 2 items per SM
+  return std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
+}
+
+// value + gradient on the single-pass engine: K* digits -> variance GEMM (sum of squares) -> V = K^-1 k* (store GEMM over the
+// same K* digits, dense left factor) -> gradient assembly -> tail
+static int run_eval_grad_oz5(tb_gp* gp, EvalRequest& rq) {
+  TB_CUDA(cudaSetDevice(gp->device));
+  cudaStream_t st = gp->stream;
+  const int D = gp->D;
+  if (rq.want_argmax) {
+    TB_CHECK(rq.M > 0, "argmax over an empty candidate set");
+    TB_TRY(gp->sRun.reserve(16));
+    double init_v = -INFINITY;
+    int64_t init_i = INT64_MAX;
+    TB_CUDA(cudaMemcpyAsync(gp->sRun.p, &init_v, 8, cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaMemcpyAsync((char*)gp->sRun.p + 8, &init_i, 8, cudaMemcpyHostToDevice, st));
+  }
+  if (rq.M == 0) return 0;
+  TB_CHECK(rq.acq >= 0, "gradients need an acquisition kind");
+  const int nt = oz5_tile_width(gp);
+  const size_t per_tile = oz5_tile_bytes(gp);
+  const int64_t ldv = (int64_t)gp->NB * BM;
+  // scratch per chunk: K* digits + V (ldv doubles per candidate): bound both at ~1.3 GB
+  int64_t max_tiles = std::max<int64_t>(1, (int64_t)(((size_t)1280 << 20) / std::max(per_tile, (size_t)nt * ldv * sizeof(double))));
+  if (max_tiles >= 148) max_tiles = (max_tiles / 148) * 148;
+  const int64_t chunk_cap = std::min<int64_t>(max_tiles * nt, ((rq.M + nt - 1) / nt) * nt);
+  const int64_t tiles_cap = chunk_cap / nt;
+  const bool xc_dev = is_device_ptr(rq.Xc);
+  const bool vals_dev = is_device_ptr(rq.out_vals), mean_dev = is_device_ptr(rq.out_mean), var_dev = is_device_ptr(rq.out_var);
+  const bool gdev = is_device_ptr(rq.out_grad);
+  const int Gcap = gp->NB;
+  TB_TRY(gp->sKs.reserve((size_t)tiles_cap * per_tile));
+  TB_TRY(gp->sPartial.reserve(sizeof(double) * (size_t)Gcap * chunk_cap));
+  TB_TRY(gp->sMean.reserve(sizeof(double) * chunk_cap));
+  TB_TRY(gp->sV.reserve((size_t)chunk_cap * ldv * sizeof(double)));
+  TB_TRY(gp->sMisc.reserve(sizeof(double) * 2 * chunk_cap));
+  if (!xc_dev) TB_TRY(gp->sXc.reserve(sizeof(double) * chunk_cap * D));
+  if (rq.out_vals && !vals_dev) TB_TRY(gp->sVals.reserve(sizeof(double) * chunk_cap));
+  if (rq.out_var && !var_dev) TB_TRY(gp->sVar.reserve(sizeof(double) * chunk_cap));
+  if (!gdev) TB_TRY(gp->sGrad.reserve(sizeof(double) * chunk_cap * D));
+  const int tail_blocks_cap = (int)((chunk_cap + 255) / 256);
+  if (rq.want_argmax) {
+    TB_TRY(gp->sBlkBest.reserve(sizeof(double) * tail_blocks_cap));
+    TB_TRY(gp->sBlkIdx.reserve(sizeof(int64_t) * tail_blocks_cap));
+  }
+  for (int64_t c0 = 0; c0 < rq.M; c0 += chunk_cap) {
+    const int64_t mc = std::min<int64_t>(chunk_cap, rq.M - c0);
+    const int tiles = (int)((mc + nt - 1) / nt);
+    const int64_t McPad = (int64_t)tiles * nt;
+    const int G = oz5_groups(gp, tiles);
+    const double* xc_chunk;
+    if (xc_dev) {
+      xc_chunk = rq.Xc + c0 * D;
+    } else {
+      TB_CUDA(cudaMemcpyAsync(gp->sXc.p, rq.Xc + c0 * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, st));
+      xc_chunk = gp->sXc.as<double>();
+    }
+    TB_TRY(oz5_launch_kstar(gp, st, xc_chunk, mc, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
+    TB_TRY(oz5_launch_gemm(gp, st, gp->sKs.as<int8_t>(), tiles, G, McPad, gp->sPartial.as<double>()));
+    double* cmu = gp->sMisc.as<double>();
+    acq_partials_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, st>>>(gp->sPartial.as<double>(), G, McPad, gp->sMean.as<double>(), mc,
+                                                                      gp->variance, rq.acq, rq.param, gp->noise, gp->dMes.as<double>(), gp->mesS,
+                                                                      cmu, cmu + mc);
+    TB_LAUNCHED();
+    TB_TRY(oz5_launch_gemm_store(gp, st, 1, gp->sKs.as<int8_t>(), tiles, G, gp->sV.as<double>(), ldv));
+    double* gd = gdev ? rq.out_grad + c0 * D : gp->sGrad.as<double>();
+    switch (gp->kernel) {
+      case TB_RBF: launch_grad_dp<TB_RBF>(gp, xc_chunk, mc, gd); break;
+      case TB_MATERN12: launch_grad_dp<TB_MATERN12>(gp, xc_chunk, mc, gd); break;
+      case TB_MATERN32: launch_grad_dp<TB_MATERN32>(gp, xc_chunk, mc, gd); break;
+      default: launch_grad_dp<TB_MATERN52>(gp, xc_chunk, mc, gd); break;
+    }
+    TB_LAUNCHED();
+    TB_CUDA(cudaGetLastError());
+    if (!gdev) TB_CUDA(cudaMemcpyAsync(rq.out_grad + c0 * D, gd, sizeof(double) * mc * D, cudaMemcpyDeviceToHost, st));
+    double* d_vals = rq.out_vals ? (vals_dev ? rq.out_vals + c0 : gp->sVals.as<double>()) : nullptr;
+    double* d_mean = rq.out_mean ? (mean_dev ? rq.out_mean + c0 : nullptr) : nullptr;
+    double* d_var = rq.out_var ? (var_dev ? rq.out_var + c0 : gp->sVar.as<double>()) : nullptr;
+    const int tb_blocks = (int)((mc + 255) / 256);
+    tail_kernel<<<tb_blocks, 256, 0, st>>>(gp->sPartial.as<double>(), G, McPad, gp->sMean.as<double>(), mc, c0, gp->variance, rq.acq,
+                                           rq.param, gp->noise, gp->dMes.as<double>(), gp->mesS, d_vals, d_mean, d_var,
+                                           rq.want_argmax ? gp->sBlkBest.as<double>() : nullptr,
+                                           rq.want_argmax ? gp->sBlkIdx.as<int64_t>() : nullptr);
+    TB_LAUNCHED();
+    if (rq.want_argmax) {
+      argmax_fold_kernel<<<1, 256, 0, st>>>(gp->sBlkBest.as<double>(), gp->sBlkIdx.as<int64_t>(), tb_blocks, gp->sRun.as<double>(),
+                                            reinterpret_cast<int64_t*>((char*)gp->sRun.p + 8));
+      TB_LAUNCHED();
+    }
+    if (rq.out_vals && !vals_dev) TB_CUDA(cudaMemcpyAsync(rq.out_vals + c0, gp->sVals.p, sizeof(double) * mc, cudaMemcpyDeviceToHost, st));
+    if (rq.out_mean && !mean_dev) TB_CUDA(cudaMemcpyAsync(rq.out_mean + c0, gp->sMean.p, sizeof(double) * mc, cudaMemcpyDeviceToHost, st));
+    if (rq.out_var && !var_dev) TB_CUDA(cudaMemcpyAsync(rq.out_var + c0, gp->sVar.p, sizeof(double) * mc, cudaMemcpyDeviceToHost, st));
+    if (!xc_dev || (rq.out_vals && !vals_dev) || (rq.out_mean && !mean_dev) || (rq.out_var && !var_dev) || !gdev)
+      TB_CUDA(cudaStreamSynchronize(st));  // scratch is reused by the next chunk: host-staged copies must drain first
+  }
+  if (rq.want_argmax) {
+    TB_CUDA(cudaMemcpyAsync(&rq.best_value, gp->sRun.p, 8, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaMemcpyAsync(&rq.best_index, (char*)gp->sRun.p + 8, 8, cudaMemcpyDeviceToHost, st));
+  }
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int run_eval(tb_gp* gp, EvalRequest& rq) {
   TB_CHECK(gp->cache_valid, "posterior cache is not built: call tb_gp_update_posterior_cache first");
   TB_CHECK(rq.M >= 0, "negative candidate count");
   // int32 accumulators of the int8 engine are exact up to K = 16384; larger models use the native fp64 engine
   if (gp->engine == 1 && !rq.out_grad && gp->N <= 16384) return run_eval_oz(gp, rq);
+  if (rq.out_grad && rq.acq >= 0) {
+    bool fast = false;
+    TB_CUDA(cudaSetDevice(gp->device));
+    TB_TRY(oz5_store_ready(gp, true, &fast));
+    if (fast) return run_eval_grad_oz5(gp, rq);
+  }
   TB_CUDA(cudaSetDevice(gp->device));
   cudaStream_t st = gp->stream;
   const int D = gp->D;
@@ -1459,15 +1593,19 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
   int64_t nbc_cap = std::max<int64_t>(1, (max_tiles * BT) / q);  // whole batches per chunk
   nbc_cap = std::min<int64_t>(nbc_cap, rq.B);
   const int64_t cand_cap = nbc_cap * q;
-  const int64_t tiles_cap = (cand_cap + BT - 1) / BT;
   const bool oz_joint = gp->engine == 1 && gp->N <= 16384;
-  if (oz_joint) {
+  bool fast = false;  // single-pass engine (ozaki5.cuh) for A = Linv K*
+  TB_TRY(oz5_store_ready(gp, false, &fast));
+  const int nt = fast ? oz5_tile_width(gp) : BT;  // candidates per tile
+  const int64_t tiles_cap = (cand_cap + nt - 1) / nt;
+  if (oz_joint && !fast) {
     TB_TRY(ensure_ozaki(gp));
     TB_CUDA(cudaStreamSynchronize(st));
   }
-  TB_TRY(gp->sKs.reserve(std::max((size_t)tiles_cap * gp->nkc * PANEL * sizeof(double), (size_t)tiles_cap * gp->nst * oz::S * oz::TILE)));
-  TB_TRY(gp->sV.reserve((size_t)tiles_cap * BT * lda * sizeof(double)));  // A plain
-  TB_TRY(gp->sMean.reserve(sizeof(double) * tiles_cap * BT));
+  TB_TRY(gp->sKs.reserve(fast ? (size_t)tiles_cap * oz5_tile_bytes(gp)
+                              : std::max((size_t)tiles_cap * gp->nkc * PANEL * sizeof(double), (size_t)tiles_cap * gp->nst * oz::S * oz::TILE)));
+  TB_TRY(gp->sV.reserve((size_t)tiles_cap * nt * lda * sizeof(double)));  // A plain
+  TB_TRY(gp->sMean.reserve(sizeof(double) * tiles_cap * nt));
   const bool xc_dev = is_device_ptr(rq.Xc);
   if (!xc_dev) TB_TRY(gp->sXc.reserve(sizeof(double) * cand_cap * D));
   const double* eps_dev = nullptr;
@@ -1498,8 +1636,8 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
   for (int64_t b0 = 0; b0 < rq.B; b0 += nbc_cap) {
     const int64_t nbc = std::min<int64_t>(nbc_cap, rq.B - b0);
     const int64_t mc = nbc * q;
-    const int tiles = (int)((mc + BT - 1) / BT);
-    const int64_t McPad = (int64_t)tiles * BT;
+    const int tiles = (int)((mc + nt - 1) / nt);
+    const int64_t McPad = (int64_t)tiles * nt;
     const int G = pick_groups(gp, tiles);
     const double* xc_chunk;
     if (xc_dev) {
@@ -1508,7 +1646,11 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
       TB_CUDA(cudaMemcpyAsync(gp->sXc.p, rq.Xc + b0 * q * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, st));
       xc_chunk = gp->sXc.as<double>();
     }
-    if (oz_joint) {
+    if (fast) {
+      // A = Linv K* as 15 (fp32 models: 10) exact digit products in one pass, stored for the per-batch Gram kernel
+      TB_TRY(oz5_launch_kstar(gp, st, xc_chunk, mc, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
+      TB_TRY(oz5_launch_gemm_store(gp, st, 0, gp->sKs.as<int8_t>(), tiles, oz5_groups(gp, tiles), gp->sV.as<double>(), lda));
+    } else if (oz_joint) {
       // A = Linv K* on the int8 tensor cores (fp64-accurate digit GEMM), stored for the per-batch Gram kernel
       TB_TRY(launch_kstar_digits(gp, xc_chunk, mc, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
       const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
@@ -1556,13 +1698,22 @@ static int run_joint(tb_gp* gp, JointRequest& rq) {
 static int compute_a_plain(tb_gp* gp, const double* xc_dev, int64_t M) {
   cudaStream_t st = gp->stream;
   const int64_t lda = (int64_t)gp->NB * BM;
-  const int tiles = (int)((M + BT - 1) / BT);
-  const int64_t McPad = (int64_t)tiles * BT;
   const bool oz_path = gp->engine == 1 && gp->N <= 16384;
-  if (oz_path) TB_TRY(ensure_ozaki(gp));
-  TB_TRY(gp->sKs.reserve(std::max((size_t)tiles * gp->nkc * PANEL * sizeof(double), (size_t)tiles * gp->nst * oz::S * oz::TILE)));
+  bool fast = false;
+  TB_TRY(oz5_store_ready(gp, false, &fast));
+  const int nt = fast ? oz5_tile_width(gp) : BT;
+  const int tiles = (int)((M + nt - 1) / nt);
+  const int64_t McPad = (int64_t)tiles * nt;
+  if (oz_path && !fast) TB_TRY(ensure_ozaki(gp));
+  TB_TRY(gp->sKs.reserve(fast ? (size_t)tiles * oz5_tile_bytes(gp)
+                              : std::max((size_t)tiles * gp->nkc * PANEL * sizeof(double), (size_t)tiles * gp->nst * oz::S * oz::TILE)));
   TB_TRY(gp->sA.reserve((size_t)McPad * lda * sizeof(double)));
   TB_TRY(gp->sMean.reserve(sizeof(double) * McPad));
+  if (fast) {
+    TB_TRY(oz5_launch_kstar(gp, st, xc_dev, M, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
+    TB_TRY(oz5_launch_gemm_store(gp, st, 0, gp->sKs.as<int8_t>(), tiles, oz5_groups(gp, tiles), gp->sA.as<double>(), lda));
+    return 0;
+  }
   if (oz_path) {
     TB_TRY(launch_kstar_digits(gp, xc_dev, M, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
     const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
@@ -1805,7 +1956,11 @@ static int run_qei_grad(tb_gp* gp, const double* Xc, int64_t B, int q, const dou
   const int D = gp->D;
   const int QT = (q + 7) / 8, QP = QT * 8;
   const int64_t lda = (int64_t)gp->NB * BM;
-  if (oz_path) {
+  bool fast = false;  // single-pass engine for both store GEMMs (A = Linv K*, V = K^-1 K*)
+  if (oz_path) TB_TRY(oz5_store_ready(gp, true, &fast));
+  const int nt = fast ? oz5_tile_width(gp) : BT;
+  if (fast) {
+  } else if (oz_path) {
     TB_TRY(ensure_ozaki(gp));
     TB_TRY(ensure_kinv_digits(gp));
   } else {
@@ -1814,23 +1969,23 @@ static int run_qei_grad(tb_gp* gp, const double* Xc, int64_t B, int q, const dou
   const int64_t max_tiles = chunk_tiles(gp);
   int64_t nbc_cap = std::min<int64_t>(std::max<int64_t>(1, (max_tiles * BT) / q), B);
   const int64_t cand_cap = nbc_cap * q;
-  const int64_t tiles_cap = (cand_cap + BT - 1) / BT;
+  const int64_t tiles_cap = (cand_cap + nt - 1) / nt;
   tb::DevBuf baplain;  // fp64 engine: plain copy of A for the Gram kernel (sA holds the packed panels the upper GEMM reads)
   struct ReleaseA {
     tb::DevBuf* b;
     ~ReleaseA() { b->release(); }
   } rel_a{&baplain};
   if (oz_path) {
-    TB_TRY(gp->sKs.reserve((size_t)tiles_cap * gp->nst * oz::S * oz::TILE));
-    TB_TRY(gp->sA.reserve((size_t)tiles_cap * BT * lda * sizeof(double)));  // A plain
+    TB_TRY(gp->sKs.reserve(fast ? (size_t)tiles_cap * oz5_tile_bytes(gp) : (size_t)tiles_cap * gp->nst * oz::S * oz::TILE));
+    TB_TRY(gp->sA.reserve((size_t)tiles_cap * nt * lda * sizeof(double)));  // A plain
   } else {
     TB_TRY(gp->sKs.reserve((size_t)tiles_cap * gp->nkc * PANEL * sizeof(double)));
     TB_TRY(gp->sA.reserve((size_t)tiles_cap * gp->NB * (BM / BK) * PANEL * sizeof(double)));  // A packed
     TB_TRY(baplain.reserve((size_t)tiles_cap * BT * lda * sizeof(double)));
     TB_TRY(gp->sPartial.reserve(sizeof(double) * (size_t)gp->NB * tiles_cap * BT));
   }
-  TB_TRY(gp->sV.reserve((size_t)tiles_cap * BT * lda * sizeof(double)));  // V plain
-  TB_TRY(gp->sMean.reserve(sizeof(double) * tiles_cap * BT));
+  TB_TRY(gp->sV.reserve((size_t)tiles_cap * nt * lda * sizeof(double)));  // V plain
+  TB_TRY(gp->sMean.reserve(sizeof(double) * tiles_cap * nt));
   TB_TRY(gp->sMisc.reserve(sizeof(double) * 2 * cand_cap));  // c_mu, c_var
   const bool xc_dev = is_device_ptr(Xc), val_dev = is_device_ptr(out_val), grad_dev = is_device_ptr(out_grad);
   if (!xc_dev) TB_TRY(gp->sXc.reserve(sizeof(double) * cand_cap * D));
@@ -1863,8 +2018,8 @@ static int run_qei_grad(tb_gp* gp, const double* Xc, int64_t B, int q, const dou
   for (int64_t b0 = 0; b0 < B; b0 += nbc_cap) {
     const int64_t nbc = std::min<int64_t>(nbc_cap, B - b0);
     const int64_t mc = nbc * q;
-    const int tiles = (int)((mc + BT - 1) / BT);
-    const int64_t McPad = (int64_t)tiles * BT;
+    const int tiles = (int)((mc + nt - 1) / nt);
+    const int64_t McPad = (int64_t)tiles * nt;
     const double* xc_chunk;
     if (xc_dev) {
       xc_chunk = Xc + b0 * q * D;
@@ -1873,7 +2028,13 @@ static int run_qei_grad(tb_gp* gp, const double* Xc, int64_t B, int q, const dou
       xc_chunk = gp->sXc.as<double>();
     }
     const double* a_plain;
-    if (oz_path) {
+    if (fast) {
+      TB_TRY(oz5_launch_kstar(gp, st, xc_chunk, mc, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
+      const int Gs = oz5_groups(gp, tiles);
+      TB_TRY(oz5_launch_gemm_store(gp, st, 0, gp->sKs.as<int8_t>(), tiles, Gs, gp->sA.as<double>(), lda));
+      TB_TRY(oz5_launch_gemm_store(gp, st, 1, gp->sKs.as<int8_t>(), tiles, Gs, gp->sV.as<double>(), lda));
+      a_plain = gp->sA.as<double>();
+    } else if (oz_path) {
       TB_TRY(launch_kstar_digits(gp, xc_chunk, mc, tiles, gp->sKs.as<int8_t>(), gp->sMean.as<double>()));
       const int Goz = std::max(std::max(1, (gp->NB + 3) / 4), std::min(gp->NB, (2 * 148 + tiles - 1) / tiles));
       oz::trigemm_i8_kernel<oz::OZ_STORE, 8><<<dim3(Goz, tiles), 10 * 32, oz::SMEM_BYTES, st>>>(
