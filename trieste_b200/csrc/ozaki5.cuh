@@ -221,7 +221,7 @@ __global__ void sym_digits_kernel(const double* __restrict__ A, int64_t N, int n
 // ------------------------------------------------------------------------------------------------
 constexpr int KGEN_WARPS = 8;
 template <int KIND, int DP, int S>
-__global__ void __launch_bounds__(KGEN_WARPS * 32, 4)  // 64 registers (a few bytes of spill), 32 warps per SM
+__global__ void __launch_bounds__(KGEN_WARPS * 32, DP <= 12 ? 4 : 3)  // 64 registers / 32 warps per SM (80 / 24 for D > 12: no spills)
 kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ X2, const double* __restrict__ alpha,
                     const double* __restrict__ Xc, const double* __restrict__ inv_ls, int N, int nst, int D, int64_t M, double variance,
                     double inv_bscale_2p, double dig_c, double mean_const, const __grid_constant__ fm::Consts fc, int ntiles,
