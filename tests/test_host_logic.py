@@ -388,3 +388,39 @@ def test_conditional_predict_host_algebra_reproduces_an_updated_model():
         np.testing.assert_allclose(v2[1], var, rtol=1e-12, atol=1e-15)
     with pytest.raises(ValueError):
         f.conditional_predict_f(Xq[None], add)
+
+
+def test_qmc_base_samples_and_skip_counter():
+    # models/gpflow/sampler.py:53-79, 90-117, 239-254: Sobol base samples through the normal quantile; successive samplers with
+    # qmc_skip=True take disjoint blocks of the sequence; no point is the origin (its quantile would be -inf)
+    from trieste_b200.sampler import (BatchReparametrizationSampler, IndependentReparametrizationSampler,
+                                      qmc_normal_samples)
+
+    x = qmc_normal_samples(1024, 3)
+    assert x.shape == (1024, 3) and np.all(np.isfinite(x))
+    assert np.abs(x.mean(0)).max() < 0.01 and np.abs(x.std(0) - 1).max() < 0.01  # far tighter than 1024 random draws
+    np.testing.assert_array_equal(qmc_normal_samples(8, 2)[4:], qmc_normal_samples(4, 2, skip=4))
+    assert qmc_normal_samples(0, 3).shape == (0, 3) and qmc_normal_samples(5, 0).shape == (5, 0)
+
+    class Model:  # predict / predict_joint of a unit Gaussian: the samplers' host arithmetic is what is under test
+        def predict(self, x):
+            return np.zeros(x.shape[:-1] + (1,)), np.ones(x.shape[:-1] + (1,))
+
+        def predict_joint(self, x):
+            q = x.shape[-2]
+            return np.zeros(x.shape[:-1] + (1,)), np.broadcast_to(np.eye(q), x.shape[:-2] + (1, q, q)).copy()
+
+    IndependentReparametrizationSampler.skip = 0
+    s1 = IndependentReparametrizationSampler(16, Model(), qmc=True)
+    a = s1.sample(np.zeros((1, 1, 2)), jitter=0.0)[0, :, 0, 0]
+    s2 = IndependentReparametrizationSampler(16, Model(), qmc=True)
+    b = s2.sample(np.zeros((1, 1, 2)), jitter=0.0)[0, :, 0, 0]
+    assert IndependentReparametrizationSampler.skip == 32
+    np.testing.assert_allclose(np.concatenate([a, b]), qmc_normal_samples(32, 1)[:, 0])
+    s3 = IndependentReparametrizationSampler(16, Model(), qmc=True, qmc_skip=False)
+    np.testing.assert_allclose(s3.sample(np.zeros((1, 1, 2)), jitter=0.0)[0, :, 0, 0], a)
+    np.testing.assert_allclose(s1.sample(np.zeros((1, 1, 2)), jitter=0.0)[0, :, 0, 0], a)  # fixed until reset
+    sb = BatchReparametrizationSampler(8, Model(), qmc=True)
+    eps = sb._get_eps(3)
+    assert eps.shape == (3, 8) and IndependentReparametrizationSampler.skip == 40
+    np.testing.assert_allclose(eps.T, qmc_normal_samples(8, 3, skip=32))

@@ -23,6 +23,18 @@ int main() {
     const double es = (double)fabsl(((long double)gs - rs) / rs);
     if (es > worst_s) { worst_s = es; at_s = x; }
   }
+  const tb::fm::TrigConsts TC;
+  double worst_c = 0, at_c = 0;
+  for (int i = 0; i < 20000000; ++i) {
+    const double r = u(rng);
+    const double a = (i % 2 ? 60.0 : 3000.0) * (2.0 * r - 1.0);
+    const double got = tb::fm::cos_fast(a, TC);
+    const double err = (double)fabsl((long double)got - cosl((long double)a));
+    if (err > worst_c) { worst_c = err; at_c = a; }
+  }
+  printf("cos_fast: max ABS err %.3e at a = %.17g; cos_fast(0) = %.17g, cos_fast(pi) = %.17g\n", worst_c, at_c, tb::fm::cos_fast(0.0, TC),
+         tb::fm::cos_fast(3.141592653589793, TC));
+  if (worst_c > 1e-13) return 1;
   printf("exp_neg: max rel err %.3e at s = %.17g\nsqrt_pos: max rel err %.3e at x = %.17g\n", worst_e, at_e, worst_s, at_s);
   printf("exp_neg(0) = %.17g, exp_neg(1e-17) = %.17g, exp_neg(800) = %.3e, exp_neg(1e4) = %.3e\n", tb::fm::exp_neg(0.0, tb::fm::EXP2_TABLE_HOST, C),
          tb::fm::exp_neg(1e-17, tb::fm::EXP2_TABLE_HOST, C), tb::fm::exp_neg(800.0, tb::fm::EXP2_TABLE_HOST, C), tb::fm::exp_neg(1e4, tb::fm::EXP2_TABLE_HOST, C));

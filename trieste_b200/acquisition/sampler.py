@@ -58,6 +58,9 @@ class ThompsonSamplerFromTrajectory(ThompsonSampler):
             raise ValueError(
                 f"Thompson sampling from trajectory only supports models with a trajectory_sampler method; received {model!r}"
             )
+        # The reference calls ``trajectory_sampler.get_trajectory()`` once per sample (sampler.py:262-263); every such call
+        # shares the SAMPLER's feature functions (W, b drawn once in its __init__, models/gpflow/sampler.py:375, 398-400) and
+        # draws fresh weights.  ``resample_trajectory`` does exactly that on one trajectory object without re-uploading W, b.
         trajectory_sampler = model.trajectory_sampler()
         trajectory = trajectory_sampler.get_trajectory()
         picked = []

@@ -134,5 +134,38 @@ TB_FM_HD double sqrt_pos(double x) {
   return fma(d, h, g);
 }
 
+// cos(a) for |a| < ~1e6 (the random-Fourier-feature arguments w.x + b): cos(a) = sin(a + pi/2) = (-1)^k sin(r) with
+// k = rint(a / pi + 1/2), r = a - (2k - 1) pi/2 in [-pi/2, pi/2] (three-term Cody-Waite, the odd multiple m = 2k - 1 times each
+// 33-bit part of pi/2 is exact for |m| < 2^20), sin(r) by its Taylor polynomial through r^19 (remainder < 3e-16; max absolute error
+// measured by tools/fastmath_check.cu: 4e-16).  ncu: the library cos() left rff_eval_kernel issue-bound
+// (issue 77 %, fp64 pipe 48 %) on its slow-path branches and constant traffic.
+struct TrigConsts {
+  double inv_pi = 0x1.45f306dc9c883p-2;
+  double pio2_hi = 0x1.921fb54400000p+0, pio2_mid = 0x1.0b4611a600000p-34, pio2_lo = 0x1.3198a2e037073p-69;
+  double s3 = -0x1.5555555555555p-3, s5 = 0x1.1111111111111p-7, s7 = -0x1.a01a01a01a01ap-13, s9 = 0x1.71de3a556c734p-19;
+  double s11 = -0x1.ae64567f544e4p-26, s13 = 0x1.6124613a86d09p-33, s15 = -0x1.ae7f3e733b81fp-41, s17 = 0x1.952c77030ad4ap-49;
+  double s19 = -0x1.2f49b46814157p-57;
+};
+
+TB_FM_HD double cos_fast(double a, const TrigConsts& c) {
+  const double t = fma(a, c.inv_pi, 0.5) + MAGIC;  // low word = k = rint(a / pi + 1/2)  (MAGIC + 0.5 is not representable)
+  const int k = lo_word(t);
+  const double m = fma(2.0, t - MAGIC, -1.0);      // 2k - 1 (exact)
+  double r = fma(m, -c.pio2_hi, a);
+  r = fma(m, -c.pio2_mid, r);
+  r = fma(m, -c.pio2_lo, r);
+  const double r2 = r * r;
+  double p = fma(c.s19, r2, c.s17);
+  p = fma(p, r2, c.s15);
+  p = fma(p, r2, c.s13);
+  p = fma(p, r2, c.s11);
+  p = fma(p, r2, c.s9);
+  p = fma(p, r2, c.s7);
+  p = fma(p, r2, c.s5);
+  p = fma(p, r2, c.s3);
+  const double sr = fma(p * r2, r, r);  // sin(r)
+  return with_hi_word(sr, hi_word(sr) ^ (k << 31));  // (-1)^k
+}
+
 }  // namespace fm
 }  // namespace tb

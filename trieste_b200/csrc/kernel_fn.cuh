@@ -40,6 +40,19 @@ __device__ __forceinline__ double kernel_from_r2_fast(double r2, double variance
   return variance * fma(s2, c.third, 1.0 + s) * fm::exp_neg(s, T, c);
 }
 
+template <int KIND>
+__device__ __forceinline__ double kernel_dr2_fast(double r2, double variance, const double* T, const fm::Consts& c) {
+  if (KIND == TB_RBF) return -0.5 * variance * fm::exp_neg(0.5 * fm::clamp_below(r2, 0.0), T, c);
+  const double q = fm::clamp_below(r2, 1e-36);
+  if (KIND == TB_MATERN12) {
+    const double r = fm::sqrt_pos(q);
+    return -variance * fm::exp_neg(r, T, c) / (2.0 * r);
+  }
+  if (KIND == TB_MATERN32) return -1.5 * variance * fm::exp_neg(fm::sqrt_pos(3.0 * q), T, c);
+  const double s = fm::sqrt_pos(5.0 * q);
+  return -(5.0 / 6.0) * variance * (1.0 + s) * fm::exp_neg(s, T, c);
+}
+
 // dk/d(r2) (for gradients w.r.t. x*: dk/dx*_d = dk/dr2 * 2 (x*_d - x_d) / l_d^2)
 template <int KIND>
 __device__ __forceinline__ double kernel_dr2(double r2, double variance) {

@@ -341,7 +341,10 @@ __global__ void __launch_bounds__(256)
 grad_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha, const double* __restrict__ Xc,
             const double* __restrict__ inv_ls, int N, int D, int64_t Mc, const double* __restrict__ Vplain,
             int64_t ldv, const double* __restrict__ cmu, const double* __restrict__ cvar, double variance,
-            double* __restrict__ grad) {
+            const __grid_constant__ fm::Consts fc, double* __restrict__ grad) {
+  __shared__ double exp_tab[64];  // 2^(j/64) for the branch-free exp of fastmath.cuh
+  if (threadIdx.x < 64) exp_tab[threadIdx.x] = fm::EXP2_TABLE_DEV[threadIdx.x];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= Mc) return;
@@ -364,7 +367,7 @@ grad_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha, con
       r2 = fma(diff[d], diff[d], r2);
       r2 = fma(diff[d + 1], diff[d + 1], r2);
     }
-    const double w = 2.0 * kernel_dr2<KIND>(r2, variance) * fma(cm, __ldg(alpha + k), cv * v[k]);
+    const double w = 2.0 * kernel_dr2_fast<KIND>(r2, variance, exp_tab, fc) * fma(cm, __ldg(alpha + k), cv * v[k]);
 #pragma unroll
     for (int d = 0; d < DP; ++d) g[d] = fma(w, diff[d], g[d]);
   }
@@ -411,7 +414,8 @@ rff_eval_kernel(const double* __restrict__ Wp,     // [F][DP] (zero padded)
                 const double* __restrict__ theta,  // [nb][F]
                 const double* __restrict__ Xc, const double* __restrict__ inv_ls, int D, int F, int nb,
                 int b0, int64_t M, int64_t idx0, double scale, double mean_const, const double* __restrict__ addend,
-                double* __restrict__ out, double* __restrict__ blk_best, int64_t* __restrict__ blk_idx) {
+                const __grid_constant__ fm::TrigConsts tc, double* __restrict__ out, double* __restrict__ blk_best,
+                int64_t* __restrict__ blk_idx) {
   extern __shared__ __align__(16) unsigned char rsm[];
   double* sW = reinterpret_cast<double*>(rsm);   // [RFF_FCHUNK][DP]
   double* sb = sW + RFF_FCHUNK * DP;             // [RFF_FCHUNK]
@@ -442,7 +446,7 @@ rff_eval_kernel(const double* __restrict__ Wp,     // [F][DP] (zero padded)
         a = fma(w.x, x[d], a);
         a = fma(w.y, x[d + 1], a);
       }
-      const double c = cos(a);
+      const double c = fm::cos_fast(a, tc);  // branch-free, constants from the constant bank (fastmath.cuh)
 #pragma unroll
       for (int b = 0; b < NBT; ++b) acc[b] = fma(sth[b * RFF_FCHUNK + f], c, acc[b]);
     }
@@ -485,7 +489,10 @@ template <int KIND, int DP, int NBT>
 __global__ void __launch_bounds__(256)
 kdot_kernel(const double* __restrict__ Xs, const double* __restrict__ V, int64_t ldv, const double* __restrict__ Xc,
             const double* __restrict__ inv_ls, int N, int D, int nb, int b0, int64_t M, double variance,
-            double* __restrict__ out) {
+            const __grid_constant__ fm::Consts fc, double* __restrict__ out) {
+  __shared__ double exp_tab[64];
+  if (threadIdx.x < 64) exp_tab[threadIdx.x] = fm::EXP2_TABLE_DEV[threadIdx.x];
+  __syncthreads();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = t < M;
   double x[DP], acc[NBT];
@@ -503,7 +510,7 @@ kdot_kernel(const double* __restrict__ Xs, const double* __restrict__ V, int64_t
       r2 = fma(d0, d0, r2);
       r2 = fma(d1, d1, r2);
     }
-    const double kv = kernel_from_r2<KIND>(r2, variance);
+    const double kv = kernel_from_r2_fast<KIND>(r2, variance, exp_tab, fc);
 #pragma unroll
     for (int b = 0; b < NBT; ++b)
       if (b0 + b < nb) acc[b] = fma(kv, __ldg(V + (int64_t)(b0 + b) * ldv + k), acc[b]);

@@ -758,7 +758,7 @@ static void launch_grad_dp(tb_gp* gp, const double* xc, int64_t mc, double* grad
   const double* cmu = gp->sMisc.as<double>();
   const double* cvar = cmu + mc;
 #define TB_GRAD(DPV) \
-  grad_kernel<KIND, DPV><<<blocks, 256, 0, gp->stream>>>(Xs, al, xc, il, (int)gp->N, gp->D, mc, V, ldv, cmu, cvar, gp->variance, grad_dev)
+  grad_kernel<KIND, DPV><<<blocks, 256, 0, gp->stream>>>(Xs, al, xc, il, (int)gp->N, gp->D, mc, V, ldv, cmu, cvar, gp->variance, fm::Consts(), grad_dev)
   switch (gp->DP) {
     case 2: TB_GRAD(2); break;
     case 4: TB_GRAD(4); break;
@@ -2308,12 +2308,13 @@ static int launch_rff(tb_rff* r, int nbt, int blocks, const double* xc, int b0, 
     TB_CUDA(cudaFuncSetAttribute(rff_eval_kernel<DP, NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     rff_eval_kernel<DP, NBT><<<blocks, RFF_THREADS, smem, r->stream>>>(r->dW.as<double>(), r->dB.as<double>(),      \
         r->dTheta.as<double>(), xc, r->dInvLs.as<double>(), r->D, r->F, r->nb, b0, mc, idx0, scale, r->mean_const,  \
-        addend, out, bb, bi);                                                                                             \
+        addend, fm::TrigConsts(), out, bb, bi);                                                                          \
   }
   switch (nbt) {
     case 1: TB_RFF(1); break;
     case 2: TB_RFF(2); break;
-    default: TB_RFF(4); break;
+    case 4: TB_RFF(4); break;
+    default: TB_RFF(8); break;
   }
 #undef TB_RFF
   TB_LAUNCHED();
@@ -2330,13 +2331,13 @@ static void launch_kdot_nbt(tb_rff* r, const double* xc, int64_t mc, double* out
     const int rem = r->nbc - b0;
     if (rem >= 3)
       kdot_kernel<KIND, DP, 4><<<blocks, 256, 0, r->stream>>>(r->dXs.as<double>(), r->dV.as<double>(), r->N, xc, r->dInvLs.as<double>(),
-                                                            (int)r->N, r->D, r->nbc, b0, mc, r->variance, out);
+                                                            (int)r->N, r->D, r->nbc, b0, mc, r->variance, fm::Consts(), out);
     else if (rem == 2)
       kdot_kernel<KIND, DP, 2><<<blocks, 256, 0, r->stream>>>(r->dXs.as<double>(), r->dV.as<double>(), r->N, xc, r->dInvLs.as<double>(),
-                                                            (int)r->N, r->D, r->nbc, b0, mc, r->variance, out);
+                                                            (int)r->N, r->D, r->nbc, b0, mc, r->variance, fm::Consts(), out);
     else
       kdot_kernel<KIND, DP, 1><<<blocks, 256, 0, r->stream>>>(r->dXs.as<double>(), r->dV.as<double>(), r->N, xc, r->dInvLs.as<double>(),
-                                                            (int)r->N, r->D, r->nbc, b0, mc, r->variance, out);
+                                                            (int)r->N, r->D, r->nbc, b0, mc, r->variance, fm::Consts(), out);
     TB_LAUNCHED();
   }
 }
@@ -2443,9 +2444,9 @@ int tb_rff_eval(tb_rff* r, const void* Xc, int64_t M, void* out, double* min_val
       TB_TRY(tb::launch_kdot(r, xc, mc, r->sCanon.as<double>()));
       addend = r->sCanon.as<double>();
     }
-    for (int b0 = 0; b0 < nb; b0 += 4) {
+    for (int b0 = 0, nbt = 0; b0 < nb; b0 += nbt) {
       const int rem = nb - b0;
-      const int nbt = rem >= 3 ? 4 : rem;  // kernel handles up to nbt trajectories per pass
+      nbt = rem >= 5 ? 8 : rem >= 3 ? 4 : rem;  // trajectories per pass: the cosine of a feature is shared by all of them
       double* bb = want_min ? r->sBlkBest.as<double>() : nullptr;
       int64_t* bi = want_min ? r->sBlkIdx.as<int64_t>() : nullptr;
 #define TB_RFF_DP(DPV) TB_TRY((tb::launch_rff<DPV>(r, nbt, blocks, xc, b0, mc, c0, scale, addend, od, bb, bi)))

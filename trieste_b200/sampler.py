@@ -27,17 +27,38 @@ def _reparam_sample(model: GaussianProcessRegression, at, eps: np.ndarray, jitte
     return out.reshape(lead + (S, q, 1))
 
 
+def qmc_normal_samples(num_samples: int, n_sample_dim: int, skip: int = 0, dtype=np.float64) -> np.ndarray:
+    """sampler.py:53-79: ``num_samples`` points of the (unscrambled, Joe-Kuo) Sobol sequence in ``n_sample_dim`` dimensions,
+    skipping the first ``skip``, mapped through the standard normal quantile.  ``tf.math.sobol_sample`` never returns the
+    origin (its quantile would be -inf), so the sequence starts at the first non-zero point; SciPy's generator uses the same
+    direction numbers and Gray-code order.  The exact point order of TensorFlow's kernel cannot be checked here (parity
+    unpinned); what the samplers rely on — low-discrepancy, deterministic, disjoint blocks for successive ``skip`` values —
+    holds by construction."""
+    if num_samples == 0 or n_sample_dim == 0:
+        return np.zeros((num_samples, n_sample_dim), dtype=dtype)
+    from scipy.special import ndtri
+    from scipy.stats import qmc
+
+    gen = qmc.Sobol(d=int(n_sample_dim), scramble=False)
+    gen.fast_forward(int(skip) + 1)  # + 1: never the origin
+    return ndtri(gen.random(int(num_samples))).astype(dtype)
+
+
 class IndependentReparametrizationSampler:
     """sampler.py:82-164: ``x -> mu(x) + eps * sigma(x)`` with base samples eps [S, 1] fixed until
     :meth:`reset_sampler`; batch size one only.  One batched GPU ``predict`` per call; the S-fold broadcast is host
-    arithmetic on the [..., 1] outputs (the reference's ``qmc=True`` Sobol option is not provided — draws are from a
-    NumPy generator or injected with :meth:`set_eps`)."""
+    arithmetic on the [..., 1] outputs.  ``qmc=True`` draws the base samples from the Sobol sequence (:func:`qmc_normal_samples`);
+    ``qmc_skip`` advances the class-wide ``skip`` counter so that different samplers use different points (:90-117)."""
 
-    def __init__(self, sample_size: int, model, seed: Optional[int] = None):
+    skip: int = 0  # number of Sobol points already handed out (sampler.py:93-94: shared by both sampler classes)
+
+    def __init__(self, sample_size: int, model, qmc: bool = False, qmc_skip: bool = True, seed: Optional[int] = None):
         if sample_size <= 0:
             raise ValueError(f"sample_size must be positive, got {sample_size}")
         self._sample_size = sample_size
         self._model = model
+        self._qmc = qmc
+        self._qmc_skip = qmc_skip
         self._rng = np.random.default_rng(seed)
         self._eps: Optional[np.ndarray] = None  # [S, 1]
         self._initialized = False
@@ -60,7 +81,14 @@ class IndependentReparametrizationSampler:
         mean, var = self._model.predict(x[..., None, :, :])  # [..., 1, 1, 1]
         mean, var = np.asarray(mean, dtype=np.float64), np.asarray(var, dtype=np.float64)
         if not self._initialized or self._eps is None:
-            self._eps = self._rng.standard_normal((self._sample_size, 1))
+            if self._qmc:  # sampler.py:140-148
+                skip = 0
+                if self._qmc_skip:
+                    skip = IndependentReparametrizationSampler.skip
+                    IndependentReparametrizationSampler.skip = skip + self._sample_size
+                self._eps = qmc_normal_samples(self._sample_size, 1, skip)
+            else:
+                self._eps = self._rng.standard_normal((self._sample_size, 1))
             self._initialized = True
         return mean + np.sqrt(var + jitter) * self._eps[:, None, :]  # [..., S, 1, 1]
 
@@ -73,13 +101,16 @@ class BatchReparametrizationSampler:
     the reference uses tf.random.normal; RNG streams are never bit-compatible, so ``eps`` can also be
     injected with :meth:`set_eps`) and stay fixed until :meth:`reset_sampler`."""
 
-    def __init__(self, sample_size: int, model: GaussianProcessRegression, seed: Optional[int] = None):
+    def __init__(self, sample_size: int, model: GaussianProcessRegression, qmc: bool = False, qmc_skip: bool = True,
+                 seed: Optional[int] = None):
         if sample_size <= 0:
             raise ValueError(f"sample_size must be positive, got {sample_size}")
         if not hasattr(model, "predict_joint"):
             raise ValueError(f"BatchReparametrizationSampler only works with models that support predict_joint; received {model!r}")
         self._sample_size = sample_size
         self._model = model
+        self._qmc = qmc
+        self._qmc_skip = qmc_skip
         self._rng = np.random.default_rng(seed)
         self._eps: Optional[np.ndarray] = None  # [q, S]
         self._initialized = False
@@ -97,7 +128,14 @@ class BatchReparametrizationSampler:
         if batch_size <= 0:
             raise ValueError("batch size must be positive")
         if not self._initialized or self._eps is None:
-            self._eps = self._rng.standard_normal((batch_size, self._sample_size))
+            if self._qmc:  # sampler.py:241-254: S points in batch_size dimensions, stored [q, S]
+                skip = 0
+                if self._qmc_skip:
+                    skip = IndependentReparametrizationSampler.skip
+                    IndependentReparametrizationSampler.skip = skip + self._sample_size
+                self._eps = np.ascontiguousarray(qmc_normal_samples(self._sample_size, batch_size, skip).T)
+            else:
+                self._eps = self._rng.standard_normal((batch_size, self._sample_size))
             self._initialized = True
         if self._eps.shape[0] != batch_size:
             raise ValueError(
