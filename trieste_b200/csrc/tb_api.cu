@@ -985,11 +985,13 @@ static int run_eval_oz(tb_gp* gp, EvalRequest& rq) {
   // half the usual scratch budget per slot (two slots are live)
   const size_t per_tile = fast ? oz5_tile_bytes(gp) : (size_t)gp->nst * oz::S * oz::TILE;
   int64_t max_tiles = std::max<int64_t>(1, (int64_t)(((size_t)1280 << 20) / per_tile));
-  // whole waves for both kernels of a chunk: the generation kernel runs 2 CTAs per SM (one per tile), the GEMM one CTA per SM
-  // and G per tile (ncu: 444 tiles left the generation kernel with a half-empty second wave)
+  // chunks of whole GEMM rounds (148 CTAs, G items per tile).  The generation kernel of the single-pass engine runs 1.5 CTAs per
+  // tile, 4 resident per SM, so 592 tiles are 1.5 of its waves; chunks of 789 / 1184 tiles (2 / 3 whole waves) were measured
+  // on B200 and change the step by < 0.2 % (the step is power-bound), so the smaller scratch stays
   if (max_tiles >= 296) max_tiles = (max_tiles / 296) * 296;
   else if (max_tiles >= 148) max_tiles = 148;
   max_tiles = std::min<int64_t>(max_tiles, 296 * 4);
+  if (const char* e = std::getenv("TB_OZ_TILES")) max_tiles = std::max(1, std::atoi(e));  // experiment knob
   const int64_t chunk_cap = std::min<int64_t>(max_tiles * nt, ((rq.M + nt - 1) / nt) * nt);
   const int64_t tiles_cap = chunk_cap / nt;
   // row-block groups per candidate tile: ~4 row-blocks per CTA amortise the CTA prologue while the co-resident CTAs still
