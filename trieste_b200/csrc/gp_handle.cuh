@@ -89,6 +89,7 @@ struct tb_gp {
   int64_t kinv_dense_N = 0;      // update it by rank m (tb_gp_append_data) instead of rebuilding it in O(N^3)
   tb::DevBuf dKinvSpare;
   tb::DevBuf sKs2, sMean2, sPartial2;  // second scratch slot of the pipelined driver
+  tb::DevBuf sMeanPart;                // per-split mean partials of the k-split K* generation (few candidate tiles)
   cudaStream_t stream2 = nullptr;      // K* digit generation stream (overlaps the digit GEMM)
   cudaEvent_t evK[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr};
   bool oz_valid = false;

@@ -334,20 +334,24 @@ qei_cross_kernel(const double* __restrict__ Xc, const double* __restrict__ inv_l
 // ------------------------------------------------------------------------------------------------
 // K1g: gradient assembly.  grad[t][d] = sum_k dk/dr2(k,t) * 2 (x~_t,d - x~_k,d) / l_d *
 //                                       (c_mu[t] alpha[k] - 2 c_var[t] V[k,t])
-//   with V = K^-1 k* = Linv^T (Linv k*) (plain layout [t][ldv]).  One warp per candidate.
+//   with V = K^-1 k* = Linv^T (Linv k*) (plain layout [t][ldv]).  WPC warps per candidate: 1 (one warp walks all N training
+//   rows) or 8 (the CTA's warps take interleaved 32-row slices and are summed in warp order through shared memory — small
+//   batches, e.g. the late rounds of the multi-start optimiser, where one warp per candidate leaves most SMs idle).
 // ------------------------------------------------------------------------------------------------
-template <int KIND, int DP>
+template <int KIND, int DP, int WPC>
 __global__ void __launch_bounds__(256)
 grad_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha, const double* __restrict__ Xc,
             const double* __restrict__ inv_ls, int N, int D, int64_t Mc, const double* __restrict__ Vplain,
             int64_t ldv, const double* __restrict__ cmu, const double* __restrict__ cvar, double variance,
             const __grid_constant__ fm::Consts fc, double* __restrict__ grad) {
+  static_assert(WPC == 1 || WPC == 8, "one warp or one CTA per candidate");
   __shared__ double exp_tab[64];  // 2^(j/64) for the branch-free exp of fastmath.cuh
+  __shared__ double red[WPC == 8 ? 8 * DP : 1];
   if (threadIdx.x < 64) exp_tab[threadIdx.x] = fm::EXP2_TABLE_DEV[threadIdx.x];
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= Mc) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t = WPC == 8 ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (t >= Mc) return;  // WPC == 8: the whole CTA returns together
   double xc[DP], g[DP];
 #pragma unroll
   for (int d = 0; d < DP; ++d) {
@@ -356,7 +360,7 @@ grad_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha, con
   }
   const double cm = cmu[t], cv = -2.0 * cvar[t];
   const double* v = Vplain + t * ldv;
-  for (int k = lane; k < N; k += 32) {
+  for (int k = (WPC == 8 ? warp * 32 : 0) + lane; k < N; k += 32 * WPC) {
     const double* xr = Xs + (int64_t)k * DP;
     double diff[DP], r2 = 0.0;
 #pragma unroll
@@ -376,7 +380,20 @@ grad_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha, con
     double s = g[d];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0 && d < D) grad[t * D + d] = s * inv_ls[d];
+    if (WPC == 8) {
+      if (lane == 0) red[warp * DP + d] = s;
+    } else if (lane == 0 && d < D) {
+      grad[t * D + d] = s * inv_ls[d];
+    }
+  }
+  if (WPC == 8) {
+    __syncthreads();
+    if (threadIdx.x < D) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w * DP + threadIdx.x];
+      grad[t * D + threadIdx.x] = s * inv_ls[threadIdx.x];
+    }
   }
 }
 

@@ -159,9 +159,23 @@ static int launch_kstar_s(tb_gp* gp, cudaStream_t st, const double* Xc_dev, int6
   const double* X2 = gp->dX2.as<double>();
   constexpr int TH = oz5::KGEN_WARPS * 32;
   const unsigned ctas = (unsigned)(((int64_t)tiles * (oz5::Geo<S>::NT / 8) + oz5::KGEN_WARPS - 1) / oz5::KGEN_WARPS);
+  // few tiles (the late rounds of the multi-start optimiser, small predict calls): split the training rows over blockIdx.y so
+  // that ~4 CTAs per SM exist; each split covers >= 2 stages
+  int ksplit = 1, kc_per = nst;
+  if (ctas < 148 && nst >= 4) {
+    ksplit = std::min<int>(nst / 2, (int)((592 + ctas - 1) / ctas));
+    kc_per = (nst + ksplit - 1) / ksplit;
+    ksplit = (nst + kc_per - 1) / kc_per;
+  }
+  const int64_t mstride = (int64_t)tiles * oz5::Geo<S>::NT;
+  double* mean_dst = mean;
+  if (ksplit > 1) {
+    TB_TRY(gp->sMeanPart.reserve(sizeof(double) * (size_t)ksplit * mstride));
+    mean_dst = gp->sMeanPart.as<double>();
+  }
 #define TB_KD(KIND, DPV)                                                                                                            \
-  oz5::kstar_digits_kernel<KIND, DPV, S><<<ctas, TH, 0, st>>>(Xs, X2, al, Xc_dev, il, N, nst, D, mc, var, inv_b, dig_c, mc0, fm::Consts(), \
-                                                              tiles, BS, mean)
+  oz5::kstar_digits_kernel<KIND, DPV, S><<<dim3(ctas, ksplit), TH, 0, st>>>(Xs, X2, al, Xc_dev, il, N, nst, D, mc, var, inv_b, dig_c, mc0, \
+                                                                            fm::Consts(), tiles, kc_per, BS, mean_dst)
 #define TB_KD_DP(KIND)                 \
   switch (gp->DP) {                    \
     case 2: TB_KD(KIND, 2); break;     \
@@ -184,6 +198,10 @@ static int launch_kstar_s(tb_gp* gp, cudaStream_t st, const double* Xc_dev, int6
 #undef TB_KD_DP
 #undef TB_KD
   TB_LAUNCHED();
+  if (ksplit > 1) {
+    oz5::mean_reduce_kernel<<<(unsigned)((mstride + 255) / 256), 256, 0, st>>>(mean_dst, ksplit, mstride, mc0, mean);
+    TB_LAUNCHED();
+  }
   TB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(KGEN_WARPS * 32, DP <= 12 ? 4 : 3)  // 64 regi
 kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ X2, const double* __restrict__ alpha,
                     const double* __restrict__ Xc, const double* __restrict__ inv_ls, int N, int nst, int D, int64_t M, double variance,
                     double inv_bscale_2p, double dig_c, double mean_const, const __grid_constant__ fm::Consts fc, int ntiles,
-                    int8_t* __restrict__ BS, double* __restrict__ mean_out) {
+                    int kc_per, int8_t* __restrict__ BS, double* __restrict__ mean_out) {
   constexpr int NT = Geo<S>::NT, BTILE = NT * KST, TH = KGEN_WARPS * 32, WPT = NT / 8;  // WPT: warps per candidate tile
   // No masking of k >= N or of candidates t >= M is needed: training rows beyond N are zero-padded (their kernel values are
   // finite), alpha is zero there and so are all digits of Linv's columns k >= N, so those K* digits never reach a result;
@@ -278,15 +278,18 @@ kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ X2
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  stage_load(0, 0);
+  // k-split (small candidate counts: a tile is 1.5 - 2 CTAs, far too few to fill 148 SMs): blockIdx.y takes the stages
+  // [kc0, kc1) and writes its share of the mean to mean_out[blockIdx.y][ntiles NT] (summed in fixed order by mean_reduce_kernel)
+  const int kc0 = (int)blockIdx.y * kc_per, kc1 = min(nst, kc0 + kc_per);
+  stage_load(kc0, 0);
   // digit extraction without a conversion: v = rint(k inv) - c rides in the low mantissa bits of
   //   fma(k, inv, dig_c),  dig_c = 1.5 2^52 + 0x80..80 - c,  c = the INTEGER nearest to h inv (host: the centre actually
   //   subtracted is h_eff = c / inv, and the epilogue's row constant uses the same h_eff, so no bias is introduced);
   // the int8 digits are the low S bytes XOR 0x80 (digit_bytes, folded)
   double macc = 0.0;
-  for (int kc = 0; kc < nst; ++kc) {
-    const int buf = kc & 1;
-    if (kc + 1 < nst) {
+  for (int kc = kc0; kc < kc1; ++kc) {
+    const int buf = (kc - kc0) & 1;
+    if (kc + 1 < kc1) {
       stage_load(kc + 1, buf ^ 1);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
@@ -335,7 +338,18 @@ kstar_digits_kernel(const double* __restrict__ Xs, const double* __restrict__ X2
   }
   macc += __shfl_xor_sync(0xffffffffu, macc, 8);
   macc += __shfl_xor_sync(0xffffffffu, macc, 16);
-  if (ch == 0 && tile_id < ntiles) mean_out[tile_id * NT + t_local] = macc + mean_const;
+  if (ch == 0 && tile_id < ntiles)
+    mean_out[(int64_t)blockIdx.y * ntiles * NT + tile_id * NT + t_local] = gridDim.y == 1 ? macc + mean_const : macc;
+}
+
+// mean[t] = mean_const + Σ_s part[s][t] (fixed order: results do not depend on the scheduling of the k-split CTAs)
+__global__ void mean_reduce_kernel(const double* __restrict__ part, int ksplit, int64_t stride, double mean_const,
+                                   double* __restrict__ mean_out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= stride) return;
+  double s = 0.0;
+  for (int i = 0; i < ksplit; ++i) s += part[(int64_t)i * stride + t];
+  mean_out[t] = s + mean_const;
 }
 
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {

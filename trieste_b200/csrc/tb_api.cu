@@ -4,6 +4,7 @@
 #include "kernels_extra.cuh"
 #include "ozaki.cuh"
 #include "oz5_api.h"
+#include <chrono>
 #include "factor.cuh"
 #include "lbfgs.cuh"
 
@@ -288,7 +289,9 @@ int tb_gp_destroy(tb_gp* gp) {
   for (tb::DevBuf* b : {&gp->dX, &gp->dy, &gp->dXs, &gp->dInvLs, &gp->dAlpha, &gp->dL, &gp->dLinv,
                         &gp->dLinvP, &gp->dLinvTP, &gp->dAS, &gp->dRowScale, &gp->dKinv, &gp->dKinvS, &gp->dKinvScale, &gp->dDinv, &gp->sKs2, &gp->sMean2, &gp->sPartial2, &gp->dWork, &gp->dInfo, &gp->sKs, &gp->sPartial, &gp->sMean,
                         &gp->sVals, &gp->sVar, &gp->sXc, &gp->sBlkBest, &gp->sBlkIdx, &gp->sRun,
-                        &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc, &gp->dMes, &gp->dXspare, &gp->dyspare, &gp->dLspare, &gp->dLinvSpare})
+                        &gp->sA, &gp->sV, &gp->sGrad, &gp->sMisc, &gp->dMes, &gp->dXspare, &gp->dyspare, &gp->dLspare, &gp->dLinvSpare,
+                        &gp->dAS5, &gp->dRowScale5, &gp->dRowSum5, &gp->dX2, &gp->dKinvS5, &gp->dKinvScale5, &gp->dKinvSum5,
+                        &gp->dKinvSpare, &gp->sMeanPart})
     b->release();
   for (auto& ev : gp->prof_events) {
     cudaEventDestroy(ev.first);
@@ -749,7 +752,8 @@ static int ensure_upper_panels(tb_gp* gp) {
 
 template <int KIND>
 static void launch_grad_dp(tb_gp* gp, const double* xc, int64_t mc, double* grad_dev) {
-  const int blocks = (int)((mc + 7) / 8);
+  const bool wide = mc <= 2048;  // one CTA (8 warps) per candidate when one warp each would leave SMs idle
+  const int blocks = wide ? (int)mc : (int)((mc + 7) / 8);
   const double* Xs = gp->dXs.as<double>();
   const double* al = gp->dAlpha.as<double>();
   const double* il = gp->dInvLs.as<double>();
@@ -757,8 +761,13 @@ static void launch_grad_dp(tb_gp* gp, const double* xc, int64_t mc, double* grad
   const int64_t ldv = (int64_t)gp->NB * BM;
   const double* cmu = gp->sMisc.as<double>();
   const double* cvar = cmu + mc;
-#define TB_GRAD(DPV) \
-  grad_kernel<KIND, DPV><<<blocks, 256, 0, gp->stream>>>(Xs, al, xc, il, (int)gp->N, gp->D, mc, V, ldv, cmu, cvar, gp->variance, fm::Consts(), grad_dev)
+#define TB_GRAD(DPV)                                                                                                                     \
+  if (wide)                                                                                                                              \
+    grad_kernel<KIND, DPV, 8><<<blocks, 256, 0, gp->stream>>>(Xs, al, xc, il, (int)gp->N, gp->D, mc, V, ldv, cmu, cvar, gp->variance,     \
+                                                              fm::Consts(), grad_dev);                                                   \
+  else                                                                                                                                   \
+    grad_kernel<KIND, DPV, 1><<<blocks, 256, 0, gp->stream>>>(Xs, al, xc, il, (int)gp->N, gp->D, mc, V, ldv, cmu, cvar, gp->variance,     \
+                                                              fm::Consts(), grad_dev)
   switch (gp->DP) {
     case 2: TB_GRAD(2); break;
     case 4: TB_GRAD(4); break;
@@ -2725,7 +2734,11 @@ int tb_acq_maximize(tb_gp* gp, int acq, double param, const double* lower, const
   TB_TRY(compact());
   // every problem ends after at most maxiter accepted steps of at most maxls trials each
   const int64_t max_rounds = (int64_t)maxiter * (int64_t)maxls + 2;
+  const bool trace = std::getenv("TB_LBFGS_TRACE") != nullptr;  // per-round (active starts, milliseconds) on stderr
+  std::vector<std::pair<int, double>> trace_rows;
   for (int64_t round = 0; n_active > 0 && round < max_rounds; ++round) {
+    const auto t_round = std::chrono::steady_clock::now();
+    const int n_round = n_active;
     tb::EvalRequest rq;
     rq.acq = acq;
     rq.param = param;
@@ -2738,6 +2751,14 @@ int tb_acq_maximize(tb_gp* gp, int acq, double param, const double* lower, const
                                                                              bval.as<double>(), bgrad.as<double>(), dlo, dup);
     TB_LAUNCHED();
     TB_TRY(compact());
+    if (trace) trace_rows.emplace_back(n_round, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_round).count());
+  }
+  if (trace) {
+    double total = 0.0;
+    for (auto& r : trace_rows) total += r.second;
+    std::fprintf(stderr, "[tb_acq_maximize] P=%lld rounds=%zu total=%.2f ms:", (long long)P, trace_rows.size(), total);
+    for (auto& r : trace_rows) std::fprintf(stderr, " %d:%.2f", r.first, r.second);
+    std::fprintf(stderr, "\n");
   }
   TB_TRY(bres.reserve((8 + 4 + 8) * (size_t)P));
   double* rf = bres.as<double>();
