@@ -68,7 +68,7 @@ def allgather_best(value, global_index, point: Optional[np.ndarray] = None, grou
         mine = torch.as_tensor(payload, device=device)
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine, group=group)
-        rows = np.stack([g.cpu().numpy() for g in gathered])  # [world, B, 2 + D]
+        rows = torch.stack(gathered).cpu().numpy()  # [world, B, 2 + D]: one device-to-host copy
         bv, bi = np.empty(B), np.empty(B, dtype=np.int64)
         bp = None if not D else np.empty((B, D))
         for b in range(B):
@@ -80,6 +80,16 @@ def allgather_best(value, global_index, point: Optional[np.ndarray] = None, grou
     if scalar:
         return float(bv[0]), int(bi[0]), None if bp is None else bp[0]
     return bv, bi, bp
+
+
+def _gather_rows(points, indices) -> np.ndarray:
+    """points[indices] as a host array — ONE indexed gather + one device-to-host copy for a torch.cuda tensor."""
+    idx = np.asarray(indices, dtype=np.int64).reshape(-1)
+    if hasattr(points, "detach"):
+        import torch
+
+        return points[torch.as_tensor(idx, device=points.device)].detach().cpu().numpy()
+    return np.asarray(points)[idx]
 
 
 def _world_rank(group):
@@ -120,7 +130,7 @@ def sharded_thompson_argmin_local(trajectory, local_points, global_offset: int, 
         mv, mi = trajectory.argmin_over(local_points)
         B = len(mv)
         vals, gidx = -np.asarray(mv, dtype=np.float64), global_offset + np.asarray(mi, dtype=np.int64)
-        pts = np.stack([_to_host(local_points[int(i)]) for i in mi])
+        pts = _gather_rows(local_points, mi)
     else:
         B = int(getattr(trajectory, "_batch_size", 1) or 1)
         vals, gidx, pts = np.full(B, -np.inf), np.full(B, -1, dtype=np.int64), np.zeros((B, D))
