@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "trieste_b200", "libtrieste_b200.so")
 WANT = ["oz5::trigemm_kernel", "oz5::kstar_digits_kernel<3, 10, 5>", "oz::trigemm_i8_kernel", "tb::trigemm_kernel<false, 0>",
-        "tb::tail_kernel", "rff_eval_kernel<6, 8>", "joint_kernel<3, 1>", "lbfgs_step_kernel", "kdot_kernel<3, 6, 4>", "grad_kernel<3, 10>",
+        "tb::tail_kernel", "rff_eval_kernel<6, 8>", "joint_kernel<3, 1>", "lbfgs_step_kernel", "kdot_kernel<3, 6, 4>", "grad_kernel<3, 10, 1>", "grad_kernel<3, 10, 8>",
         "fac::chol_syrk_kernel", "fac::kinv_kernel"]
 KEY = ["UTCIMMA", "UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "DMMA", "HMMA", "IMMA", "DFMA", "DADD", "DMUL", "MUFU", "F2F", "I2F", "F2I",
        "LDS", "STS", "LDG", "STG", "LDGSTS", "SHFL", "BAR", "UMOV", "PRMT", "LOP3"]
