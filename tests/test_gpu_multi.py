@@ -21,7 +21,8 @@ def _worker(rank, world, port, q):
         import trieste_b200 as tb
         from oracle import gp_oracle as o  # only for the objective / data generator (checker side)
         from trieste_b200.acquisition import ExpectedImprovement, LogExpectedImprovement
-        from trieste_b200.parallel import sharded_argmax, sharded_multistart, sharded_thompson_argmin
+        from trieste_b200.parallel import sharded_argmax, sharded_multistart, sharded_thompson_argmin, sharded_topk
+        from trieste_b200.sampler import top_k
         from trieste_b200.sampler import RandomFourierFeatureTrajectorySampler
 
         om = o.synthetic_model(o.hartmann_6, 512, 6)
@@ -49,8 +50,12 @@ def _worker(rank, world, port, q):
 
         ms_pt, ms_v, ms_i = sharded_multistart(optimise, starts)
         xs_all, f_all = optimise(starts)
+        # running top-k of generate_initial_points, sharded: local tb_topk + one all-gather of k tuples per rank
+        tk_pts, tk_v, tk_i = sharded_topk(fn, pts, 16)
+        tv1, ti1 = top_k(np.ascontiguousarray(np.asarray(fn(pts[:, None, :])).reshape(-1)), 16)
         q.put((rank, int(bi), float(bv), pt.tolist(), int(idx1), float(val1), tidx.tolist(), tvals.tolist(), mi1.tolist(), mv1.tolist(),
-               int(ms_i), float(ms_v), int(np.argmax(f_all)), float(f_all.max())))
+               int(ms_i), float(ms_v), int(np.argmax(f_all)), float(f_all.max()),
+               tk_i.tolist(), tk_v.tolist(), tk_pts.tolist(), np.asarray(ti1).tolist(), np.asarray(tv1).tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -73,7 +78,9 @@ def test_sharded_helpers_over_nccl_world2():
         p.join(timeout=120)
         assert p.exitcode == 0
     pts = np.random.default_rng(5).uniform(size=(200_001, 6))
-    for (rank, bi, bv, pt, idx1, val1, tidx, tvals, mi1, mv1, ms_i, ms_v, best_i, best_v) in res:
+    for (rank, bi, bv, pt, idx1, val1, tidx, tvals, mi1, mv1, ms_i, ms_v, best_i, best_v, tk_i, tk_v, tk_pts, ti1, tv1) in res:
+        assert tk_i == ti1 and tk_v == tv1  # the sharded top-k IS the single-GPU tb_topk over everything
+        np.testing.assert_allclose(tk_pts, pts[tk_i])
         assert bi == idx1 and bv == val1  # the sharded winner IS the single-GPU first-max winner
         np.testing.assert_allclose(pt[0], pts[bi])
         assert tidx == mi1

@@ -176,6 +176,64 @@ def test_merge_best_tie_and_nan_rules():
     assert merge_best([]) == (-np.inf, -1)
 
 
+def test_merge_topk_follows_tf_top_k():
+    from trieste_b200.parallel import merge_topk
+
+    v = np.array([0.5, 2.0, 2.0, np.nan, 1.0, 2.0, -np.inf])
+    i = np.array([40, 30, 7, 1, 5, -1, 9])
+    sel = merge_topk(v, i, 4)
+    assert list(i[sel]) == [7, 30, 5, 40]  # ties on the value: lower global index first; NaN and padding (-1) never selected
+    assert list(merge_topk(v, i, 100)) == list(merge_topk(v, i, 5))  # k larger than the valid count
+    assert len(merge_topk(v, i, 0)) == 0
+
+
+def _gloo_topk_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from trieste_b200.parallel import allgather_topk, shard_bounds
+
+        pts = np.random.default_rng(4).uniform(size=(301, 2))
+        vals = np.round(np.sin(7 * pts[:, 0]) + pts[:, 1], 1)  # many ties
+        lo, hi = shard_bounds(len(pts), rank, world)
+        k = 9
+        order = np.lexsort((np.arange(lo, hi), -vals[lo:hi]))[:k]  # the rank's own top-k (stands in for tb_topk)
+        bv, bi, bp = allgather_topk(vals[lo:hi][order], lo + order, pts[lo:hi][order], k)
+        # a rank with fewer than k candidates pads its payload
+        sv, si, sp = allgather_topk(vals[lo : lo + 2], np.arange(lo, lo + 2), pts[lo : lo + 2], 3)
+        q.put((rank, bv.tolist(), bi.tolist(), bp.tolist(), si.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allgather_topk_gloo_world2():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_topk_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pts = np.random.default_rng(4).uniform(size=(301, 2))
+    vals = np.round(np.sin(7 * pts[:, 0]) + pts[:, 1], 1)
+    want = np.lexsort((np.arange(301), -vals))[:9]
+    small = sorted([0, 1, 151, 152], key=lambda j: (-vals[j], j))[:3]
+    for rank, bv, bi, bp, si in res:
+        assert bi == list(want)
+        np.testing.assert_allclose(bv, vals[want])
+        np.testing.assert_allclose(bp, pts[want])
+        assert si == small
+    assert res[0][1:] == res[1][1:]
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
 

@@ -2,8 +2,8 @@
 
 The path shards embarrassingly: every rank holds a replica of the model state and owns a contiguous
 slice of the candidates (or q-batches, or L-BFGS starts).  The only exchange is ONE all-gather of a
-(value, global index, x[D]) tuple per rank; every rank then selects the same winner with the
-reference's tie rule (first maximal index, optimizer.py:149).  One process per GPU,
+(value, global index, x[D]) tuple per rank (k tuples for the running top-k of ``generate_initial_points``); every rank then
+selects the same winner(s) with the reference's tie rule (first maximal index, optimizer.py:149).  One process per GPU,
 ``torch.distributed`` (NCCL on GPUs; gloo in the CPU tests)."""
 from __future__ import annotations
 
@@ -165,3 +165,69 @@ def sharded_multistart(optimize_starts, starts, group=None):
     world, rank = _world_rank(group)
     lo, hi = shard_bounds(starts.shape[0], rank, world)
     return sharded_multistart_local(optimize_starts, starts[lo:hi], lo, group=group)
+
+
+def merge_topk(values, indices, k: int):
+    """``tf.math.top_k`` over the union of per-rank candidates: values descending, ties -> lower global index
+    (optimizer.py:321-335 keeps a running top-k with exactly this primitive).  NaN values and indices < 0 (padding of short
+    shards) are dropped.  Returns the positions (into the flattened inputs) of the winners, at most k of them."""
+    v = np.asarray(values, dtype=np.float64).reshape(-1)
+    i = np.asarray(indices, dtype=np.int64).reshape(-1)
+    keep = np.flatnonzero((i >= 0) & (v == v))
+    order = keep[np.lexsort((i[keep], -v[keep]))]  # primary: value descending; secondary: global index ascending
+    return order[: max(int(k), 0)]
+
+
+def allgather_topk(values, global_indices, points, k: int, group=None, device=None):
+    """Every rank contributes its local top-k (values [m], global indices [m], points [m, D], m <= k, any order); ONE
+    all-gather of k (2 + D)-word tuples per rank; every rank returns the same global top-k
+    (values [k'], global indices [k'], points [k', D]), k' = min(k, number of valid candidates)."""
+    import torch
+    import torch.distributed as dist
+
+    vals = np.asarray(values, dtype=np.float64).reshape(-1)
+    idxs = np.asarray(global_indices, dtype=np.int64).reshape(-1)
+    pts = np.asarray(_to_host(points), dtype=np.float64).reshape(len(vals), -1)
+    D = pts.shape[1]
+    payload = np.zeros((k, 2 + D))
+    payload[:, 1] = -1.0  # padding rows: never selected
+    m = min(k, len(vals))
+    payload[:m, 0], payload[:m, 1], payload[:m, 2:] = np.where(vals[:m] == vals[:m], vals[:m], -np.inf), idxs[:m], pts[:m]
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        mine = torch.as_tensor(payload, device=device)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=group)
+        payload = torch.stack(gathered).cpu().numpy().reshape(world * k, 2 + D)
+    sel = merge_topk(payload[:, 0], payload[:, 1].astype(np.int64), k)
+    return payload[sel, 0], payload[sel, 1].astype(np.int64), payload[sel, 2:]
+
+
+def sharded_topk_local(fn, local_points, global_offset: int, k: int, group=None):
+    """The initial-point selection of ``generate_initial_points`` (optimizer.py:247-341) over candidates sharded across
+    the ranks: the rank evaluates ``fn`` on its own shard ([m, D] -> values [m]), takes its local top-k with the native
+    ``tb_topk`` and one all-gather of k tuples per rank yields the global top-k, identical on every rank.
+    Returns (points [k, D], values [k], global indices [k])."""
+    from .sampler import top_k
+
+    m = int(local_points.shape[0])
+    if m > 0:
+        vals = fn(local_points[:, None, :])
+        vals = vals.reshape(-1)
+        tv, ti = top_k(vals, min(k, m))
+        ti_h = np.asarray(_to_host(ti), dtype=np.int64)
+        tv_h, pts = np.asarray(_to_host(tv), dtype=np.float64), _gather_rows(local_points, ti_h)
+        gi = global_offset + ti_h
+    else:
+        tv_h, gi, pts = np.zeros(0), np.zeros(0, dtype=np.int64), np.zeros((0, local_points.shape[1]))
+    bv, bi, bp = allgather_topk(tv_h, gi, pts, k, group=group)
+    return bp, bv, bi
+
+
+def sharded_topk(fn, points, k: int, group=None):
+    """As above with ``points`` [M, D] identical on every rank (sliced here)."""
+    world, rank = _world_rank(group)
+    lo, hi = shard_bounds(points.shape[0], rank, world)
+    return sharded_topk_local(fn, points[lo:hi], lo, k, group=group)
