@@ -52,7 +52,7 @@ def _worker(rank, world, port, q):
         xs_all, f_all = optimise(starts)
         # running top-k of generate_initial_points, sharded: local tb_topk + one all-gather of k tuples per rank
         tk_pts, tk_v, tk_i = sharded_topk(fn, pts, 16)
-        tv1, ti1 = top_k(np.ascontiguousarray(np.asarray(fn(pts[:, None, :])).reshape(-1)), 16)
+        tv1, ti1 = top_k(np.ascontiguousarray(np.asarray(fn(pts[:, None, :])).reshape(-1)), 16, device=rank)
         q.put((rank, int(bi), float(bv), pt.tolist(), int(idx1), float(val1), tidx.tolist(), tvals.tolist(), mi1.tolist(), mv1.tolist(),
                int(ms_i), float(ms_v), int(np.argmax(f_all)), float(f_all.max()),
                tk_i.tolist(), tk_v.tolist(), tk_pts.tolist(), np.asarray(ti1).tolist(), np.asarray(tv1).tolist()))

@@ -97,25 +97,3 @@ def test_int8_engine_ei_and_argmax():
     # gradients fall back to the fp64 engine transparently
     val, grad = fn.value_and_gradient(Xq[:100, None, :])
     np.testing.assert_allclose(val, ei[:100], rtol=1e-6, atol=1e-15)
-
-
-def test_small_batches_take_the_split_kernels_and_agree_with_large_batches():
-    """Few candidate tiles: the K* digit generation splits the training rows over CTAs (fixed-order mean reduction) and the
-    gradient assembly runs one CTA per candidate; the same points inside a large batch take the unsplit kernels.  Both are
-    the same arithmetic up to the summation order of the mean / the gradient sums."""
-    from trieste_b200.acquisition import expected_improvement
-
-    om, nm = model_pair(o.ackley, 2048, 10)
-    fn = expected_improvement(nm, float(om.y.min()))
-    Xbig = candidates(20_000, 10, seed=5)  # > 148 K* CTAs, > 2048 candidates: unsplit kernels
-    vb, gb = fn.value_and_gradient(Xbig[:, None, :])
-    mb, sb = nm.predict(Xbig)
-    for m in (1, 7, 96, 130):
-        vs, gs = fn.value_and_gradient(Xbig[:m, None, :])
-        ms, ss = nm.predict(Xbig[:m])
-        np.testing.assert_allclose(ms, mb[:m], rtol=1e-12, atol=1e-13)
-        np.testing.assert_allclose(ss, sb[:m], rtol=0, atol=1e-13 * om.variance)  # identical digit GEMM
-        np.testing.assert_allclose(vs, vb[:m], rtol=1e-9, atol=1e-14)
-        np.testing.assert_allclose(gs, gb[:m], rtol=1e-9, atol=1e-12)
-    omean, ovar = o.predict_batched(om, Xbig[:130])
-    np.testing.assert_allclose(mb[:130], omean, rtol=1e-9, atol=1e-9 * np.sqrt(om.variance))

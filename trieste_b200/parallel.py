@@ -210,19 +210,26 @@ def sharded_topk_local(fn, local_points, global_offset: int, k: int, group=None)
     the ranks: the rank evaluates ``fn`` on its own shard ([m, D] -> values [m]), takes its local top-k with the native
     ``tb_topk`` and one all-gather of k tuples per rank yields the global top-k, identical on every rank.
     Returns (points [k, D], values [k], global indices [k])."""
+    import torch
+
     from .sampler import top_k
 
+    # the rank's own GPU, read before any native call: it sorts the shard's values and carries the all-gather
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else None
     m = int(local_points.shape[0])
     if m > 0:
         vals = fn(local_points[:, None, :])
         vals = vals.reshape(-1)
-        tv, ti = top_k(vals, min(k, m))
+        tv, ti = top_k(vals, min(k, m), device=dev)
         ti_h = np.asarray(_to_host(ti), dtype=np.int64)
         tv_h, pts = np.asarray(_to_host(tv), dtype=np.float64), _gather_rows(local_points, ti_h)
         gi = global_offset + ti_h
     else:
         tv_h, gi, pts = np.zeros(0), np.zeros(0, dtype=np.int64), np.zeros((0, local_points.shape[1]))
-    bv, bi, bp = allgather_topk(tv_h, gi, pts, k, group=group)
+    import torch.distributed as dist
+
+    nccl = dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl"
+    bv, bi, bp = allgather_topk(tv_h, gi, pts, k, group=group, device=torch.device("cuda", dev) if nccl and dev is not None else None)
     return bp, bv, bi
 
 

@@ -160,9 +160,10 @@ class BatchReparametrizationSampler:
 # ---------------------------------------------------------------------------------------------------
 # Random Fourier features (sampler.py:452-591, 741-806, 858-953)
 # ---------------------------------------------------------------------------------------------------
-def top_k(values, k: int, device: int = 0):
+def top_k(values, k: int, device: Optional[int] = None):
     """tf.math.top_k over a 1-D score vector (values desc, ties -> lower index): returns
-    (top_values [k], top_indices [k]); NumPy in -> NumPy out, torch.cuda in -> torch.cuda out."""
+    (top_values [k], top_indices [k]); NumPy in -> NumPy out, torch.cuda in -> torch.cuda out.  ``device``: the GPU that sorts a
+    host vector — default: the process's current CUDA device (one process per GPU: the rank's own)."""
     v, pv = _lib.as_f64_contiguous(values)
     if v.ndim != 1:
         raise ValueError(f"values must be 1-D, got shape {tuple(v.shape)}")
@@ -174,6 +175,10 @@ def top_k(values, k: int, device: int = 0):
     ti, pti = _lib.empty_like_kind(v, (k,), dtype=np.int64)
     if _lib.is_torch(v):
         device = v.device.index or 0
+    elif device is None:
+        import torch
+
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
     _lib.check(_lib.lib().tb_topk(device, _lib.TB_F64, pv, M, k, ptv, C.cast(pti, C.POINTER(C.c_int64))))
     return tv, ti
 
