@@ -42,3 +42,37 @@ def test_fails_loudly_without_gpu(native_lib):
     spec = tb.GPRSpec((np.zeros((3, 2)), np.zeros((3, 1))), tb.Matern52(1.0, [1.0, 1.0]), tb.Constant(0.0), 0.1)
     with pytest.raises(_lib.NativeLibraryError):
         tb.GaussianProcessRegression(spec)
+
+
+def test_product_path_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under trieste_b200/ or integration/ may import, open or execute anything under
+    oracle/ (only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference legs do, as the checker)."""
+    import ast
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for top in ("trieste_b200", "integration"):
+        for dirpath, _, files in os.walk(os.path.join(root, top)):
+            for f in files:
+                path = os.path.join(dirpath, f)
+                if f.endswith(".py"):
+                    tree = ast.parse(open(path).read())
+                    for node in ast.walk(tree):
+                        names = []
+                        if isinstance(node, ast.Import):
+                            names = [a.name for a in node.names]
+                        elif isinstance(node, ast.ImportFrom):
+                            names = [node.module or ""]
+                        if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                            offenders.append(path)
+                elif f.endswith((".cu", ".cuh", ".h", ".cpp")):
+                    if "oracle/" in open(path, errors="ignore").read():
+                        offenders.append(path)
+    assert not offenders, offenders
+    # dynamic imports: no importlib / __import__ of the oracle either
+    for dirpath, _, files in os.walk(os.path.join(root, "trieste_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import_module(\"oracle" not in src and "__import__(\"oracle" not in src, f
