@@ -4,12 +4,15 @@
 #include <cmath>
 #include <random>
 #include "../trieste_b200/csrc/fastmath.cuh"
+#ifndef FM_ITERS
+#define FM_ITERS 20000000
+#endif
 int main() {
   const tb::fm::Consts C;
   std::mt19937_64 rng(1);
   double worst_e = 0, worst_s = 0, at_e = 0, at_s = 0;
   std::uniform_real_distribution<double> u(0.0, 1.0);
-  for (int i = 0; i < 20000000; ++i) {
+  for (int i = 0; i < FM_ITERS; ++i) {
     double s;
     const double r = u(rng);
     if (i % 3 == 0) s = r * 50.0; else if (i % 3 == 1) s = std::exp(-40.0 * r); else s = 700.0 * r;
@@ -25,7 +28,7 @@ int main() {
   }
   const tb::fm::TrigConsts TC;
   double worst_c = 0, at_c = 0;
-  for (int i = 0; i < 20000000; ++i) {
+  for (int i = 0; i < FM_ITERS; ++i) {
     const double r = u(rng);
     const double a = (i % 2 ? 60.0 : 3000.0) * (2.0 * r - 1.0);
     const double got = tb::fm::cos_fast(a, TC);
