@@ -482,3 +482,38 @@ def test_qmc_base_samples_and_skip_counter():
     eps = sb._get_eps(3)
     assert eps.shape == (3, 8) and IndependentReparametrizationSampler.skip == 40
     np.testing.assert_allclose(eps.T, qmc_normal_samples(8, 3, skip=32))
+
+
+def test_rank_m_append_algebra_restated():
+    """The O(m N²) cache extension of ``tb_gp_append_data`` (csrc/factor.cuh ``append_*`` / ``kinv_grow_kernel``; the reference
+    refactorises instead, models/gpflow/models.py:171-186 -> interface.py:108-112), restated in NumPy against a from-scratch
+    factorisation: new rows of L (Y = Linv0 B), Schur-complement Cholesky of the m x m corner, new rows of Linv
+    (-L22^-1 Y^T Linv0), alpha by two triangular products, and the bordered-inverse growth of the dense K^-1."""
+    import scipy.linalg as sl
+    from oracle import gp_oracle as o
+
+    rng = np.random.default_rng(3)
+    N0, m, D = 200, 5, 4
+    X = rng.uniform(size=(N0 + m, D))
+    y = np.sin(3 * X.sum(-1))
+    var, ls, noise = 0.7, np.full(D, 0.5), 0.01
+    K = o.kernel_matrix("matern52", X, X, var, ls) + noise * np.eye(N0 + m)
+    L_full = np.linalg.cholesky(K)
+    Linv_full = sl.solve_triangular(L_full, np.eye(N0 + m), lower=True)
+    L0 = np.linalg.cholesky(K[:N0, :N0])
+    Linv0 = sl.solve_triangular(L0, np.eye(N0), lower=True)
+    B, C = K[:N0, N0:], K[N0:, N0:]
+    Y = Linv0 @ B                                   # new rows of L, transposed
+    L22 = np.linalg.cholesky(C - Y.T @ Y)           # Schur complement
+    L = np.block([[L0, np.zeros((N0, m))], [Y.T, L22]])
+    L22inv = sl.solve_triangular(L22, np.eye(m), lower=True)
+    Linv = np.block([[Linv0, np.zeros((N0, m))], [-L22inv @ Y.T @ Linv0, L22inv]])
+    np.testing.assert_allclose(L, L_full, atol=1e-12)
+    np.testing.assert_allclose(Linv, Linv_full, atol=1e-10)
+    err = y - y.mean()
+    np.testing.assert_allclose(Linv.T @ (Linv @ err), np.linalg.solve(K, err), rtol=1e-9, atol=1e-9)  # alpha
+    # dense K^-1: bordered inverse with W = K0^-1 B and the inverse Schur complement
+    Kinv0 = Linv0.T @ Linv0
+    W, Sinv = Kinv0 @ B, L22inv.T @ L22inv
+    Kinv = np.block([[Kinv0 + W @ Sinv @ W.T, -W @ Sinv], [-Sinv @ W.T, Sinv]])
+    np.testing.assert_allclose(Kinv, np.linalg.inv(K), rtol=1e-8, atol=1e-8)
