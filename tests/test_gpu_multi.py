@@ -56,6 +56,9 @@ def _worker(rank, world, port, q):
         q.put((rank, int(bi), float(bv), pt.tolist(), int(idx1), float(val1), tidx.tolist(), tvals.tolist(), mi1.tolist(), mv1.tolist(),
                int(ms_i), float(ms_v), int(np.argmax(f_all)), float(f_all.max()),
                tk_i.tolist(), tk_v.tolist(), tk_pts.tolist(), np.asarray(ti1).tolist(), np.asarray(tv1).tolist()))
+    except BaseException as exc:  # report instead of leaving the peer rank waiting in a collective until the timeout
+        q.put(("error", rank, repr(exc)))
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -73,7 +76,14 @@ def test_sharded_helpers_over_nccl_world2():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
+    res = []
+    for _ in procs:
+        item = q.get(timeout=600)
+        if item[0] == "error":  # a rank failed: its peer may be blocked in a collective — stop both, fail now
+            for p in procs:
+                p.terminate()
+            pytest.fail(f"rank {item[1]} failed: {item[2]}")
+        res.append(item)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
