@@ -76,3 +76,17 @@ def test_product_path_never_touches_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import_module(\"oracle" not in src and "__import__(\"oracle" not in src, f
+
+
+def test_every_header_symbol_is_mapped_in_integration_md():
+    """INTEGRATION.md's table names, for each C-ABI entry point, the reference interface it stands behind."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "trieste_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    symbols = sorted(set(re.findall(r"\b(tb_[a-z0-9_]+)\s*\(", header)))
+    assert len(symbols) >= 30
+    missing = [s for s in symbols if s not in doc]
+    assert not missing, missing
