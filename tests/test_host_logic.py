@@ -517,3 +517,55 @@ def test_rank_m_append_algebra_restated():
     W, Sinv = Kinv0 @ B, L22inv.T @ L22inv
     Kinv = np.block([[Kinv0 + W @ Sinv @ W.T, -W @ Sinv], [-Sinv @ W.T, Sinv]])
     np.testing.assert_allclose(Kinv, np.linalg.inv(K), rtol=1e-8, atol=1e-8)
+
+
+def test_acquisition_builders_reject_what_the_reference_rejects():
+    """Argument and data checks of the builders, as the reference's own tests state them (tests/unit/acquisition/function/
+    test_function.py: *_raises_for_empty_data, *_raises_for_invalid_*, test_entropy.py: *_raises_for_invalid_init_params);
+    every check fires before the native library is touched, so they run without a GPU."""
+    import trieste_b200 as tb
+    from trieste_b200.acquisition import (AugmentedExpectedImprovement, BatchMonteCarloExpectedImprovement, ExpectedImprovement,
+                                          LogExpectedImprovement, MinValueEntropySearch, MonteCarloExpectedImprovement,
+                                          NegativeLowerConfidenceBound, ProbabilityOfFeasibility, ProbabilityOfImprovement)
+    from trieste_b200.acquisition.function import multiple_optimism_lower_confidence_bound
+    from trieste_b200.acquisition.sampler import ThompsonSamplerFromTrajectory
+
+    class NotAModel:  # never reached by the checks below
+        pass
+
+    empty = tb.Dataset(np.zeros((0, 2)), np.zeros((0, 1)))
+    space = tb.Box([0.0, 0.0], [1.0, 1.0])
+    for builder in (ExpectedImprovement(), LogExpectedImprovement(), AugmentedExpectedImprovement(), ProbabilityOfImprovement(),
+                    MinValueEntropySearch(space), BatchMonteCarloExpectedImprovement(10), MonteCarloExpectedImprovement(10)):
+        mc = isinstance(builder, MonteCarloExpectedImprovement)
+        for data in (empty, None):  # function.py:136-137, 1113-1115 "Dataset must be populated."; MonteCarloExpectedImprovement
+            # checks the model's reparam_sampler first, as the reference does (function.py:825-829), also a ValueError
+            with pytest.raises(ValueError, match="reparam_sampler" if mc else "populated"):
+                builder.prepare_acquisition_function(NotAModel(), dataset=data)
+            with pytest.raises(ValueError):
+                builder.update_acquisition_function(object(), NotAModel(), dataset=data)
+    with pytest.raises(ValueError):
+        NegativeLowerConfidenceBound(-0.1)  # function.py:346-349
+    assert "1.96" in repr(NegativeLowerConfidenceBound())
+    for bad in (0, -5):
+        with pytest.raises(ValueError):
+            BatchMonteCarloExpectedImprovement(bad)  # function.py:1088-1090
+        with pytest.raises(ValueError):
+            MonteCarloExpectedImprovement(bad)
+        with pytest.raises(ValueError):
+            MinValueEntropySearch(space, num_samples=bad)  # entropy.py:96-99
+        with pytest.raises(ValueError):
+            MinValueEntropySearch(space, grid_size=bad)
+    with pytest.raises(ValueError):
+        BatchMonteCarloExpectedImprovement(10, jitter=-1e-6)  # function.py:1092-1094
+    with pytest.raises(ValueError):
+        MonteCarloExpectedImprovement(10, jitter=-1e-6)
+    with pytest.raises(ValueError):
+        MinValueEntropySearch(space, min_value_sampler=ThompsonSamplerFromTrajectory(sample_min_value=False))  # entropy.py:113-118
+    with pytest.raises(ValueError):
+        ProbabilityOfFeasibility(np.array([0.5, 0.6]))  # threshold must be a scalar, function.py:447
+    with pytest.raises(ValueError):
+        multiple_optimism_lower_confidence_bound(NotAModel(), 0)  # search_space_dim must be positive, function.py:1872
+    # a native function is required: the fused kernels have no generic-model path and say so
+    with pytest.raises(ValueError, match="GaussianProcessRegression"):
+        ExpectedImprovement().prepare_acquisition_function(NotAModel(), dataset=tb.Dataset(np.zeros((3, 2)), np.zeros((3, 1))))

@@ -202,6 +202,7 @@ def lower_confidence_bound(model, beta: float):
 def _eta_from_model(model, dataset: Dataset, search_space=None) -> float:
     """function.py:133-149: eta = min over the FEASIBLE training inputs of the posterior mean; with a constrained search
     space only the query points that satisfy the constraints count, and if none does eta = max of the mean."""
+    _require_native(model)
     mean, _ = model.predict(np.asarray(dataset.query_points))
     mean = np.asarray(_to_host(mean))
     if search_space is not None and getattr(search_space, "has_constraints", False):
