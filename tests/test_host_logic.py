@@ -569,3 +569,34 @@ def test_acquisition_builders_reject_what_the_reference_rejects():
     # a native function is required: the fused kernels have no generic-model path and say so
     with pytest.raises(ValueError, match="GaussianProcessRegression"):
         ExpectedImprovement().prepare_acquisition_function(NotAModel(), dataset=tb.Dataset(np.zeros((3, 2)), np.zeros((3, 1))))
+
+
+def test_optimizer_factories_reject_what_the_reference_rejects():
+    """tests/unit/acquisition/test_optimizer.py: test_generate_continuous_optimizer_raises_with_invalid_init_params,
+    test_generate_random_search_optimizer_raises_with_invalid_sample_size, test_batchify_*_raises_with_invalid_batch_size,
+    test_sample_from_space_raises (optimizer.py:215-221, 386-404, 914-916, 956-958, 984-986)."""
+    from trieste_b200.acquisition.optimizer import (batchify_joint, batchify_vectorize, generate_continuous_optimizer,
+                                                    generate_random_search_optimizer, sample_from_space)
+
+    for kwargs in (dict(num_initial_samples=0), dict(num_initial_samples=-5), dict(num_optimization_runs=0),
+                   dict(num_optimization_runs=-1), dict(num_initial_samples=5, num_optimization_runs=6), dict(num_recovery_runs=-1)):
+        with pytest.raises(ValueError):
+            generate_continuous_optimizer(**kwargs)
+    generate_continuous_optimizer(num_recovery_runs=0)  # zero recovery runs is allowed
+    for bad in (0, -3):
+        with pytest.raises(ValueError):
+            generate_random_search_optimizer(bad)
+        with pytest.raises(ValueError):
+            sample_from_space(bad)
+        with pytest.raises(ValueError):
+            sample_from_space(10, batch_size=bad)
+        with pytest.raises(ValueError):
+            batchify_joint(generate_random_search_optimizer(10), bad)
+        with pytest.raises(ValueError):
+            batchify_vectorize(generate_random_search_optimizer(10), bad)
+    space = Box([0.0], [1.0])
+    quad = lambda x: -((np.asarray(x) - 0.3) ** 2).sum(-1)  # noqa: E731  [..., 1, D] -> [..., 1]
+    with pytest.raises(ValueError):  # an already vectorised function cannot be vectorised again (optimizer.py:962-966)
+        batchify_vectorize(generate_random_search_optimizer(10), 2)(space, (quad, 2))
+    with pytest.raises(ValueError):  # joint batches of a vectorised function are not defined (optimizer.py:921-925)
+        batchify_joint(generate_random_search_optimizer(10), 2)(space, (quad, 2))
