@@ -600,3 +600,32 @@ def test_optimizer_factories_reject_what_the_reference_rejects():
         batchify_vectorize(generate_random_search_optimizer(10), 2)(space, (quad, 2))
     with pytest.raises(ValueError):  # joint batches of a vectorised function are not defined (optimizer.py:921-925)
         batchify_joint(generate_random_search_optimizer(10), 2)(space, (quad, 2))
+
+
+def test_rules_and_samplers_reject_what_the_reference_rejects():
+    """tests/unit/acquisition/test_rule.py (test_discrete_thompson_sampling_raises_for_invalid_init_params,
+    test_efficient_global_optimization_raises_for_no_query_points, ..._no_batch_fn_with_many_query_points) and
+    tests/unit/models/gpflow/test_sampler.py (*_sampler_raises_for_invalid_sample_size, ..._for_negative_jitter,
+    batch sampler needs predict_joint)."""
+    from trieste_b200.acquisition.sampler import ThompsonSamplerFromTrajectory
+    from trieste_b200.rule import DiscreteThompsonSampling, EfficientGlobalOptimization
+    from trieste_b200.sampler import BatchReparametrizationSampler, IndependentReparametrizationSampler
+
+    for bad in (0, -2):
+        with pytest.raises(ValueError):
+            EfficientGlobalOptimization(num_query_points=bad)  # rule.py:262-265
+        with pytest.raises(ValueError):
+            DiscreteThompsonSampling(bad, 1)  # rule.py:926-931
+        with pytest.raises(ValueError):
+            DiscreteThompsonSampling(100, bad)  # rule.py:933-938
+        with pytest.raises(ValueError):
+            IndependentReparametrizationSampler(bad, object())  # sampler.py:100-101
+        with pytest.raises(ValueError):
+            BatchReparametrizationSampler(bad, object())  # sampler.py:181-182
+    with pytest.raises(ValueError):
+        EfficientGlobalOptimization(num_query_points=3)  # no batch builder given (rule.py:267-275)
+    with pytest.raises(ValueError):  # a sampler of minimum VALUES cannot pick query points (rule.py:940-946)
+        DiscreteThompsonSampling(100, 2, thompson_sampler=ThompsonSamplerFromTrajectory(sample_min_value=True))
+    with pytest.raises(ValueError):  # sampler.py:184-188: the batch sampler needs predict_joint
+        BatchReparametrizationSampler(10, object())
+    assert "EfficientGlobalOptimization(" in repr(EfficientGlobalOptimization())
